@@ -1,0 +1,364 @@
+"""CPU restatement (numpy/scipy, float64 unless told otherwise) of the reference hot path.
+
+TEST INFRASTRUCTURE ONLY -- this module is the *checker* for the CUDA path.  Only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import it.  The product (``cca_zoo_b200``) never does.
+
+Parity status: PINNED.  Every function below is checked against the unmodified
+reference (imported through ``oracle/refshim.py``) by ``tests/test_oracle_vs_reference.py``
+in the authoring container, and against the committed fixtures in ``tests/golden``
+(made by ``oracle/make_golden.py`` from the reference itself) everywhere else.
+
+Two families of functions:
+
+* ``ref_*``  -- line-by-line restatements of the reference algorithms (tall SVD, n x n
+  GCCA matrix, eigh-based loss).  These *are* the reference's arithmetic.
+* ``cov_*``  -- the covariance-space forms the CUDA kernels implement:
+  everything is a function of the block moment matrix ``M = [X1..Xm]^T [X1..Xm]``,
+  the column sums ``s`` and ``n``.  They are validated against ``ref_*``.
+
+Reference citations are relative to /root/reference.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg
+
+# --------------------------------------------------------------------------------------
+# shared pieces
+# --------------------------------------------------------------------------------------
+
+
+def perview(value, default, m):
+    """cca_zoo/_utils/_validation.py:45-75 (perview_parameter)."""
+    if value is None:
+        return [default] * m
+    if isinstance(value, (list, tuple)):
+        if len(value) != m:
+            raise ValueError("per-view parameter has wrong length")
+        return list(value)
+    return [value] * m
+
+
+def setup_fit(views, center=True):
+    """cca_zoo/_base.py:78-102 -- means and centred copies (dtype preserved)."""
+    views = [np.asarray(v) for v in views]
+    if center:
+        means = [v.mean(axis=0) for v in views]
+        views = [v - mu for v, mu in zip(views, means)]
+    else:
+        means = [np.zeros(v.shape[1]) for v in views]
+    return views, means
+
+
+def transform(views, means, weights):
+    """cca_zoo/_base.py:108-123."""
+    return [(np.asarray(v) - mu) @ w for v, mu, w in zip(views, means, weights)]
+
+
+def pairwise_correlations(variates):
+    """cca_zoo/_base.py:153-174 on already-transformed variates."""
+    T = np.stack(variates, axis=0)
+    T = T - T.mean(axis=1, keepdims=True)
+    norms = np.sqrt((T**2).sum(axis=1, keepdims=True))
+    Tn = T / np.where(norms > 1e-12, norms, 1.0)
+    return np.einsum("isd,jsd->ijd", Tn, Tn)
+
+
+def average_pairwise_correlations(variates):
+    """cca_zoo/_base.py:176-194."""
+    corrs = pairwise_correlations(variates)
+    m = corrs.shape[0]
+    off = corrs.sum(axis=(0, 1)) - sum(corrs[i, i, :] for i in range(m))
+    return off / (m * (m - 1))
+
+
+def score(views, means, weights):
+    """cca_zoo/_base.py:140-151."""
+    return average_pairwise_correlations(transform(views, means, weights))
+
+
+# --------------------------------------------------------------------------------------
+# ref_* : the reference's own arithmetic
+# --------------------------------------------------------------------------------------
+
+
+def ref_svd_whiten(X, regularization=0.0):
+    """cca_zoo/_utils/_linalg.py:9-41."""
+    n = X.shape[0]
+    U, s, Vt = np.linalg.svd(X, full_matrices=False)
+    pos = s > 0
+    s, U, Vt = s[pos], U[:, pos], Vt[pos, :]
+    lam = s**2 / (n - 1)
+    inv_sqrt = 1.0 / np.sqrt((1.0 - regularization) * lam + regularization)
+    return U * (s * inv_sqrt), Vt.T * inv_sqrt
+
+
+def ref_gevp(A, B, k):
+    """cca_zoo/_utils/_linalg.py:44-73."""
+    p = A.shape[0]
+    kc = min(k, p)
+    if B is None:
+        w, v = scipy.linalg.eigh(A, subset_by_index=[p - kc, p - 1])
+    else:
+        w, v = scipy.linalg.eigh(A, B, subset_by_index=[p - kc, p - 1])
+    idx = np.argsort(w)[::-1]
+    return w[idx].real, v[:, idx].real
+
+
+def ref_rcca_fit(views, latent_dimensions=1, c=0.0, center=True):
+    """cca_zoo/linear/_rcca.py:69-101.  Returns (weights, means)."""
+    vs, means = setup_fit(views, center)
+    if len(vs) != 2:
+        raise ValueError("rCCA requires exactly 2 views")
+    c_ = perview(c, 0.0, 2)
+    X1, X2 = vs
+    X1w, W1 = ref_svd_whiten(X1, c_[0])
+    X2w, W2 = ref_svd_whiten(X2, c_[1])
+    k = min(latent_dimensions, X1w.shape[1], X2w.shape[1])
+    cross = X1w.T @ X2w / (X1.shape[0] - 1)
+    U, _, Vt = np.linalg.svd(cross, full_matrices=False)
+    return [W1 @ U[:, :k], W2 @ Vt[:k, :].T], means
+
+
+def ref_mcca_fit(views, latent_dimensions=1, c=0.0, eps=1e-6, center=True):
+    """cca_zoo/linear/_mcca.py:99-197 with pca=False (``_build_A`` :141-153,
+    ``_build_B`` :155-173).  ``pca=True`` gives the same weights for full-column-rank
+    views (checked against the reference in tests/test_oracle_vs_reference.py)."""
+    vs, means = setup_fit(views, center)
+    m = len(vs)
+    c_ = perview(c, 0.0, m)
+    A = np.cov(np.hstack(vs), rowvar=False)
+    A = A - scipy.linalg.block_diag(*[np.atleast_2d(np.cov(v, rowvar=False)) for v in vs])
+    A = A / m
+    blocks = [
+        (1.0 - c_[i]) * np.atleast_2d(np.cov(v, rowvar=False)) + c_[i] * np.eye(v.shape[1])
+        for i, v in enumerate(vs)
+    ]
+    B = scipy.linalg.block_diag(*blocks)
+    min_eig = np.linalg.eigvalsh(B).min()
+    if min_eig < eps:
+        B = B + (eps - min_eig) * np.eye(B.shape[0])
+    B = B / m
+    _, vecs = ref_gevp(A, B, latent_dimensions)
+    splits = np.cumsum([v.shape[1] for v in vs])
+    return np.split(vecs, splits[:-1], axis=0), means
+
+
+def ref_gcca_fit(views, latent_dimensions=1, c=0.0, view_weights=None, eps=1e-6, center=True):
+    """cca_zoo/linear/_gcca.py:80-110 (forms the n x n matrix: small n only)."""
+    vs, means = setup_fit(views, center)
+    m = len(vs)
+    n = vs[0].shape[0]
+    c_ = perview(c, 0.0, m)
+    mu = perview(view_weights, 1.0, m)
+    Q = np.zeros((n, n))
+    for v, ci, mi in zip(vs, c_, mu):
+        cov_i = (1.0 - ci) * np.atleast_2d(np.cov(v, rowvar=False)) + ci * np.eye(v.shape[1])
+        min_eig = np.linalg.eigvalsh(cov_i).min()
+        if min_eig < eps:
+            cov_i = cov_i + (eps - min_eig) * np.eye(cov_i.shape[0])
+        Q += mi * (v @ np.linalg.inv(cov_i) @ v.T)
+    _, vecs = ref_gevp(Q, None, latent_dimensions)
+    T = vecs[:, :latent_dimensions]
+    return [np.linalg.pinv(v) @ T for v in vs], means
+
+
+def ref_inv_sqrtm(A, eps=1e-5):
+    """cca_zoo/deep/objectives.py:9-21."""
+    L, V = np.linalg.eigh(A)
+    L = np.maximum(L, eps)
+    return (V / np.sqrt(L)) @ V.T
+
+
+def ref_ccaloss(z1, z2, eps=1e-5):
+    """cca_zoo/deep/objectives.py:79-102 (forward only, numpy)."""
+    n = z1.shape[0]
+    d1, d2 = z1.shape[1], z2.shape[1]
+    z1 = z1 - z1.mean(axis=0)
+    z2 = z2 - z2.mean(axis=0)
+    s11 = z1.T @ z1 / (n - 1) + eps * np.eye(d1)
+    s22 = z2.T @ z2 / (n - 1) + eps * np.eye(d2)
+    s12 = z1.T @ z2 / (n - 1)
+    t = ref_inv_sqrtm(s11, eps) @ s12 @ ref_inv_sqrtm(s22, eps)
+    ev = np.linalg.eigvalsh(t.T @ t)
+    return -np.maximum(ev, 0.0).sum()
+
+
+def ref_mccaloss(zs, eps=1e-5):
+    """cca_zoo/deep/objectives.py:138-153."""
+    tot = 0.0
+    for i in range(len(zs)):
+        for j in range(i + 1, len(zs)):
+            tot += ref_ccaloss(zs[i], zs[j], eps)
+    return tot
+
+
+# --------------------------------------------------------------------------------------
+# cov_* : covariance-space forms (what the CUDA kernels compute)
+# --------------------------------------------------------------------------------------
+
+
+def moments(views):
+    """Raw block moments of the hstacked views: M = X^T X (D x D), s = 1^T X (D,), n.
+
+    This is the quantity kernel K1 produces per row shard (and the quantity that is
+    all-reduced across GPUs).  np.cov(hstack) of cca_zoo/linear/_mcca.py:150-151 and the
+    per-view np.cov / SVDs elsewhere are all functions of it."""
+    X = np.hstack([np.asarray(v, dtype=np.float64) for v in views])
+    return X.T @ X, X.sum(axis=0), X.shape[0]
+
+
+def covariance_from_moments(M, s, n, center=True):
+    """C = (M - s s^T / n) / (n - 1)  (ddof=1, as np.cov / the 1/(n-1) in _rcca.py:96)."""
+    if center:
+        return (M - np.outer(s, s) / n) / (n - 1)
+    return M / (n - 1)
+
+
+def block_slices(dims):
+    off = np.concatenate([[0], np.cumsum(dims)])
+    return [slice(int(off[i]), int(off[i + 1])) for i in range(len(dims))]
+
+
+def cov_whiten(Cii, c, n_samples, rank_tol=None):
+    """Covariance form of svd_whiten (cca_zoo/_utils/_linalg.py:9-41):
+    C = V diag(lam) V^T ; W = V diag(((1-c) lam + c)^-1/2), columns by DEscending lam
+    (the SVD order).  Directions with lam <= tol*lam_max are dropped: they are the
+    covariance-space image of the reference's ``s > 0`` filter (:30)."""
+    lam, V = np.linalg.eigh(Cii)
+    lam, V = lam[::-1], V[:, ::-1]
+    d = Cii.shape[0]
+    if rank_tol is None:
+        rank_tol = max(d, n_samples) * np.finfo(Cii.dtype).eps
+    keep = lam > rank_tol * max(lam[0], 0.0)
+    keep[min(d, n_samples):] = False  # thin SVD has at most min(n, d) directions
+    lam, V = lam[keep], V[:, keep]
+    g = 1.0 / np.sqrt((1.0 - c) * lam + c)
+    return V * g, lam
+
+
+def cov_rcca_fit(C, dims, latent_dimensions=1, c=0.0, n_samples=None):
+    """Covariance form of rCCA.fit (cca_zoo/linear/_rcca.py:83-101)."""
+    if len(dims) != 2:
+        raise ValueError("rCCA requires exactly 2 views")
+    c_ = perview(c, 0.0, 2)
+    s1, s2 = block_slices(dims)
+    n_samples = n_samples if n_samples is not None else 10**9
+    W1, _ = cov_whiten(C[s1, s1], c_[0], n_samples)
+    W2, _ = cov_whiten(C[s2, s2], c_[1], n_samples)
+    k = min(latent_dimensions, W1.shape[1], W2.shape[1])
+    T = W1.T @ C[s1, s2] @ W2
+    U, sv, Vt = np.linalg.svd(T, full_matrices=False)
+    return [W1 @ U[:, :k], W2 @ Vt[:k, :].T], sv[:k]
+
+
+def cov_mcca_fit(C, dims, latent_dimensions=1, c=0.0, eps=1e-6):
+    """Covariance form of MCCA.fit (cca_zoo/linear/_mcca.py:113-135,141-173):
+    A = (C - blkdiag(C_ii))/m ; B = blkdiag((1-c_i) C_ii + c_i I)/m (+ eps floor) ;
+    top-k of A v = lam B v with v^T B v = 1, descending."""
+    m = len(dims)
+    c_ = perview(c, 0.0, m)
+    sl = block_slices(dims)
+    D = C.shape[0]
+    A = C.copy()
+    B = np.zeros_like(C)
+    for i, s in enumerate(sl):
+        A[s, s] = 0.0
+        B[s, s] = (1.0 - c_[i]) * C[s, s] + c_[i] * np.eye(dims[i])
+    min_eig = min(np.linalg.eigvalsh(B[s, s]).min() for s in sl)
+    if min_eig < eps:
+        B = B + (eps - min_eig) * np.eye(D)
+    A, B = A / m, B / m
+    lam, vecs = ref_gevp(A, B, latent_dimensions)
+    return [vecs[s, :] for s in sl], lam
+
+
+def cov_gcca_fit(C, dims, n_samples, latent_dimensions=1, c=0.0, view_weights=None, eps=1e-6):
+    """Primal (D x D) restatement of GCCA.fit (cca_zoo/linear/_gcca.py:94-109;
+    SURVEY.md §3.3).  R_i = ((1-c_i)C_ii + c_i I (+floor))^-1/2, S = blkdiag(sqrt(mu_i) R_i),
+    G = (n-1) S C S ; top-k G U = U diag(sig) ; W_i = pinv(C_ii) [C S U]_i diag(sig)^-1/2."""
+    m = len(dims)
+    c_ = perview(c, 0.0, m)
+    mu = perview(view_weights, 1.0, m)
+    sl = block_slices(dims)
+    D = C.shape[0]
+    S = np.zeros_like(C)
+    pinvs = []
+    for i, s in enumerate(sl):
+        Cii = C[s, s]
+        lam, V = np.linalg.eigh(Cii)
+        reg = (1.0 - c_[i]) * lam + c_[i]
+        if reg.min() < eps:
+            reg = reg + (eps - reg.min())
+        S[s, s] = np.sqrt(mu[i]) * (V / np.sqrt(reg)) @ V.T
+        tol = max(dims[i], n_samples) * np.finfo(C.dtype).eps * max(lam.max(), 0.0)
+        inv = np.where(lam > tol, 1.0 / np.where(lam > tol, lam, 1.0), 0.0)
+        pinvs.append((V * inv) @ V.T)
+    G = (n_samples - 1) * (S @ C @ S)
+    k = min(latent_dimensions, D, n_samples)
+    sig, U = ref_gevp(G, None, k)
+    CSU = C @ (S @ U)
+    ws = [pinvs[i] @ CSU[s, :] / np.sqrt(sig) for i, s in enumerate(sl)]
+    return ws, sig
+
+
+def cov_ccaloss(z1, z2, eps=1e-5):
+    """Closed form of CCALoss.forward valid whenever no clamp fires
+    (cca_zoo/deep/objectives.py:20,101):
+    loss = -tr(S11^-1 S12 S22^-1 S21).  Also returns the analytic gradients w.r.t. z1, z2."""
+    z1 = np.asarray(z1, dtype=np.float64)
+    z2 = np.asarray(z2, dtype=np.float64)
+    n = z1.shape[0]
+    a = z1 - z1.mean(axis=0)
+    b = z2 - z2.mean(axis=0)
+    s11 = a.T @ a / (n - 1) + eps * np.eye(a.shape[1])
+    s22 = b.T @ b / (n - 1) + eps * np.eye(b.shape[1])
+    s12 = a.T @ b / (n - 1)
+    i11 = np.linalg.inv(s11)
+    i22 = np.linalg.inv(s22)
+    P = i11 @ s12 @ i22  # d1 x d2
+    loss = -np.sum(P * s12)
+    # dL/dS12 = -2 P ; dL/dS11 = P S21 S11^-1 (sym) ; dL/dS22 = S22^-1 S21 P (sym)
+    g12 = -2.0 * P
+    g11 = P @ s12.T @ i11
+    g22 = i22 @ s12.T @ P
+    # back through S = a^T b/(n-1) and the centring (projection onto 1-perp, a no-op on
+    # already-centred cotangents because a, b are centred and the cotangents are linear in a, b)
+    ga = (a @ (g11 + g11.T) + b @ g12.T) / (n - 1)
+    gb = (b @ (g22 + g22.T) + a @ g12) / (n - 1)
+    ga -= ga.mean(axis=0)
+    gb -= gb.mean(axis=0)
+    return loss, ga, gb
+
+
+# --------------------------------------------------------------------------------------
+# comparison helpers used by the parity tests
+# --------------------------------------------------------------------------------------
+
+
+def align_signs(weights, ref_weights):
+    """Flip component signs jointly across views (a component flips in all views together)."""
+    k = ref_weights[0].shape[1]
+    out = [w.copy() for w in weights]
+    for j in range(k):
+        dot = sum(float(w[:, j] @ r[:, j]) for w, r in zip(weights, ref_weights))
+        if dot < 0:
+            for w in out:
+                w[:, j] *= -1.0
+    return out
+
+
+def max_rel_err_per_vector(weights, ref_weights):
+    ws = align_signs(weights, ref_weights)
+    errs = []
+    for w, r in zip(ws, ref_weights):
+        errs.append(np.linalg.norm(w - r, axis=0) / np.maximum(np.linalg.norm(r, axis=0), 1e-300))
+    return float(np.max(errs))
+
+
+def subspace_distance(W, Wref):
+    """|| P - Pref ||_2 between the column spans."""
+    Q, _ = np.linalg.qr(W)
+    Qr, _ = np.linalg.qr(Wref)
+    return float(np.linalg.norm(Q @ Q.T - Qr @ Qr.T, 2))

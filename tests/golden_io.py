@@ -1,0 +1,67 @@
+"""Load the committed reference outputs (tests/golden) and rebuild their seeded inputs."""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+from cca_zoo_b200.datasets import conftest_views, joint_data
+
+_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+with open(os.path.join(_DIR, "reference_outputs.json")) as _f:
+    META = json.load(_f)
+_NPZ = np.load(os.path.join(_DIR, "reference_outputs.npz"))
+
+CASES = {c["name"]: c for c in META["cases"]}
+LOSS_CASES = {c["name"]: c for c in META["loss_cases"]}
+
+
+def dataset(name, dtype="f64"):
+    kind, args = META["datasets"][name]
+    views = conftest_views(args["name"]) if kind == "conftest" else joint_data(**args)
+    if dtype == "f32":
+        views = [v.astype(np.float32) for v in views]
+    return views
+
+
+def case_inputs(name):
+    c = CASES[name]
+    return dataset(c["dataset"], c["dtype"])
+
+
+def case_outputs(name):
+    m = len(META["datasets"][CASES[name]["dataset"]][1].get("n_features", [])) or None
+    ws, mus, i = [], [], 0
+    while f"{name}/w{i}" in _NPZ:
+        ws.append(_NPZ[f"{name}/w{i}"])
+        mus.append(_NPZ[f"{name}/mean{i}"])
+        i += 1
+    return ws, mus, _NPZ[f"{name}/score"]
+
+
+def get(key):
+    return _NPZ[key]
+
+
+def loss_inputs(name):
+    """Same recipe as oracle/make_golden.py:loss_inputs (torch CPU generator)."""
+    import torch
+
+    c = LOSS_CASES[name]
+    g = torch.Generator().manual_seed(c["seed"])
+    zl = torch.randn(c["batch"], 4, generator=g, dtype=torch.float64)
+    out = []
+    for w in c["widths"]:
+        a = torch.randn(4, w, generator=g, dtype=torch.float64)
+        out.append(zl @ a + 0.5 * torch.randn(c["batch"], w, generator=g, dtype=torch.float64))
+    return out
+
+
+def loss_outputs(name):
+    grads, i = [], 0
+    while f"{name}/grad{i}" in _NPZ:
+        grads.append(_NPZ[f"{name}/grad{i}"])
+        i += 1
+    return float(_NPZ[f"{name}/loss"]), grads

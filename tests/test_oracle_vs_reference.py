@@ -1,0 +1,80 @@
+"""Pin the oracle against the LIVE reference (authoring container only: /root/reference).
+
+Skipped on the GPU box.  This is the evidence behind the "parity pinned" line in
+oracle/restatement.py: each ref_* / cov_* function against the reference estimator it restates,
+on the reference's own conftest fixtures and on JointData draws, plus the data generator.
+"""
+import numpy as np
+import pytest
+
+from oracle import refshim
+from oracle import restatement as R
+
+pytestmark = pytest.mark.reference
+
+if refshim.available():
+    refshim.install()
+    from cca_zoo.datasets import JointData
+    from cca_zoo.linear import GCCA, MCCA, rCCA
+
+from cca_zoo_b200.datasets import conftest_views, joint_data
+
+
+def _C(views, center=True):
+    M, s, n = R.moments(views)
+    return R.covariance_from_moments(M, s, n, center), n
+
+
+@pytest.mark.parametrize("c", [0.0, 0.1, [0.2, 0.7], 1.0])
+@pytest.mark.parametrize("ds", ["two_views", "correlated_views"])
+def test_rcca(ds, c):
+    v = conftest_views(ds)
+    ref = rCCA(latent_dimensions=3, c=c).fit(v)
+    w, mu = R.ref_rcca_fit(v, 3, c)
+    assert R.max_rel_err_per_vector(w, ref.weights_) < 1e-12
+    C, n = _C(v)
+    w, _ = R.cov_rcca_fit(C, [10, 8], 3, c, n)
+    assert R.max_rel_err_per_vector(w, ref.weights_) < 1e-9
+    np.testing.assert_allclose(R.score(v, mu, w), ref.score(v), rtol=1e-9)
+
+
+@pytest.mark.parametrize("c,pca", [(0.0, True), (0.0, False), (0.3, False), ([0.1, 0.2, 0.3], True)])
+def test_mcca(c, pca):
+    v = conftest_views("three_views")
+    ref = MCCA(latent_dimensions=3, c=c, pca=pca).fit(v)
+    w, _ = R.ref_mcca_fit(v, 3, c)
+    assert R.max_rel_err_per_vector(w, ref.weights_) < 1e-10
+    C, n = _C(v)
+    w, _ = R.cov_mcca_fit(C, [10, 8, 6], 3, c)
+    assert R.max_rel_err_per_vector(w, ref.weights_) < 1e-10
+
+
+@pytest.mark.parametrize("c,mu", [(0.0, None), (0.2, [1.0, 1.0, 2.0])])
+def test_gcca(c, mu):
+    v = conftest_views("three_views")
+    ref = GCCA(latent_dimensions=3, c=c, view_weights=mu).fit(v)
+    w, _ = R.ref_gcca_fit(v, 3, c, mu)
+    assert R.max_rel_err_per_vector(w, ref.weights_) < 1e-10
+    C, n = _C(v)
+    w, _ = R.cov_gcca_fit(C, [10, 8, 6], n, 3, c, mu)
+    assert R.max_rel_err_per_vector(w, ref.weights_) < 1e-9
+
+
+def test_joint_data_generator_matches_reference():
+    args = dict(n_views=3, n_samples=77, latent_dimensions=3, n_features=[5, 9, 4],
+                signal_to_noise=[0.5, 1.0, 2.0], random_state=11)
+    for a, b in zip(joint_data(**args), JointData(**args).sample()):
+        assert np.array_equal(a, b)
+
+
+def test_conftest_fixture_recipe_matches_reference_file():
+    """The fixture recipe in cca_zoo_b200.datasets must be the one in tests/conftest.py."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_conftest", "/root/reference/tests/conftest.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for name in ["two_views", "three_views", "correlated_views", "two_views_test"]:
+        ref = getattr(mod, name).__wrapped__()
+        for a, b in zip(conftest_views(name), ref):
+            assert np.array_equal(a, b)
