@@ -1,0 +1,291 @@
+// C ABI of libccab200 (see include/ccab200.h).  Thin argument checking + dispatch; no exceptions
+// leave this file.
+#include "../../include/ccab200.h"
+
+#include <cstdarg>
+#include <cstring>
+#include <exception>
+
+#include "common.cuh"
+#include "dense.cuh"
+#include "moments.cuh"
+#include "syevj.cuh"
+
+namespace ccab {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return (int)e;
+}
+}  // namespace ccab
+
+using namespace ccab;
+
+#define CCAB_TRY try {
+#define CCAB_CATCH                                 \
+  }                                                \
+  catch (const std::exception& e) {                \
+    set_error("internal exception: %s", e.what()); \
+    return -100;                                   \
+  }                                                \
+  catch (...) {                                    \
+    set_error("internal exception");               \
+    return -100;                                   \
+  }
+
+static int require_device() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice (no CUDA device: libccab200 has no CPU fallback)");
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) {
+    set_error("libccab200 is built for sm_100a only; device %d has compute capability major %d", dev, major);
+    return -10;
+  }
+  return 0;
+}
+
+extern "C" {
+
+int ccab_version(void) { return 100; }
+const char* ccab_last_error(void) { return g_err; }
+
+int64_t ccab_moments_size(int n_views, const int64_t* dims) {
+  ColumnLayout L;
+  if (make_layout(n_views, dims, &L)) return -1;
+  return (int64_t)L.Dp * L.Dp + L.Dp;
+}
+int64_t ccab_moments_padded_dim(int n_views, const int64_t* dims) {
+  ColumnLayout L;
+  if (make_layout(n_views, dims, &L)) return -1;
+  return L.Dp;
+}
+
+size_t ccab_moments_workspace_bytes(int dtype, int precision, int n_views, const int64_t* dims, int64_t n_rows) {
+  ColumnLayout L;
+  if (make_layout(n_views, dims, &L)) return 0;
+  return moments_workspace_bytes(dtype, precision, L, n_rows) + 512;
+}
+
+int ccab_moments(int dtype, int precision, int n_views, const void* const* views, const int64_t* dims,
+                 const int64_t* lds, int64_t n_rows, double* moments, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(precision >= 0 && precision <= 2, "bad precision %d", precision);
+  CCAB_CHECK_ARG(!(dtype == CCAB_F64 && precision != CCAB_PREC_EXACT),
+                 "float64 inputs support CCAB_PREC_EXACT only (tcgen05 has no f64 kind)");
+  CCAB_CHECK_ARG(views && dims && lds && moments && workspace, "null pointer argument");
+  ColumnLayout L;
+  int rc = make_layout(n_views, dims, &L);
+  if (rc) return rc;
+  for (int v = 0; v < n_views; ++v) {
+    CCAB_CHECK_ARG(views[v] != nullptr, "view %d is NULL", v);
+    CCAB_CHECK_ARG(lds[v] >= dims[v], "lds[%d] < dims[%d]", v, v);
+  }
+  rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (precision == CCAB_PREC_EXACT) {
+    if (dtype == CCAB_F32) return moments_simt<float>(L, views, lds, n_rows, moments, workspace, workspace_bytes, s);
+    return moments_simt<double>(L, views, lds, n_rows, moments, workspace, workspace_bytes, s);
+  }
+  return moments_tf32(L, views, lds, n_rows, precision == CCAB_PREC_TF32X3, moments, workspace, workspace_bytes, s);
+  CCAB_CATCH
+}
+
+int ccab_covariance(int out_dtype, int n_views, const int64_t* dims, const double* moments, double n_total,
+                    int center, void* C, int64_t ldc, void* mean, void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(out_dtype == CCAB_F32 || out_dtype == CCAB_F64, "bad dtype %d", out_dtype);
+  CCAB_CHECK_ARG(dims && moments && C, "null pointer argument");
+  ColumnLayout L;
+  int rc = make_layout(n_views, dims, &L);
+  if (rc) return rc;
+  rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (out_dtype == CCAB_F32)
+    return covariance_from_moments<float>(L, moments, n_total, center, static_cast<float*>(C), ldc,
+                                          static_cast<float*>(mean), s);
+  return covariance_from_moments<double>(L, moments, n_total, center, static_cast<double*>(C), ldc,
+                                         static_cast<double*>(mean), s);
+  CCAB_CATCH
+}
+
+size_t ccab_syevj_workspace_bytes(int dtype, int n, int batch) {
+  if (n < 1 || batch < 1) return 0;
+  return dtype == CCAB_F32 ? jacobi_workspace_bytes<float>(n, n, batch) : jacobi_workspace_bytes<double>(n, n, batch);
+}
+
+}  // extern "C"
+
+template <typename T>
+static int syevj_t(int n, int batch, const void* A, int64_t lda, int64_t batch_stride, double shift, void* evals,
+                   void* evecs_t, int64_t ldv, int* info, float* info_offdiag, void* ws, size_t wsb, cudaStream_t s) {
+  JacobiArgs<T> a;
+  memset(&a, 0, sizeof(a));
+  a.in = static_cast<const T*>(A);
+  a.ld_in = lda;
+  a.batch_stride_in = batch_stride;
+  a.colmajor_in = 1;  // symmetric: either reading order is the same matrix, this one is coalesced
+  a.m = n;
+  a.n = n;
+  a.batch = batch;
+  a.svd_mode = 0;
+  a.shift = shift;
+  a.out_vals = static_cast<T*>(evals);
+  a.vals_stride = n;
+  a.out_right = static_cast<T*>(evecs_t);
+  a.ld_right = ldv;
+  a.right_stride = (int64_t)n * ldv;
+  a.info = info;
+  a.final_offdiag = info_offdiag;
+  return jacobi_solve<T>(a, ws, wsb, s);
+}
+
+extern "C" {
+
+int ccab_syevj(int dtype, int n, int batch, const void* A, int64_t lda, int64_t batch_stride, double shift,
+               void* evals, void* evecs_t, int64_t ldv, int* info, float* info_offdiag, void* workspace,
+               size_t workspace_bytes, void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(n >= 1 && batch >= 1, "bad shape n=%d batch=%d", n, batch);
+  CCAB_CHECK_ARG(A && workspace, "null pointer argument");
+  CCAB_CHECK_ARG(lda >= n && (evecs_t == nullptr || ldv >= n), "leading dimension too small");
+  int rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CCAB_F32)
+    return syevj_t<float>(n, batch, A, lda, batch_stride, shift, evals, evecs_t, ldv, info, info_offdiag, workspace,
+                          workspace_bytes, s);
+  return syevj_t<double>(n, batch, A, lda, batch_stride, shift, evals, evecs_t, ldv, info, info_offdiag, workspace,
+                         workspace_bytes, s);
+  CCAB_CATCH
+}
+
+size_t ccab_gesvj_workspace_bytes(int dtype, int m, int n) {
+  if (n < 1 || m < 1) return 0;
+  return dtype == CCAB_F32 ? jacobi_workspace_bytes<float>(m, n, 1) : jacobi_workspace_bytes<double>(m, n, 1);
+}
+
+}  // extern "C"
+
+template <typename T>
+static int gesvj_t(int m, int n, const void* A, int64_t lda, void* sigma, void* right_t, int64_t ldr, void* left_t,
+                   int64_t ldl, int* info, float* info_offdiag, void* ws, size_t wsb, cudaStream_t s) {
+  JacobiArgs<T> a;
+  memset(&a, 0, sizeof(a));
+  a.in = static_cast<const T*>(A);
+  a.ld_in = lda;
+  a.batch_stride_in = 0;
+  a.colmajor_in = 1;
+  a.m = m;
+  a.n = n;
+  a.batch = 1;
+  a.svd_mode = 1;
+  a.out_vals = static_cast<T*>(sigma);
+  a.vals_stride = n;
+  a.out_right = static_cast<T*>(right_t);
+  a.ld_right = ldr;
+  a.out_left = static_cast<T*>(left_t);
+  a.ld_left = ldl;
+  a.info = info;
+  a.final_offdiag = info_offdiag;
+  return jacobi_solve<T>(a, ws, wsb, s);
+}
+
+extern "C" {
+
+int ccab_gesvj(int dtype, int m, int n, const void* A, int64_t lda, void* sigma, void* right_t, int64_t ldr,
+               void* left_t, int64_t ldl, int* info, float* info_offdiag, void* workspace, size_t workspace_bytes,
+               void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(m >= 1 && n >= 1, "bad shape m=%d n=%d", m, n);
+  CCAB_CHECK_ARG(A && workspace, "null pointer argument");
+  CCAB_CHECK_ARG(lda >= m, "lda < m");
+  CCAB_CHECK_ARG((right_t == nullptr || ldr >= n) && (left_t == nullptr || ldl >= m), "leading dimension too small");
+  int rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CCAB_F32)
+    return gesvj_t<float>(m, n, A, lda, sigma, right_t, ldr, left_t, ldl, info, info_offdiag, workspace,
+                          workspace_bytes, s);
+  return gesvj_t<double>(m, n, A, lda, sigma, right_t, ldr, left_t, ldl, info, info_offdiag, workspace,
+                         workspace_bytes, s);
+  CCAB_CATCH
+}
+
+int ccab_gemm(int dtype, int transa, int transb, int m, int n, int k, double alpha, const void* A, int64_t lda,
+              const void* B, int64_t ldb, double beta, void* C, int64_t ldc, void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(A && B && C, "null pointer argument");
+  int rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CCAB_F32)
+    return gemm<float>(transa, transb, m, n, k, (float)alpha, static_cast<const float*>(A), lda,
+                       static_cast<const float*>(B), ldb, (float)beta, static_cast<float*>(C), ldc, s);
+  return gemm<double>(transa, transb, m, n, k, alpha, static_cast<const double*>(A), lda,
+                      static_cast<const double*>(B), ldb, beta, static_cast<double*>(C), ldc, s);
+  CCAB_CATCH
+}
+
+int ccab_whiten_rows(int dtype, int d, const void* lam, const void* Vt, int64_t ldv, double c, double floor_add,
+                     const void* floor_dev, double scale, double rank_tol, int max_rank, void* Wt, int64_t ldw,
+                     void* g_out, int* rank_out, void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(lam && Vt && Wt, "null pointer argument");
+  CCAB_CHECK_ARG(scale > 0.0, "scale must be positive");
+  int rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CCAB_F32)
+    return whiten_rows<float>(d, static_cast<const float*>(lam), static_cast<const float*>(Vt), ldv, c, floor_add,
+                              static_cast<const float*>(floor_dev), scale, rank_tol, max_rank,
+                              static_cast<float*>(Wt), ldw, static_cast<float*>(g_out), rank_out, s);
+  return whiten_rows<double>(d, static_cast<const double*>(lam), static_cast<const double*>(Vt), ldv, c, floor_add,
+                             static_cast<const double*>(floor_dev), scale, rank_tol, max_rank,
+                             static_cast<double*>(Wt), ldw, static_cast<double*>(g_out), rank_out, s);
+  CCAB_CATCH
+}
+
+int ccab_frobenius_norm(int dtype, int m, int n, const void* A, int64_t lda, void* out, void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(A && out, "null pointer argument");
+  int rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CCAB_F32)
+    return frobenius_norm<float>(m, n, static_cast<const float*>(A), lda, static_cast<float*>(out), s);
+  return frobenius_norm<double>(m, n, static_cast<const double*>(A), lda, static_cast<double*>(out), s);
+  CCAB_CATCH
+}
+
+int ccab_debug_set(const char* key, int value) {
+  if (!key) return -1;
+  TcDebug& d = tc_debug();
+  if (!strcmp(key, "lbo_bytes")) d.lbo_bytes = value;
+  else if (!strcmp(key, "sbo_bytes")) d.sbo_bytes = value;
+  else if (!strcmp(key, "tma_dtype")) d.tma_dtype = value;
+  else if (!strcmp(key, "force_splits")) d.force_splits = value;
+  else {
+    set_error("unknown debug key %s", key);
+    return -1;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+#include "dense.cuh"
+
+namespace ccab {
+
+// 64x64 output tile, 16-deep k chunks, 256 threads, 4x4 register tile per thread.
+template <typename T, int TA, int TB>
+__global__ void __launch_bounds__(256) gemm_kernel(int m, int n, int k, T alpha, const T* __restrict__ A,
+                                                   int64_t lda, const T* __restrict__ B, int64_t ldb, T beta,
+                                                   T* __restrict__ C, int64_t ldc) {
+  constexpr int KC = 16;
+  __shared__ T As[KC][64 + 4];
+  __shared__ T Bs[KC][64 + 4];
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+
+  for (int k0 = 0; k0 < k; k0 += KC) {
+    // A tile -> As[kk][mm]
+    if (TA) {  // op(A) = A^T : stored k x m, contiguous along m
+      const int mm = threadIdx.x & 63, kk0 = threadIdx.x >> 6;
+#pragma unroll
+      for (int i = 0; i < KC / 4; ++i) {
+        const int kk = kk0 + 4 * i;
+        As[kk][mm] = (k0 + kk < k && m0 + mm < m) ? A[(size_t)(k0 + kk) * lda + m0 + mm] : T(0);
+      }
+    } else {  // stored m x k, contiguous along k
+      const int kk = threadIdx.x & 15, mm0 = threadIdx.x >> 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int mm = mm0 + 16 * i;
+        As[kk][mm] = (k0 + kk < k && m0 + mm < m) ? A[(size_t)(m0 + mm) * lda + k0 + kk] : T(0);
+      }
+    }
+    // B tile -> Bs[kk][nn]
+    if (TB) {  // op(B) = B^T : stored n x k, contiguous along k
+      const int kk = threadIdx.x & 15, nn0 = threadIdx.x >> 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int nn = nn0 + 16 * i;
+        Bs[kk][nn] = (k0 + kk < k && n0 + nn < n) ? B[(size_t)(n0 + nn) * ldb + k0 + kk] : T(0);
+      }
+    } else {  // stored k x n, contiguous along n
+      const int nn = threadIdx.x & 63, kk0 = threadIdx.x >> 6;
+#pragma unroll
+      for (int i = 0; i < KC / 4; ++i) {
+        const int kk = kk0 + 4 * i;
+        Bs[kk][nn] = (k0 + kk < k && n0 + nn < n) ? B[(size_t)(k0 + kk) * ldb + n0 + nn] : T(0);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      T a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + ty * 4 + i;
+    if (r >= m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cidx = n0 + tx * 4 + j;
+      if (cidx >= n) continue;
+      T v = alpha * acc[i][j];
+      if (beta != T(0)) v += beta * C[(size_t)r * ldc + cidx];
+      C[(size_t)r * ldc + cidx] = v;
+    }
+  }
+}
+
+template <typename T>
+int gemm(int transa, int transb, int m, int n, int k, T alpha, const T* A, int64_t lda, const T* B, int64_t ldb,
+         T beta, T* C, int64_t ldc, cudaStream_t stream) {
+  CCAB_CHECK_ARG(m >= 0 && n >= 0 && k >= 0, "negative gemm dimension");
+  if (m == 0 || n == 0) return 0;
+  dim3 grid((unsigned)ceil_div(n, 64), (unsigned)ceil_div(m, 64));
+  if (!transa && !transb) gemm_kernel<T, 0, 0><<<grid, 256, 0, stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  else if (transa && !transb) gemm_kernel<T, 1, 0><<<grid, 256, 0, stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  else if (!transa && transb) gemm_kernel<T, 0, 1><<<grid, 256, 0, stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  else gemm_kernel<T, 1, 1><<<grid, 256, 0, stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+template int gemm<float>(int, int, int, int, int, float, const float*, int64_t, const float*, int64_t, float, float*,
+                         int64_t, cudaStream_t);
+template int gemm<double>(int, int, int, int, int, double, const double*, int64_t, const double*, int64_t, double,
+                          double*, int64_t, cudaStream_t);
+
+template <typename T>
+__global__ void whiten_rows_kernel(int d, const T* __restrict__ lam, const T* __restrict__ Vt, int64_t ldv, double c,
+                                   double floor_add, const T* __restrict__ floor_dev, double scale, double rank_tol,
+                                   int max_rank, T* __restrict__ Wt, int64_t ldw, T* __restrict__ g_out,
+                                   int* __restrict__ rank_out) {
+  const int j = blockIdx.x;
+  const double l0 = fmax((double)lam[0], 0.0);
+  const double lj = (double)lam[j];
+  const bool keep = (lj > rank_tol * l0) && (j < max_rank);
+  const double fl = floor_add + (floor_dev ? (double)floor_dev[0] : 0.0);
+  const double g = keep ? 1.0 / sqrt(((1.0 - c) * lj + c + fl) * scale) : 0.0;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) Wt[(size_t)j * ldw + i] = (T)(g * (double)Vt[(size_t)j * ldv + i]);
+  if (threadIdx.x == 0) {
+    if (g_out) g_out[j] = (T)g;
+    if (rank_out && keep) atomicAdd(rank_out, 1);
+  }
+}
+
+template <typename T>
+int whiten_rows(int d, const T* lam, const T* Vt, int64_t ldv, double c, double floor_add, const T* floor_dev,
+                double scale, double rank_tol, int max_rank, T* Wt, int64_t ldw, T* g_out, int* rank_out,
+                cudaStream_t stream) {
+  CCAB_CHECK_ARG(d >= 1, "bad dimension");
+  if (rank_out) CCAB_CUDA(cudaMemsetAsync(rank_out, 0, sizeof(int), stream));
+  whiten_rows_kernel<T><<<d, 128, 0, stream>>>(d, lam, Vt, ldv, c, floor_add, floor_dev, scale, rank_tol, max_rank,
+                                               Wt, ldw, g_out, rank_out);
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+template int whiten_rows<float>(int, const float*, const float*, int64_t, double, double, const float*, double, double,
+                                int, float*, int64_t, float*, int*, cudaStream_t);
+template int whiten_rows<double>(int, const double*, const double*, int64_t, double, double, const double*, double,
+                                 double, int, double*, int64_t, double*, int*, cudaStream_t);
+
+template <typename T>
+__global__ void frobenius_kernel(int m, int n, const T* __restrict__ A, int64_t lda, T* __restrict__ out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  const size_t total = (size_t)m * n;
+  for (size_t i = threadIdx.x; i < total; i += blockDim.x) {
+    const double v = (double)A[(i / n) * lda + (i % n)];
+    acc += v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) out[0] = (T)sqrt(acc);
+  }
+}
+
+template <typename T>
+int frobenius_norm(int m, int n, const T* A, int64_t lda, T* out, cudaStream_t stream) {
+  frobenius_kernel<T><<<1, 1024, 0, stream>>>(m, n, A, lda, out);  // deterministic single-block reduction
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+template int frobenius_norm<float>(int, int, const float*, int64_t, float*, cudaStream_t);
+template int frobenius_norm<double>(int, int, const double*, int64_t, double*, cudaStream_t);
+
+}  // namespace ccab

@@ -1,0 +1,29 @@
+// Small dense glue on CUDA cores (exact fp32 / fp64 FMA): GEMM with optional transposes, whitening
+// scale of eigenvector rows, Frobenius norm.  None of these is on the roofline-critical path; they
+// connect K1 (moments) to K3/K4 (Jacobi) at sizes D <= a few thousand.
+#pragma once
+#include "common.cuh"
+
+namespace ccab {
+
+// C (m x n, row-major, ldc) = alpha * op(A) * op(B) + beta * C ; op(X) = X or X^T, row-major storage.
+template <typename T>
+int gemm(int transa, int transb, int m, int n, int k, T alpha, const T* A, int64_t lda, const T* B, int64_t ldb,
+         T beta, T* C, int64_t ldc, cudaStream_t stream);
+
+// Whitening factors from an eigendecomposition (covariance form of svd_whiten,
+// cca_zoo/_utils/_linalg.py:30-38):  for eigenpair j (descending, rows of Vt)
+//   keep_j = lam_j > rank_tol * lam_0  and  j < max_rank
+//   g_j    = keep_j ? 1 / sqrt(((1 - c) * lam_j + c + floor_add) * scale) : 0
+//   Wt[j,:] = g_j * Vt[j,:]
+// and *rank_out = #kept.  `floor_dev` (may be null) points at a device scalar added to floor_add.
+template <typename T>
+int whiten_rows(int d, const T* lam, const T* Vt, int64_t ldv, double c, double floor_add, const T* floor_dev,
+                double scale, double rank_tol, int max_rank, T* Wt, int64_t ldw, T* g_out, int* rank_out,
+                cudaStream_t stream);
+
+// out[0] = ||A||_F (m x n, row-major)
+template <typename T>
+int frobenius_norm(int m, int n, const T* A, int64_t lda, T* out, cudaStream_t stream);
+
+}  // namespace ccab

@@ -1,0 +1,701 @@
+// K1: block moments M = X^T X (+ column sums) of the hstacked views, upper block triangle only.
+//
+//   * moments_tf32_kernel : tcgen05.mma kind::tf32, both operands MN-major straight out of row-major X
+//     (TMA 128B-swizzled boxes of 32 columns x KC rows), fp32 accumulators in TMEM, warp-specialised
+//     (TMA producer / single-thread MMA issuer / 4 epilogue warps), split over the sample axis.
+//     Optional 3xTF32 (hi/lo split operands, 3 MMAs per k-step) for fp32-grade accuracy.
+//     Column sums ride on the same pipeline as one extra N=16 MMA against a block of ones.
+//   * moments_simt_kernel : exact FMA (fp32 or fp64) tile kernel for fp64 inputs and as the
+//     non-tensor reference path.
+//   * reduce / covariance kernels (K2): fixed-order sum of the split partials into a double
+//     moment buffer (the all-reduce payload), then C = (M - s s^T / n) / (n - 1).
+//
+// Replaces, in covariance form, the tall SVDs / np.cov calls of the reference:
+//   cca_zoo/_utils/_linalg.py:28, cca_zoo/linear/_rcca.py:96, cca_zoo/linear/_mcca.py:150-152,166,
+//   cca_zoo/linear/_gcca.py:101, cca_zoo/deep/objectives.py:83-92.
+#include "moments.cuh"
+
+#include <mutex>
+
+namespace ccab {
+
+// =============================================================================================
+// layout
+// =============================================================================================
+int make_layout(int n_views, const int64_t* dims, ColumnLayout* L) {
+  CCAB_CHECK_ARG(n_views >= 1 && n_views <= kMaxViews, "n_views must be in [1,%d], got %d", kMaxViews,
+                 n_views);
+  L->n_views = n_views;
+  L->coff[0] = 0;
+  L->poff[0] = 0;
+  int nb = 0;
+  for (int v = 0; v < n_views; ++v) {
+    CCAB_CHECK_ARG(dims[v] >= 1 && dims[v] <= kMaxBlocks * kBlk, "bad view width %lld", (long long)dims[v]);
+    L->dims[v] = (int)dims[v];
+    int b = (int)ceil_div(dims[v], kBlk);
+    nb += b;
+    L->coff[v + 1] = L->coff[v] + (int)dims[v];
+    L->poff[v + 1] = L->poff[v] + b * kBlk;
+  }
+  CCAB_CHECK_ARG(nb <= kMaxBlocks, "total padded width %d exceeds %d", nb * kBlk, kMaxBlocks * kBlk);
+  L->nblocks = nb;
+  L->D = L->coff[n_views];
+  L->Dp = nb * kBlk;
+  return 0;
+}
+
+TcDebug& tc_debug() {
+  static TcDebug d = {-1, -1, -1, 0};
+  return d;
+}
+
+// =============================================================================================
+// tcgen05 kernel
+// =============================================================================================
+struct alignas(64) TcParams {
+  CUtensorMap maps[2 * kMaxViews];  // [v] raw / hi operand, [8+v] lo operand (3xTF32)
+  float* partial;                   // [S][Dp][Dp]
+  float* partial_sum;               // [S][Dp]
+  int total_chunks, chunks_per_split, num_splits;
+  int nblocks, Dp;
+  int lbo_bytes, sbo_bytes;
+  int row_tile_start[kMaxBlocks + 1];
+  int blk_col0[kMaxBlocks];
+  uint8_t blk_view[kMaxBlocks];
+};
+static_assert(sizeof(TcParams) <= 4096, "kernel parameter space");
+
+constexpr int kTcThreads = 192;  // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int kTcStages = 4;
+constexpr int kSumCol = 256;     // TMEM column of the column-sum accumulator (N = 16)
+
+template <int KC, bool X3>
+struct TcCfg {
+  static constexpr int kAtom = KC * 128;               // one 32-col x KC-row box
+  static constexpr int kSet = 12 * kAtom;              // A (4 atoms) + B (8 atoms)
+  static constexpr int kStage = (X3 ? 2 : 1) * kSet;
+  static constexpr int kSmem = kTcStages * kStage + 1024 /*ones*/ + 1024 /*align slack*/ + 128;
+};
+
+template <int KC, bool X3>
+__global__ void __launch_bounds__(kTcThreads, 1)
+moments_tf32_kernel(const __grid_constant__ TcParams p) {
+  using Cfg = TcCfg<KC, X3>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ones = smem + kTcStages * Cfg::kStage;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ones + 1024);
+  uint64_t* empty_bar = full_bar + kTcStages;
+  uint64_t* tmem_full_bar = empty_bar + kTcStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile decode: blockIdx.x -> (A block, up to two B blocks) ----
+  const int tile = blockIdx.x;
+  int bi = 0;
+  while (p.row_tile_start[bi + 1] <= tile) ++bi;
+  const int t_in_row = tile - p.row_tile_start[bi];
+  const int bj0 = bi + 2 * t_in_row;
+  const int nB = (bj0 + 1 < p.nblocks) ? 2 : 1;
+  const int N = nB * 128;
+  const bool do_sum = (t_in_row == 0);
+  const int split = blockIdx.y;
+  const int c0 = split * p.chunks_per_split;
+  const int c1 = min(c0 + p.chunks_per_split, p.total_chunks);
+  const bool has_work = c1 > c0;
+
+  // ---- one-time setup ----
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int v = 0; v < kMaxViews; ++v) {
+      // harmless for unused slots: they hold a copy of view 0's map
+      tma_prefetch_desc(&p.maps[v]);
+      if (X3) tma_prefetch_desc(&p.maps[kMaxViews + v]);
+    }
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp >= 2) {
+    float* o = reinterpret_cast<float*>(ones);
+    for (int i = threadIdx.x - 64; i < 256; i += 128) o[i] = 1.0f;
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0 && has_work) {
+      const int vA = p.blk_view[bi], colA = p.blk_col0[bi];
+      int vB[2], colB[2];
+      for (int b = 0; b < 2; ++b) {
+        int bj = min(bj0 + b, p.nblocks - 1);
+        vB[b] = p.blk_view[bj];
+        colB[b] = p.blk_col0[bj];
+      }
+      const uint32_t bytes = (X3 ? 2u : 1u) * (4u + 4u * nB) * Cfg::kAtom;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = c0; c < c1; ++c) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], bytes);
+        uint8_t* st = smem + stage * Cfg::kStage;
+        const int row = c * KC;
+#pragma unroll
+        for (int o = 0; o < (X3 ? 2 : 1); ++o) {
+          uint8_t* base = st + o * Cfg::kSet;
+          const CUtensorMap* mA = &p.maps[o * kMaxViews + vA];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) tma_load_2d(base + a * Cfg::kAtom, mA, &full_bar[stage], colA + 32 * a, row);
+          for (int b = 0; b < nB; ++b) {
+            const CUtensorMap* mB = &p.maps[o * kMaxViews + vB[b]];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              tma_load_2d(base + (4 + 4 * b + a) * Cfg::kAtom, mB, &full_bar[stage], colB[b] + 32 * a, row);
+          }
+        }
+        if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one elected thread) =================
+    if (has_work) {
+      const uint32_t idesc_main = umma_idesc_tf32_mn(128, N);
+      const uint32_t idesc_sum = umma_idesc_tf32_mn(128, 16);
+      const uint32_t lbo = p.lbo_bytes, sbo = p.sbo_bytes;
+      const uint64_t ones_desc = umma_smem_desc(smem_u32(ones), lbo, sbo, 2);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = c0; c < c1; ++c) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sA = smem_u32(smem + stage * Cfg::kStage);
+          const uint32_t sB = sA + 4 * Cfg::kAtom;
+#pragma unroll
+          for (int kk = 0; kk < KC / 8; ++kk) {
+            const uint32_t acc = (c > c0 || kk > 0) ? 1u : 0u;
+            const uint64_t a_hi = umma_smem_desc(sA + kk * 1024, lbo, sbo, 2);
+            const uint64_t b_hi = umma_smem_desc(sB + kk * 1024, lbo, sbo, 2);
+            if (X3) {
+              const uint64_t a_lo = umma_smem_desc(sA + Cfg::kSet + kk * 1024, lbo, sbo, 2);
+              const uint64_t b_lo = umma_smem_desc(sB + Cfg::kSet + kk * 1024, lbo, sbo, 2);
+              // small cross terms first, then the leading term
+              umma_tf32(tmem_base, a_lo, b_hi, idesc_main, acc);
+              umma_tf32(tmem_base, a_hi, b_lo, idesc_main, 1u);
+              umma_tf32(tmem_base, a_hi, b_hi, idesc_main, 1u);
+              if (do_sum) {
+                umma_tf32(tmem_base + kSumCol, a_lo, ones_desc, idesc_sum, acc);
+                umma_tf32(tmem_base + kSumCol, a_hi, ones_desc, idesc_sum, 1u);
+              }
+            } else {
+              umma_tf32(tmem_base, a_hi, b_hi, idesc_main, acc);
+              if (do_sum) umma_tf32(tmem_base + kSumCol, a_hi, ones_desc, idesc_sum, acc);
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+        }
+        __syncwarp();
+        if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+      }
+      if (lane == 0) umma_commit(tmem_full_bar);
+      __syncwarp();
+    }
+  } else {
+    // ================= epilogue: TMEM -> registers -> global partials =================
+    const int g = warp & 3;           // TMEM lane group this warp may touch
+    const int m = g * 32 + lane;      // accumulator row = column of the A block
+    float* prow = p.partial + ((size_t)split * p.Dp + (size_t)bi * 128 + m) * p.Dp;
+    if (has_work) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    for (int cc = 0; cc < N / 32; ++cc) {
+      uint32_t r[32];
+      if (has_work) {
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + cc * 32, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = 0u;
+      }
+      const int bj = bj0 + (cc >> 2);
+      float4* dst = reinterpret_cast<float4*>(prow + (size_t)bj * 128 + (cc & 3) * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                             __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+    }
+    if (do_sum) {
+      uint32_t sv = 0u;
+      if (has_work) {
+        sv = tmem_ld_32x32b_x1(tmem_base + ((uint32_t)(g * 32) << 16) + kSumCol);
+        tmem_ld_wait();
+      }
+      p.partial_sum[(size_t)split * p.Dp + bi * 128 + m] = __uint_as_float(sv);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// hi = rna_tf32(x), lo = rna_tf32(x - hi): the 3xTF32 operand split (one HBM-bound pre-pass)
+__global__ void split_tf32_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx,
+                                  float* __restrict__ hi, float* __restrict__ lo, int64_t ldo) {
+  const int64_t total = n * (int64_t)d;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / d;
+    const int c = (int)(i - r * d);
+    const float v = x[r * ldx + c];
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    const float hf = __uint_as_float(h);
+    uint32_t l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hf));
+    hi[r * ldo + c] = hf;
+    lo[r * ldo + c] = __uint_as_float(l);
+  }
+}
+
+// =============================================================================================
+// exact SIMT kernel (fp32 / fp64), 64x64 tiles inside the same padded tile space
+// =============================================================================================
+struct SimtParams {
+  const void* view_ptr[kMaxViews];
+  int64_t view_ld[kMaxViews];
+  int view_dim[kMaxViews];
+  int view_poff[kMaxViews + 1];
+  int n_views;
+  int64_t n_rows;
+  int64_t rows_per_split;
+  int nb64, Dp;
+  void* partial;      // T [S][Dp][Dp]
+  void* partial_sum;  // T [S][Dp]
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) moments_simt_kernel(const SimtParams p) {
+  constexpr int KC = 16;
+  __shared__ T As[KC][64];
+  __shared__ T Bs[KC][64];
+  // tile decode over the upper triangle of nb64 x nb64
+  int t = blockIdx.x, bi = 0, rowlen = p.nb64;
+  while (t >= rowlen) { t -= rowlen; ++bi; --rowlen; }
+  const int bj = bi + t;
+  const int split = blockIdx.y;
+  const int64_t r0 = split * p.rows_per_split;
+  const int64_t r1 = min(r0 + p.rows_per_split, p.n_rows);
+
+  auto locate = [&](int pcol0, int& v, int& c0) {
+    v = 0;
+    while (v + 1 < p.n_views && p.view_poff[v + 1] <= pcol0) ++v;
+    c0 = pcol0 - p.view_poff[v];
+  };
+  int vA, cA, vB, cB;
+  locate(bi * 64, vA, cA);
+  locate(bj * 64, vB, cB);
+  const T* XA = static_cast<const T*>(p.view_ptr[vA]);
+  const T* XB = static_cast<const T*>(p.view_ptr[vB]);
+  const int64_t ldA = p.view_ld[vA], ldB = p.view_ld[vB];
+  const int dA = p.view_dim[vA], dB = p.view_dim[vB];
+
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+  T csum[4] = {T(0), T(0), T(0), T(0)};
+
+  const int lc = threadIdx.x & 63, lr = threadIdx.x >> 6;  // loader: 4 rows x 64 cols per pass
+  for (int64_t r = r0; r < r1; r += KC) {
+#pragma unroll
+    for (int i = 0; i < KC / 4; ++i) {
+      const int kr = lr + 4 * i;
+      const int64_t row = r + kr;
+      const bool rv = row < r1;
+      As[kr][lc] = (rv && cA + lc < dA) ? XA[row * ldA + cA + lc] : T(0);
+      Bs[kr][lc] = (rv && cB + lc < dB) ? XB[row * ldB + cB + lc] : T(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      T a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+      if (ty == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) csum[j] += b[j];
+      }
+    }
+    __syncthreads();
+  }
+  T* P = static_cast<T*>(p.partial) + (size_t)split * p.Dp * p.Dp;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      P[(size_t)(bi * 64 + ty * 4 + i) * p.Dp + bj * 64 + tx * 4 + j] = acc[i][j];
+  if (bi == bj && ty == 0) {
+    T* S = static_cast<T*>(p.partial_sum) + (size_t)split * p.Dp;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) S[bi * 64 + tx * 4 + j] = csum[j];
+  }
+}
+
+// =============================================================================================
+// K2: reduce split partials (fixed order => deterministic) and finalise the covariance
+// =============================================================================================
+// valid_blk: partial tiles exist for block-row <= block-col where blocks are `blk` wide.
+template <typename T>
+__global__ void reduce_partials_kernel(const T* __restrict__ partial, const T* __restrict__ partial_sum,
+                                       int S, int Dp, int blk, double* __restrict__ out) {
+  const size_t total = (size_t)Dp * Dp + Dp;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    if (i < (size_t)Dp * Dp) {
+      const int r = (int)(i / Dp), c = (int)(i % Dp);
+      if (r / blk <= c / blk)
+        for (int s = 0; s < S; ++s) acc += (double)partial[(size_t)s * Dp * Dp + i];
+    } else {
+      const size_t j = i - (size_t)Dp * Dp;
+      for (int s = 0; s < S; ++s) acc += (double)partial_sum[(size_t)s * Dp + j];
+    }
+    out[i] = acc;
+  }
+}
+
+struct CovParams {
+  int n_views, D, Dp;
+  int dims[kMaxViews];
+  int coff[kMaxViews + 1];
+  int poff[kMaxViews + 1];
+};
+
+__device__ __forceinline__ int compact_to_padded(const CovParams& p, int g) {
+  int v = 0;
+  while (v + 1 < p.n_views && p.coff[v + 1] <= g) ++v;
+  return p.poff[v] + (g - p.coff[v]);
+}
+
+template <typename Tout>
+__global__ void covariance_kernel(const CovParams p, const double* __restrict__ mom, double n_total,
+                                  int center, Tout* __restrict__ C, int64_t ldc, Tout* __restrict__ mean) {
+  const double* M = mom;
+  const double* s = mom + (size_t)p.Dp * p.Dp;
+  const int gi = blockIdx.y * blockDim.y + threadIdx.y;
+  const int gj = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= p.D || gj >= p.D) return;
+  const int pi = compact_to_padded(p, gi), pj = compact_to_padded(p, gj);
+  const int r = min(pi, pj), c = max(pi, pj);  // upper block triangle (and exact symmetry)
+  double v = M[(size_t)r * p.Dp + c];
+  if (center) v -= s[pi] * s[pj] / n_total;
+  C[(size_t)gi * ldc + gj] = (Tout)(v / (n_total - 1.0));
+  if (gi == 0 && mean) mean[gj] = (Tout)(center ? s[pj] / n_total : 0.0);
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+int encode_view_map(CUtensorMap* map, const void* ptr, int64_t n_rows, int64_t d, int64_t ld, int kc) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
+    return -2;
+  }
+  CCAB_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "view pointer must be 16-byte aligned for TMA");
+  CCAB_CHECK_ARG((ld * 4) % 16 == 0, "leading dimension (%lld floats) must be a multiple of 4 for TMA",
+                 (long long)ld);
+  cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)n_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)kc};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  if (tc_debug().tma_dtype >= 0) dt = (CUtensorMapDataType)tc_debug().tma_dtype;
+  CUresult r = enc(map, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (d=%lld n=%lld ld=%lld)", (int)r, (long long)d,
+              (long long)n_rows, (long long)ld);
+    return -3;
+  }
+  return 0;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+struct TcPlan {
+  int kc, total_chunks, num_splits, chunks_per_split, ntiles;
+  size_t partial_bytes, sum_bytes, split_bytes;  // split_bytes: hi/lo operand copies (3xTF32)
+};
+
+TcPlan plan_tc(const ColumnLayout& L, int64_t n_rows, bool x3) {
+  TcPlan P;
+  P.kc = x3 ? 16 : 32;
+  P.total_chunks = (int)ceil_div(n_rows, P.kc);
+  int nt = 0;
+  for (int i = 0; i < L.nblocks; ++i) nt += (L.nblocks - i + 1) / 2;
+  P.ntiles = nt;
+  int S = 1;
+  if (nt < sm_count()) S = sm_count() / nt;
+  const int min_chunks = 8;  // keep the pipeline prologue/epilogue amortised
+  S = (int)std::min<int64_t>(S, std::max<int64_t>(1, P.total_chunks / min_chunks));
+  S = std::min(S, 64);
+  if (tc_debug().force_splits > 0) S = tc_debug().force_splits;
+  S = std::max(1, std::min(S, P.total_chunks));
+  P.chunks_per_split = (int)ceil_div(P.total_chunks, S);
+  P.num_splits = (int)ceil_div(P.total_chunks, P.chunks_per_split);
+  P.partial_bytes = (size_t)P.num_splits * L.Dp * L.Dp * sizeof(float);
+  P.sum_bytes = (size_t)P.num_splits * L.Dp * sizeof(float);
+  P.split_bytes = 0;
+  if (x3) {
+    for (int v = 0; v < L.n_views; ++v) {
+      int64_t ldo = ceil_div(L.dims[v], 4) * 4;
+      P.split_bytes += 2 * (size_t)n_rows * ldo * sizeof(float);
+    }
+  }
+  return P;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct SimtPlan {
+  int nb64, ntiles, num_splits;
+  int64_t rows_per_split;
+};
+
+SimtPlan plan_simt(const ColumnLayout& L, int64_t n_rows) {
+  SimtPlan P;
+  P.nb64 = L.Dp / 64;
+  P.ntiles = P.nb64 * (P.nb64 + 1) / 2;
+  int S = 1;
+  if (P.ntiles < 2 * sm_count()) S = (2 * sm_count()) / P.ntiles;
+  S = (int)std::min<int64_t>(S, std::max<int64_t>(1, n_rows / 256));
+  S = std::max(1, std::min(S, 64));
+  P.rows_per_split = ceil_div(ceil_div(n_rows, S), 16) * 16;
+  P.num_splits = (int)ceil_div(n_rows, P.rows_per_split);
+  return P;
+}
+
+}  // namespace
+
+size_t moments_workspace_bytes(int dtype, int precision, const ColumnLayout& L, int64_t n_rows) {
+  if (precision == 2 || dtype == 1) {
+    SimtPlan P = plan_simt(L, n_rows);
+    size_t el = dtype == 1 ? 8 : 4;
+    return align256((size_t)P.num_splits * L.Dp * L.Dp * el) + align256((size_t)P.num_splits * L.Dp * el);
+  }
+  TcPlan P = plan_tc(L, n_rows, precision == 1);
+  return align256(P.partial_bytes) + align256(P.sum_bytes) + align256(P.split_bytes) + 256;
+}
+
+int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t* lds, int64_t n_rows, bool x3,
+                 double* moments_out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  CCAB_CHECK_ARG(n_rows >= 1 && n_rows < (int64_t)1 << 31, "n_rows out of range");
+  TcPlan P = plan_tc(L, n_rows, x3);
+  const size_t need = align256(P.partial_bytes) + align256(P.sum_bytes) + align256(P.split_bytes) + 256;
+  CCAB_CHECK_ARG(ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
+  uint8_t* w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+
+  TcParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.partial = reinterpret_cast<float*>(w);
+  prm.partial_sum = reinterpret_cast<float*>(w + align256(P.partial_bytes));
+  uint8_t* splitbuf = w + align256(P.partial_bytes) + align256(P.sum_bytes);
+
+  // operands (raw, or hi/lo copies for 3xTF32) and their tensor maps
+  for (int v = 0; v < L.n_views; ++v) {
+    const float* x = static_cast<const float*>(views[v]);
+    if (x3) {
+      const int64_t ldo = ceil_div(L.dims[v], 4) * 4;
+      float* hi = reinterpret_cast<float*>(splitbuf);
+      float* lo = hi + (size_t)n_rows * ldo;
+      splitbuf += 2 * (size_t)n_rows * ldo * sizeof(float);
+      const int64_t total = n_rows * (int64_t)L.dims[v];
+      int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
+      split_tf32_kernel<<<blocks, 256, 0, stream>>>(x, n_rows, L.dims[v], lds[v], hi, lo, ldo);
+      CCAB_CUDA(cudaGetLastError());
+      int rc = encode_view_map(&prm.maps[v], hi, n_rows, L.dims[v], ldo, P.kc);
+      if (rc) return rc;
+      rc = encode_view_map(&prm.maps[kMaxViews + v], lo, n_rows, L.dims[v], ldo, P.kc);
+      if (rc) return rc;
+    } else {
+      int rc = encode_view_map(&prm.maps[v], x, n_rows, L.dims[v], lds[v], P.kc);
+      if (rc) return rc;
+    }
+  }
+  for (int v = L.n_views; v < kMaxViews; ++v) {
+    prm.maps[v] = prm.maps[0];
+    prm.maps[kMaxViews + v] = prm.maps[x3 ? kMaxViews : 0];
+  }
+  if (!x3)
+    for (int v = 0; v < kMaxViews; ++v) prm.maps[kMaxViews + v] = prm.maps[0];
+
+  prm.total_chunks = P.total_chunks;
+  prm.chunks_per_split = P.chunks_per_split;
+  prm.num_splits = P.num_splits;
+  prm.nblocks = L.nblocks;
+  prm.Dp = L.Dp;
+  prm.lbo_bytes = tc_debug().lbo_bytes >= 0 ? tc_debug().lbo_bytes : P.kc * 128;
+  prm.sbo_bytes = tc_debug().sbo_bytes >= 0 ? tc_debug().sbo_bytes : 1024;
+  int b = 0;
+  for (int v = 0; v < L.n_views; ++v)
+    for (int c = 0; c < L.dims[v]; c += kBlk, ++b) {
+      prm.blk_view[b] = (uint8_t)v;
+      prm.blk_col0[b] = c;
+    }
+  prm.row_tile_start[0] = 0;
+  for (int i = 0; i < L.nblocks; ++i) prm.row_tile_start[i + 1] = prm.row_tile_start[i] + (L.nblocks - i + 1) / 2;
+  for (int i = L.nblocks + 1; i <= kMaxBlocks; ++i) prm.row_tile_start[i] = 0x7fffffff;
+
+  dim3 grid(P.ntiles, P.num_splits);
+  if (x3) {
+    using Cfg = TcCfg<16, true>;
+    static bool attr = false;
+    if (!attr) {
+      CCAB_CUDA(cudaFuncSetAttribute(moments_tf32_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::kSmem));
+      attr = true;
+    }
+    moments_tf32_kernel<16, true><<<grid, kTcThreads, Cfg::kSmem, stream>>>(prm);
+  } else {
+    using Cfg = TcCfg<32, false>;
+    static bool attr = false;
+    if (!attr) {
+      CCAB_CUDA(cudaFuncSetAttribute(moments_tf32_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::kSmem));
+      attr = true;
+    }
+    moments_tf32_kernel<32, false><<<grid, kTcThreads, Cfg::kSmem, stream>>>(prm);
+  }
+  CCAB_CUDA(cudaGetLastError());
+
+  const size_t total = (size_t)L.Dp * L.Dp + L.Dp;
+  int rblocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
+  reduce_partials_kernel<float><<<rblocks, 256, 0, stream>>>(prm.partial, prm.partial_sum, P.num_splits, L.Dp,
+                                                            kBlk, moments_out);
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int moments_simt(const ColumnLayout& L, const void* const* views, const int64_t* lds, int64_t n_rows,
+                 double* moments_out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  CCAB_CHECK_ARG(n_rows >= 1, "n_rows must be positive");
+  SimtPlan P = plan_simt(L, n_rows);
+  const size_t pb = align256((size_t)P.num_splits * L.Dp * L.Dp * sizeof(T));
+  const size_t sb = align256((size_t)P.num_splits * L.Dp * sizeof(T));
+  CCAB_CHECK_ARG(ws_bytes >= pb + sb, "workspace too small: %zu < %zu", ws_bytes, pb + sb);
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  SimtParams prm;
+  memset(&prm, 0, sizeof(prm));
+  for (int v = 0; v < L.n_views; ++v) {
+    prm.view_ptr[v] = views[v];
+    prm.view_ld[v] = lds[v];
+    prm.view_dim[v] = L.dims[v];
+  }
+  for (int v = 0; v <= L.n_views; ++v) prm.view_poff[v] = L.poff[v];
+  prm.n_views = L.n_views;
+  prm.n_rows = n_rows;
+  prm.rows_per_split = P.rows_per_split;
+  prm.nb64 = P.nb64;
+  prm.Dp = L.Dp;
+  prm.partial = w;
+  prm.partial_sum = w + pb;
+  // partial sums of non-diagonal 64-blocks inside a 128-block are never written by the kernel: the
+  // reducer only reads what a tile wrote (block-triangle test at 64 granularity).
+  dim3 grid(P.ntiles, P.num_splits);
+  moments_simt_kernel<T><<<grid, 256, 0, stream>>>(prm);
+  CCAB_CUDA(cudaGetLastError());
+  const size_t total = (size_t)L.Dp * L.Dp + L.Dp;
+  int rblocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
+  reduce_partials_kernel<T><<<rblocks, 256, 0, stream>>>(static_cast<const T*>(prm.partial),
+                                                        static_cast<const T*>(prm.partial_sum), P.num_splits,
+                                                        L.Dp, 64, moments_out);
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template int moments_simt<float>(const ColumnLayout&, const void* const*, const int64_t*, int64_t, double*, void*,
+                                 size_t, cudaStream_t);
+template int moments_simt<double>(const ColumnLayout&, const void* const*, const int64_t*, int64_t, double*, void*,
+                                  size_t, cudaStream_t);
+
+template <typename Tout>
+int covariance_from_moments(const ColumnLayout& L, const double* moments, double n_total, int center, Tout* C,
+                            int64_t ldc, Tout* mean, cudaStream_t stream) {
+  CCAB_CHECK_ARG(n_total >= 2.0, "need at least 2 samples for a covariance, got %g", n_total);
+  CCAB_CHECK_ARG(ldc >= L.D, "ldc too small");
+  CovParams p;
+  p.n_views = L.n_views;
+  p.D = L.D;
+  p.Dp = L.Dp;
+  for (int v = 0; v < kMaxViews; ++v) p.dims[v] = v < L.n_views ? L.dims[v] : 0;
+  for (int v = 0; v <= kMaxViews; ++v) {
+    p.coff[v] = v <= L.n_views ? L.coff[v] : L.D;
+    p.poff[v] = v <= L.n_views ? L.poff[v] : L.Dp;
+  }
+  dim3 block(32, 8);
+  dim3 grid((unsigned)ceil_div(L.D, 32), (unsigned)ceil_div(L.D, 8));
+  covariance_kernel<Tout><<<grid, block, 0, stream>>>(p, moments, n_total, center, C, ldc, mean);
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template int covariance_from_moments<float>(const ColumnLayout&, const double*, double, int, float*, int64_t, float*,
+                                            cudaStream_t);
+template int covariance_from_moments<double>(const ColumnLayout&, const double*, double, int, double*, int64_t,
+                                             double*, cudaStream_t);
+
+}  // namespace ccab

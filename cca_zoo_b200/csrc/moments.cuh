@@ -1,0 +1,51 @@
+// Block-moment stage (kernels K1/K2 of DESIGN.md): M = [X1..Xm]^T [X1..Xm], s = 1^T X.
+#pragma once
+#include "common.cuh"
+
+namespace ccab {
+
+constexpr int kMaxViews = 8;
+constexpr int kBlk = 128;        // column-block width of the padded tile space
+constexpr int kMaxBlocks = 128;  // D_padded <= 16384
+
+// Column layout shared by every kernel of the moment stage.  Each view's columns are padded to a
+// multiple of 128 in *tile space*; "compact" is the hstacked view order the reference uses
+// (cca_zoo/linear/_mcca.py:150: np.hstack(views)).
+struct ColumnLayout {
+  int n_views;
+  int nblocks;               // total 128-column blocks
+  int D;                     // compact width  = sum(dims)
+  int Dp;                    // padded width   = nblocks * 128
+  int dims[kMaxViews];       // view widths
+  int coff[kMaxViews + 1];   // compact offset of each view
+  int poff[kMaxViews + 1];   // padded  offset of each view
+};
+
+int make_layout(int n_views, const int64_t* dims, ColumnLayout* out);
+
+// --- launchers (all asynchronous on `stream`) -------------------------------------------------
+// precision: 0 = TF32 single pass (tcgen05), 1 = 3xTF32 split (tcgen05), 2 = exact SIMT FMA.
+size_t moments_workspace_bytes(int dtype, int precision, const ColumnLayout& L, int64_t n_rows);
+
+int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t* lds, int64_t n_rows,
+                 bool x3, double* moments_out, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+template <typename T>
+int moments_simt(const ColumnLayout& L, const void* const* views, const int64_t* lds, int64_t n_rows,
+                 double* moments_out, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+// moments (double[Dp*Dp + Dp], padded, upper block triangle) -> compact covariance + means
+template <typename Tout>
+int covariance_from_moments(const ColumnLayout& L, const double* moments, double n_total, int center,
+                            Tout* C, int64_t ldc, Tout* mean, cudaStream_t stream);
+
+// debug knobs for the tcgen05 kernel (descriptor strides / TMA data type), see tools/umma_probe.py
+struct TcDebug {
+  int lbo_bytes;    // <0: default
+  int sbo_bytes;    // <0: default
+  int tma_dtype;    // <0: default (FLOAT32); else a CUtensorMapDataType value
+  int force_splits; // <=0: heuristic
+};
+TcDebug& tc_debug();
+
+}  // namespace ccab

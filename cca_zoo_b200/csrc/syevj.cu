@@ -1,0 +1,526 @@
+// K3/K4: symmetric eigensolver and SVD by one-sided block Jacobi (Hestenes), batched.
+//
+// The working matrix G (m x n, column-major: each column contiguous) starts as A (symmetric mode) or
+// as the matrix to factor (SVD mode); V (n x n) starts as I.  Columns are grouped in blocks of
+// kB = 16.  One round of the round-robin tournament handles nb/2 disjoint block pairs; for a pair
+// the 32-column panel P = [G_p G_q] gets
+//     (a) its Gram matrix  W = P^T P                      (jacobi_gram_kernel, row-split partials)
+//     (b) the small symmetric eigenproblem W = Q L Q^T    (jacobi_solve_kernel: parallel two-sided
+//         Jacobi in shared memory, 256 pair-blocks per step, ping-pong buffers, one barrier/step)
+//     (c) the update  [G;V]_panel <- [G;V]_panel Q        (jacobi_apply_kernel)
+// nb-1 rounds make a sweep; sweeps repeat until the largest normalised off-diagonal Gram entry seen
+// in a sweep drops below tol.  At convergence G = A V has orthogonal columns:
+//     symmetric mode : lambda_j = v_j . g_j  (Rayleigh quotient, sign included)
+//     SVD mode       : sigma_j = |g_j|, u_j = g_j / sigma_j.
+// Results are sorted descending and written as ROWS (row j = j-th vector).
+//
+// Replaces the LAPACK calls behind np.linalg.svd / scipy.linalg.eigh / np.linalg.eigvalsh /
+// torch.linalg.eigh at cca_zoo/_utils/_linalg.py:28,67-71, cca_zoo/linear/_rcca.py:97,
+// cca_zoo/linear/_mcca.py:117,170, cca_zoo/linear/_gcca.py:102, cca_zoo/deep/objectives.py:19.
+#include "syevj.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <type_traits>
+
+namespace ccab {
+
+constexpr int kB = 16;        // column block width
+constexpr int kS = 2 * kB;    // panel width
+constexpr int kSP = kS + 1;   // padded smem stride
+
+template <typename T>
+__device__ __forceinline__ T neg_inf();
+template <>
+__device__ __forceinline__ float neg_inf<float>() { return __int_as_float(0xff800000); }
+template <>
+__device__ __forceinline__ double neg_inf<double>() { return __longlong_as_double(0xfff0000000000000ULL); }
+
+template <typename T>
+struct Eps;
+template <>
+struct Eps<float> { static constexpr float v = 5.9604645e-8f; };
+template <>
+struct Eps<double> { static constexpr double v = 1.1102230246251565e-16; };
+
+// round-robin tournament on `np` players (np even): pair i of round r
+__host__ __device__ __forceinline__ void rr_pair(int np, int r, int i, int& p, int& q) {
+  const int m1 = np - 1;
+  int a, b;
+  if (i == 0) {
+    a = m1;
+    b = r % m1;
+  } else {
+    a = (r + i) % m1;
+    b = (r - i + m1) % m1;
+  }
+  p = a < b ? a : b;
+  q = a < b ? b : a;
+}
+
+template <typename T>
+__device__ __forceinline__ void jacobi_cs(T app, T aqq, T apq, T& c, T& s, bool& rotated) {
+  const T thresh = Eps<T>::v * sqrt(fabs(app) * fabs(aqq));
+  if (fabs(apq) <= thresh || apq == T(0)) {
+    c = T(1);
+    s = T(0);
+    return;
+  }
+  const T tau = (aqq - app) / (T(2) * apq);
+  const T t = (tau >= T(0) ? T(1) : T(-1)) / (fabs(tau) + sqrt(T(1) + tau * tau));
+  c = T(1) / sqrt(T(1) + t * t);
+  s = t * c;
+  rotated = true;
+}
+
+// Parallel cyclic two-sided Jacobi on an S x S symmetric matrix in shared memory.
+// Wa/Wb: ping-pong copies (stride S+1), Q: accumulated rotations (stride S+1, starts as I).
+// Returns with the diagonalised matrix in the buffer pointed to by the return value.
+template <typename T, int S>
+__device__ T* small_syevj(T* Wa, T* Wb, T* Q, int max_sweeps) {
+  constexpr int H = S / 2;
+  constexpr int SP = S + 1;
+  T* cur = Wa;
+  T* nxt = Wb;
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    int any = 0;
+    for (int step = 0; step < S - 1; ++step) {
+      bool rot = false;
+      for (int blk = threadIdx.x; blk < H * H; blk += blockDim.x) {
+        const int i = blk / H, j = blk % H;
+        int pi, qi, pj, qj;
+        rr_pair(S, step, i, pi, qi);
+        rr_pair(S, step, j, pj, qj);
+        T ci, si, cj, sj;
+        bool ri = false, rj = false;
+        jacobi_cs(cur[pi * SP + pi], cur[qi * SP + qi], cur[pi * SP + qi], ci, si, ri);
+        jacobi_cs(cur[pj * SP + pj], cur[qj * SP + qj], cur[pj * SP + qj], cj, sj, rj);
+        const T x00 = cur[pi * SP + pj], x01 = cur[pi * SP + qj];
+        const T x10 = cur[qi * SP + pj], x11 = cur[qi * SP + qj];
+        const T y00 = cj * x00 - sj * x01, y01 = sj * x00 + cj * x01;
+        const T y10 = cj * x10 - sj * x11, y11 = sj * x10 + cj * x11;
+        T z00 = ci * y00 - si * y10, z10 = si * y00 + ci * y10;
+        T z01 = ci * y01 - si * y11, z11 = si * y01 + ci * y11;
+        if (i == j && ri) { z01 = T(0); z10 = T(0); }
+        nxt[pi * SP + pj] = z00;
+        nxt[pi * SP + qj] = z01;
+        nxt[qi * SP + pj] = z10;
+        nxt[qi * SP + qj] = z11;
+        // Q <- Q J_i for rows j and j+H (each (row, pair) owned by exactly one thread)
+        if (ri) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int r = j + h * H;
+            const T a = Q[r * SP + pi], b = Q[r * SP + qi];
+            Q[r * SP + pi] = ci * a - si * b;
+            Q[r * SP + qi] = si * a + ci * b;
+          }
+        }
+        rot |= (ri && i == j);
+      }
+      any |= __syncthreads_or(rot ? 1 : 0);
+      T* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    if (!any) break;
+  }
+  return cur;
+}
+
+// ---------------------------------------------------------------------------------------------
+// (a) partial Gram of a panel over a row range
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct JacobiCtx {
+  T* G;          // [batch][n_pad cols][ldg]      column-major
+  T* V;          // [batch][n_pad cols][n_pad]    column-major
+  T* Wpart;      // [batch][npairs][R][kS*kS]
+  T* Qm;         // [batch][npairs][kS*kS]        row-major Q
+  int* skip;     // [batch][npairs]
+  unsigned* stat;  // [batch] max off-diagonal ratio of the sweep (float bits)
+  int m, n_pad, nb, npairs, R;
+  int64_t ldg;
+  int rows_per_part;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) jacobi_gram_kernel(const JacobiCtx<T> c, int round) {
+  constexpr int KR = 64;
+  __shared__ T Ps[KR][kSP];
+  const int pair = blockIdx.x, part = blockIdx.y, b = blockIdx.z;
+  int p, q;
+  rr_pair(c.nb, round, pair, p, q);
+  const T* G = c.G + (size_t)b * c.n_pad * c.ldg;
+  const int r0 = part * c.rows_per_part;
+  const int r1 = min(r0 + c.rows_per_part, c.m);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  T acc00 = 0, acc01 = 0, acc10 = 0, acc11 = 0;
+  const int lr = threadIdx.x & 63, lc0 = threadIdx.x >> 6;
+  for (int r = r0; r < r1; r += KR) {
+#pragma unroll
+    for (int i = 0; i < kS / 4; ++i) {
+      const int col = lc0 + 4 * i;
+      const int gcol = (col < kB ? p * kB + col : q * kB + col - kB);
+      const int row = r + lr;
+      Ps[lr][col] = row < r1 ? G[(size_t)gcol * c.ldg + row] : T(0);
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < KR; ++k) {
+      const T a0 = Ps[k][2 * ty], a1 = Ps[k][2 * ty + 1];
+      const T b0 = Ps[k][2 * tx], b1 = Ps[k][2 * tx + 1];
+      acc00 = fma(a0, b0, acc00);
+      acc01 = fma(a0, b1, acc01);
+      acc10 = fma(a1, b0, acc10);
+      acc11 = fma(a1, b1, acc11);
+    }
+    __syncthreads();
+  }
+  T* W = c.Wpart + (((size_t)b * c.npairs + pair) * c.R + part) * (kS * kS);
+  W[(2 * ty) * kS + 2 * tx] = acc00;
+  W[(2 * ty) * kS + 2 * tx + 1] = acc01;
+  W[(2 * ty + 1) * kS + 2 * tx] = acc10;
+  W[(2 * ty + 1) * kS + 2 * tx + 1] = acc11;
+}
+
+// ---------------------------------------------------------------------------------------------
+// (b) small eigenproblem of the panel Gram matrix -> Q (columns sorted by descending eigenvalue)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) jacobi_solve_kernel(const JacobiCtx<T> c, T tol) {
+  __shared__ T Wa[kS * kSP];
+  __shared__ T Wb[kS * kSP];
+  __shared__ T Q[kS * kSP];
+  __shared__ int rank_of[kS];
+  __shared__ float ratio_s;
+  const int pair = blockIdx.x, b = blockIdx.y;
+  const T* Wp = c.Wpart + ((size_t)b * c.npairs + pair) * c.R * (kS * kS);
+  if (threadIdx.x == 0) ratio_s = 0.f;
+  for (int e = threadIdx.x; e < kS * kS; e += blockDim.x) {
+    T acc = 0;
+    for (int r = 0; r < c.R; ++r) acc += Wp[(size_t)r * kS * kS + e];  // fixed order: deterministic
+    const int i = e / kS, j = e % kS;
+    Wa[i * kSP + j] = acc;
+    Q[i * kSP + j] = (i == j) ? T(1) : T(0);
+  }
+  __syncthreads();
+  // convergence statistic: max_{i<j} |w_ij| / sqrt(w_ii w_jj)
+  float myr = 0.f;
+  for (int e = threadIdx.x; e < kS * kS; e += blockDim.x) {
+    const int i = e / kS, j = e % kS;
+    if (i < j) {
+      const T d = Wa[i * kSP + i] * Wa[j * kSP + j];
+      const T w = fabs(Wa[i * kSP + j]);
+      if (d > T(0) && w > T(0)) myr = fmaxf(myr, (float)(w / sqrt(d)));
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) myr = fmaxf(myr, __shfl_xor_sync(0xffffffffu, myr, o));
+  if ((threadIdx.x & 31) == 0 && myr > 0.f) atomicMax(reinterpret_cast<int*>(&ratio_s), __float_as_int(myr));
+  __syncthreads();
+  const float ratio = ratio_s;
+  if (threadIdx.x == 0) {
+    atomicMax(c.stat + b, __float_as_uint(ratio));
+    c.skip[(size_t)b * c.npairs + pair] = (ratio <= (float)tol) ? 1 : 0;
+  }
+  if (ratio <= (float)tol) return;  // panel already orthogonal: Q = I, apply kernel skips it
+
+  T* fin = small_syevj<T, kS>(Wa, Wb, Q, 10);
+  __syncthreads();
+  if (threadIdx.x < kS) {
+    const int i = threadIdx.x;
+    const T li = fin[i * kSP + i];
+    int rk = 0;
+    for (int j = 0; j < kS; ++j) {
+      const T lj = fin[j * kSP + j];
+      rk += (lj > li || (lj == li && j < i)) ? 1 : 0;
+    }
+    rank_of[i] = rk;
+  }
+  __syncthreads();
+  T* Qo = c.Qm + ((size_t)b * c.npairs + pair) * (kS * kS);
+  for (int e = threadIdx.x; e < kS * kS; e += blockDim.x) {
+    const int r = e / kS, i = e % kS;
+    Qo[r * kS + rank_of[i]] = Q[r * kSP + i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (c) panel update: rows of [G;V] times Q
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) jacobi_apply_kernel(const JacobiCtx<T> c, int round) {
+  __shared__ T Qs[kS * kS];
+  const int pair = blockIdx.x, b = blockIdx.z;
+  if (c.skip[(size_t)b * c.npairs + pair]) return;
+  int p, q;
+  rr_pair(c.nb, round, pair, p, q);
+  const T* Qg = c.Qm + ((size_t)b * c.npairs + pair) * (kS * kS);
+  for (int e = threadIdx.x; e < kS * kS; e += blockDim.x) Qs[e] = Qg[e];
+  __syncthreads();
+  // row chunks: first ceil(m/128) chunks cover G, the rest cover V
+  const int gchunks = (c.m + 127) / 128;
+  int chunk = blockIdx.y;
+  T* base;
+  int64_t ld;
+  int rows;
+  if (chunk < gchunks) {
+    base = c.G + (size_t)b * c.n_pad * c.ldg;
+    ld = c.ldg;
+    rows = c.m;
+  } else {
+    chunk -= gchunks;
+    base = c.V + (size_t)b * c.n_pad * c.n_pad;
+    ld = c.n_pad;
+    rows = c.n_pad;
+  }
+  const int row = chunk * 128 + threadIdx.x;
+  if (row >= rows) return;
+  T x[kS], y[kS];
+#pragma unroll
+  for (int k = 0; k < kS; ++k) {
+    const int gcol = (k < kB ? p * kB + k : q * kB + k - kB);
+    x[k] = base[(size_t)gcol * ld + row];
+    y[k] = T(0);
+  }
+#pragma unroll
+  for (int k = 0; k < kS; ++k) {
+#pragma unroll
+    for (int j = 0; j < kS; ++j) y[j] = fma(x[k], Qs[k * kS + j], y[j]);
+  }
+#pragma unroll
+  for (int k = 0; k < kS; ++k) {
+    const int gcol = (k < kB ? p * kB + k : q * kB + k - kB);
+    base[(size_t)gcol * ld + row] = y[k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// setup / teardown kernels
+// ---------------------------------------------------------------------------------------------
+// G[col j][row i] = in[j*ld_in + i] (colmajor_in) or in[i*ld_in + j]; padded columns zero; V = I.
+template <typename T>
+__global__ void jacobi_init_kernel(const T* __restrict__ in, int64_t ld_in, int64_t batch_stride_in,
+                                   int colmajor_in, int m, int n, JacobiCtx<T> c, T shift) {
+  const int b = blockIdx.z;
+  const T* A = in + (size_t)b * batch_stride_in;
+  T* G = c.G + (size_t)b * c.n_pad * c.ldg;
+  T* V = c.V + (size_t)b * c.n_pad * c.n_pad;
+  const int col = blockIdx.y;
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < max(c.m, c.n_pad);
+       row += gridDim.x * blockDim.x) {
+    if (row < c.m) {
+      T v = T(0);
+      if (col < n) {
+        v = colmajor_in ? A[(size_t)col * ld_in + row] : A[(size_t)row * ld_in + col];
+        if (row == col) v += shift;
+      }
+      G[(size_t)col * c.ldg + row] = v;
+    }
+    if (row < c.n_pad) V[(size_t)col * c.n_pad + row] = (row == col) ? T(1) : T(0);
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) c.stat[b] = 0u;
+}
+
+__global__ void jacobi_reset_stat_kernel(unsigned* stat, int batch) {
+  if (threadIdx.x < batch) stat[threadIdx.x] = 0u;
+}
+
+// one warp per column: value (Rayleigh quotient or norm), pad detection, optional normalisation of G
+template <typename T>
+__global__ void jacobi_values_kernel(JacobiCtx<T> c, int n, int svd_mode, T shift, T* __restrict__ vals) {
+  const int b = blockIdx.y;
+  const int col = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (col >= c.n_pad) return;
+  T* g = c.G + (size_t)b * c.n_pad * c.ldg + (size_t)col * c.ldg;
+  const T* v = c.V + (size_t)b * c.n_pad * c.n_pad + (size_t)col * c.n_pad;
+  T acc = 0, padw = 0;
+  if (svd_mode) {
+    for (int i = lane; i < c.m; i += 32) acc = fma(g[i], g[i], acc);
+  } else {
+    for (int i = lane; i < n; i += 32) acc = fma(v[i], g[i], acc);
+  }
+  for (int i = n + lane; i < c.n_pad; i += 32) padw = fma(v[i], v[i], padw);
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    padw += __shfl_xor_sync(0xffffffffu, padw, o);
+  }
+  T val;
+  if (padw > T(0.5)) {
+    val = neg_inf<T>();  // padding direction: sorts last, never output
+  } else if (svd_mode) {
+    val = sqrt(acc);
+    const T inv = val > T(0) ? T(1) / val : T(0);
+    for (int i = lane; i < c.m; i += 32) g[i] *= inv;
+  } else {
+    val = acc - shift;
+  }
+  if (lane == 0) vals[(size_t)b * c.n_pad + col] = val;
+}
+
+// rank-by-counting sort (descending) + gather of the vectors as rows
+template <typename T>
+__global__ void jacobi_rank_kernel(const T* __restrict__ vals, int n_pad, int* __restrict__ rank) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  const T* v = vals + (size_t)b * n_pad;
+  const T vi = v[i];
+  int rk = 0;
+  for (int j = 0; j < n_pad; ++j) {
+    const T vj = v[j];
+    rk += (vj > vi || (vj == vi && j < i)) ? 1 : 0;
+  }
+  rank[(size_t)b * n_pad + i] = rk;
+}
+
+template <typename T>
+__global__ void jacobi_gather_kernel(JacobiCtx<T> c, int n, const T* __restrict__ vals,
+                                     const int* __restrict__ rank, T* __restrict__ out_vals,
+                                     int64_t vals_stride, T* __restrict__ out_right, int64_t ld_right,
+                                     int64_t right_stride, T* __restrict__ out_left, int64_t ld_left,
+                                     int64_t left_stride) {
+  const int b = blockIdx.y, col = blockIdx.x;
+  const int rk = rank[(size_t)b * c.n_pad + col];
+  if (rk >= n) return;  // padding directions
+  if (threadIdx.x == 0 && out_vals) out_vals[(size_t)b * vals_stride + rk] = vals[(size_t)b * c.n_pad + col];
+  if (out_right) {
+    const T* v = c.V + (size_t)b * c.n_pad * c.n_pad + (size_t)col * c.n_pad;
+    T* o = out_right + (size_t)b * right_stride + (size_t)rk * ld_right;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) o[i] = v[i];
+  }
+  if (out_left) {
+    const T* g = c.G + (size_t)b * c.n_pad * c.ldg + (size_t)col * c.ldg;
+    T* o = out_left + (size_t)b * left_stride + (size_t)rk * ld_left;
+    for (int i = threadIdx.x; i < c.m; i += blockDim.x) o[i] = g[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------------
+namespace {
+inline size_t al(size_t x) { return (x + 255) & ~size_t(255); }
+
+template <typename T>
+struct Plan {
+  int n_pad, nb, npairs, R, rows_per_part;
+  int64_t ldg;
+  size_t oG, oV, oW, oQ, oSkip, oStat, oVals, oRank, total;
+};
+
+template <typename T>
+Plan<T> make_plan(int m, int n, int batch) {
+  Plan<T> P;
+  P.n_pad = (int)ceil_div(n, kS) * kS;
+  P.nb = P.n_pad / kB;
+  P.npairs = P.nb / 2;
+  P.ldg = m;
+  // enough Gram partials to fill the machine, at least 128 rows each
+  int R = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(m, 128), ceil_div(4 * 148, (int64_t)P.npairs * batch)));
+  R = std::min(R, 16);
+  P.rows_per_part = (int)ceil_div(ceil_div(m, R), 64) * 64;
+  P.R = (int)ceil_div(m, P.rows_per_part);
+  size_t o = 0;
+  P.oG = o; o += al((size_t)batch * P.n_pad * P.ldg * sizeof(T));
+  P.oV = o; o += al((size_t)batch * P.n_pad * P.n_pad * sizeof(T));
+  P.oW = o; o += al((size_t)batch * P.npairs * P.R * kS * kS * sizeof(T));
+  P.oQ = o; o += al((size_t)batch * P.npairs * kS * kS * sizeof(T));
+  P.oSkip = o; o += al((size_t)batch * P.npairs * sizeof(int));
+  P.oStat = o; o += al((size_t)batch * sizeof(unsigned));
+  P.oVals = o; o += al((size_t)batch * P.n_pad * sizeof(T));
+  P.oRank = o; o += al((size_t)batch * P.n_pad * sizeof(int));
+  P.total = o + 256;
+  return P;
+}
+}  // namespace
+
+template <typename T>
+size_t jacobi_workspace_bytes(int m, int n, int batch) {
+  return make_plan<T>(m, n, batch).total;
+}
+
+template <typename T>
+int jacobi_solve(const JacobiArgs<T>& a, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  const int m = a.m, n = a.n, batch = a.batch;
+  CCAB_CHECK_ARG(m >= 1 && n >= 1 && batch >= 1 && batch <= 1024, "bad jacobi shape m=%d n=%d batch=%d", m, n,
+                 batch);
+  CCAB_CHECK_ARG(a.svd_mode || m == n, "symmetric mode needs a square matrix");
+  Plan<T> P = make_plan<T>(m, n, batch);
+  CCAB_CHECK_ARG(ws_bytes >= P.total, "workspace too small: %zu < %zu", ws_bytes, P.total);
+  uint8_t* w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  JacobiCtx<T> c;
+  c.G = reinterpret_cast<T*>(w + P.oG);
+  c.V = reinterpret_cast<T*>(w + P.oV);
+  c.Wpart = reinterpret_cast<T*>(w + P.oW);
+  c.Qm = reinterpret_cast<T*>(w + P.oQ);
+  c.skip = reinterpret_cast<int*>(w + P.oSkip);
+  c.stat = reinterpret_cast<unsigned*>(w + P.oStat);
+  T* vals = reinterpret_cast<T*>(w + P.oVals);
+  int* rank = reinterpret_cast<int*>(w + P.oRank);
+  c.m = m;
+  c.n_pad = P.n_pad;
+  c.nb = P.nb;
+  c.npairs = P.npairs;
+  c.R = P.R;
+  c.ldg = P.ldg;
+  c.rows_per_part = P.rows_per_part;
+
+  const T shift = a.svd_mode ? T(0) : (T)a.shift;
+  {
+    const int rows = std::max(m, P.n_pad);
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div(rows, 256), 64), P.n_pad, batch);
+    jacobi_init_kernel<T><<<grid, 256, 0, stream>>>(a.in, a.ld_in, a.batch_stride_in, a.colmajor_in, m, n, c, shift);
+    CCAB_CUDA(cudaGetLastError());
+  }
+  const T tol = a.tol > 0 ? (T)a.tol : (T)(4.0 * (double)Eps<T>::v * std::sqrt((double)m));
+  const int max_sweeps = a.max_sweeps > 0 ? a.max_sweeps : (std::is_same<T, float>::value ? 16 : 24);
+  const int rounds = P.nb - 1;
+  const int apply_chunks = (int)(ceil_div(m, 128) + ceil_div(P.n_pad, 128));
+  int sweeps_done = 0;
+  float last_ratio = -1.f;
+  unsigned* h_stat = nullptr;
+  CCAB_CUDA(cudaMallocHost(&h_stat, sizeof(unsigned) * batch));
+  int rc = 0;
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    for (int r = 0; r < rounds; ++r) {
+      jacobi_gram_kernel<T><<<dim3(P.npairs, P.R, batch), 256, 0, stream>>>(c, r);
+      jacobi_solve_kernel<T><<<dim3(P.npairs, batch), 256, 0, stream>>>(c, tol);
+      jacobi_apply_kernel<T><<<dim3(P.npairs, apply_chunks, batch), 128, 0, stream>>>(c, r);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { rc = cuda_fail(e, "jacobi sweep launch"); break; }
+    e = cudaMemcpyAsync(h_stat, c.stat, sizeof(unsigned) * batch, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "jacobi sweep sync"); break; }
+    ++sweeps_done;
+    float worst = 0.f;
+    for (int b = 0; b < batch; ++b) {
+      float f;
+      memcpy(&f, &h_stat[b], 4);
+      worst = std::max(worst, f);
+    }
+    last_ratio = worst;
+    if (worst <= (float)tol) break;
+    jacobi_reset_stat_kernel<<<1, 1024, 0, stream>>>(c.stat, batch);
+  }
+  cudaFreeHost(h_stat);
+  if (rc) return rc;
+  if (a.info) { a.info[0] = sweeps_done; }
+  if (a.final_offdiag) *a.final_offdiag = last_ratio;
+
+  jacobi_values_kernel<T><<<dim3((unsigned)ceil_div(P.n_pad, 8), batch), 256, 0, stream>>>(c, n, a.svd_mode, shift, vals);
+  jacobi_rank_kernel<T><<<dim3((unsigned)ceil_div(P.n_pad, 256), batch), 256, 0, stream>>>(vals, P.n_pad, rank);
+  jacobi_gather_kernel<T><<<dim3(P.n_pad, batch), 128, 0, stream>>>(
+      c, n, vals, rank, a.out_vals, a.vals_stride, a.out_right, a.ld_right, a.right_stride, a.out_left, a.ld_left,
+      a.left_stride);
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template size_t jacobi_workspace_bytes<float>(int, int, int);
+template size_t jacobi_workspace_bytes<double>(int, int, int);
+template int jacobi_solve<float>(const JacobiArgs<float>&, void*, size_t, cudaStream_t);
+template int jacobi_solve<double>(const JacobiArgs<double>&, void*, size_t, cudaStream_t);
+
+}  // namespace ccab

@@ -1,0 +1,216 @@
+"""Device-side building blocks: torch CUDA tensors in, torch CUDA tensors out, arithmetic in libccab200.
+
+torch is used for device memory (the caching allocator owns every buffer, including workspaces) and
+for the current stream -- nothing else.  Every function fails loudly when called without CUDA.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.F32, torch.float64: _lib.F64}
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name} must be a CUDA tensor: cca_zoo_b200 runs on sm_100a only and has no CPU fallback"
+        )
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+
+
+def _row_major(t: torch.Tensor, tma: bool) -> torch.Tensor:
+    """2-D tensor with unit column stride (and, for TMA, 16-byte aligned rows)."""
+    if t.dim() != 2:
+        raise ValueError("expected a 2-D tensor")
+    ok = t.stride(1) == 1 and t.stride(0) >= t.shape[1]
+    if ok and tma:
+        ok = t.data_ptr() % 16 == 0 and (t.stride(0) * t.element_size()) % 16 == 0
+    if ok:
+        return t
+    if tma and (t.shape[1] * t.element_size()) % 16 != 0:
+        per = 16 // t.element_size()
+        ld = (t.shape[1] + per - 1) // per * per
+        buf = torch.zeros((t.shape[0], ld), dtype=t.dtype, device=t.device)
+        buf[:, : t.shape[1]] = t
+        return buf[:, : t.shape[1]]
+    return t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# K1 / K2
+# --------------------------------------------------------------------------------------------------
+def moments(views, precision: str = "tf32x3") -> torch.Tensor:
+    """Block moments of the row shard held in ``views`` (list of (n, d_i) CUDA tensors, same dtype).
+
+    Returns the additive double buffer ``[Dp*Dp + Dp]`` (see ccab_moments in include/ccab200.h).
+    precision: "tf32" | "tf32x3" | "exact" (float64 views always use "exact").
+    """
+    lib = _lib.load()
+    if not (1 <= len(views) <= _lib.MAX_VIEWS):
+        raise ValueError(f"between 1 and {_lib.MAX_VIEWS} views are supported, got {len(views)}")
+    dt = views[0].dtype
+    for v in views:
+        _require_cuda(v, "view")
+        if v.dtype != dt or v.dtype not in _DT:
+            raise ValueError("views must share one dtype (float32 or float64)")
+        if v.shape[0] != views[0].shape[0]:
+            raise ValueError("All views must have the same number of samples.")
+    prec = {"tf32": _lib.PREC_TF32, "tf32x3": _lib.PREC_TF32X3, "exact": _lib.PREC_EXACT}[precision]
+    if dt == torch.float64:
+        prec = _lib.PREC_EXACT
+    vs = [_row_major(v, tma=prec != _lib.PREC_EXACT) for v in views]
+    n = vs[0].shape[0]
+    dims = _lib.i64_array([v.shape[1] for v in vs])
+    lds = _lib.i64_array([v.stride(0) for v in vs])
+    ptrs = (C.c_void_p * len(vs))(*[v.data_ptr() for v in vs])
+    dev = vs[0].device
+    size = lib.ccab_moments_size(len(vs), dims)
+    if size < 0:
+        raise ValueError(_lib.last_error())
+    out = torch.empty(size, dtype=torch.float64, device=dev)
+    wsb = lib.ccab_moments_workspace_bytes(_DT[dt], prec, len(vs), dims, n)
+    ws = _ws(wsb, dev)
+    with torch.cuda.device(dev):
+        rc = lib.ccab_moments(_DT[dt], prec, len(vs), ptrs, dims, lds, n, _ptr(out), _ptr(ws), ws.numel(), _stream(out))
+    _lib.check(rc, "ccab_moments")
+    return out
+
+
+def covariance(mom: torch.Tensor, dims, n_total: float, center: bool = True, dtype=torch.float64):
+    """(C [D,D], mean [D]) from an (all-reduced) moments buffer."""
+    lib = _lib.load()
+    _require_cuda(mom, "moments")
+    D = int(sum(dims))
+    Cm = torch.empty((D, D), dtype=dtype, device=mom.device)
+    mean = torch.empty(D, dtype=dtype, device=mom.device)
+    with torch.cuda.device(mom.device):
+        rc = lib.ccab_covariance(_DT[dtype], len(dims), _lib.i64_array(dims), _ptr(mom), float(n_total),
+                                 1 if center else 0, _ptr(Cm), D, _ptr(mean), _stream(mom))
+    _lib.check(rc, "ccab_covariance")
+    return Cm, mean
+
+
+# --------------------------------------------------------------------------------------------------
+# K3 / K4
+# --------------------------------------------------------------------------------------------------
+def syevj(A: torch.Tensor, shift: float = 0.0, return_info: bool = False):
+    """Symmetric eigendecomposition.  A: (n,n) or (batch,n,n).  Returns (evals desc, evecs_t) where
+    evecs_t[..., j, :] is the j-th eigenvector."""
+    lib = _lib.load()
+    _require_cuda(A, "A")
+    squeeze = A.dim() == 2
+    Ab = (A.unsqueeze(0) if squeeze else A).contiguous()
+    batch, n, n2 = Ab.shape
+    if n != n2:
+        raise ValueError("square matrices expected")
+    dt = _DT[Ab.dtype]
+    evals = torch.empty((batch, n), dtype=Ab.dtype, device=Ab.device)
+    evt = torch.empty((batch, n, n), dtype=Ab.dtype, device=Ab.device)
+    ws = _ws(lib.ccab_syevj_workspace_bytes(dt, n, batch), Ab.device)
+    info = C.c_int(0)
+    off = C.c_float(0)
+    with torch.cuda.device(Ab.device):
+        rc = lib.ccab_syevj(dt, n, batch, _ptr(Ab), n, n * n, float(shift), _ptr(evals), _ptr(evt), n,
+                            C.byref(info), C.byref(off), _ptr(ws), ws.numel(), _stream(Ab))
+    _lib.check(rc, "ccab_syevj")
+    if squeeze:
+        evals, evt = evals[0], evt[0]
+    if return_info:
+        return evals, evt, {"sweeps": info.value, "offdiag": off.value}
+    return evals, evt
+
+
+def gesvj(Gt: torch.Tensor, return_info: bool = False):
+    """SVD of G (m x n) given as its transpose ``Gt`` (n x m, row-major: row j = column j of G).
+
+    Returns (sigma [n] desc, right_t [n,n] rows = right singular vectors of G,
+             left_t [n,m] rows = left singular vectors of G)."""
+    lib = _lib.load()
+    _require_cuda(Gt, "Gt")
+    Gt = Gt.contiguous()
+    n, m = Gt.shape
+    dt = _DT[Gt.dtype]
+    sigma = torch.empty(n, dtype=Gt.dtype, device=Gt.device)
+    right = torch.empty((n, n), dtype=Gt.dtype, device=Gt.device)
+    left = torch.zeros((n, m), dtype=Gt.dtype, device=Gt.device)
+    ws = _ws(lib.ccab_gesvj_workspace_bytes(dt, m, n), Gt.device)
+    info = C.c_int(0)
+    off = C.c_float(0)
+    with torch.cuda.device(Gt.device):
+        rc = lib.ccab_gesvj(dt, m, n, _ptr(Gt), m, _ptr(sigma), _ptr(right), n, _ptr(left), m, C.byref(info),
+                            C.byref(off), _ptr(ws), ws.numel(), _stream(Gt))
+    _lib.check(rc, "ccab_gesvj")
+    if return_info:
+        return sigma, right, left, {"sweeps": info.value, "offdiag": off.value}
+    return sigma, right, left
+
+
+# --------------------------------------------------------------------------------------------------
+# dense glue
+# --------------------------------------------------------------------------------------------------
+def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, out=None):
+    """out = alpha * op(A) @ op(B) + beta * out  (row-major views with unit inner stride)."""
+    lib = _lib.load()
+    _require_cuda(A, "A")
+    _require_cuda(B, "B")
+    A = _row_major(A, False)
+    B = _row_major(B, False)
+    m, k = (A.shape[1], A.shape[0]) if transa else A.shape
+    k2, n = (B.shape[1], B.shape[0]) if transb else B.shape
+    if k != k2:
+        raise ValueError(f"gemm inner dimensions differ: {k} vs {k2}")
+    if out is None:
+        out = torch.empty((m, n), dtype=A.dtype, device=A.device)
+        beta = 0.0
+    with torch.cuda.device(A.device):
+        rc = lib.ccab_gemm(_DT[A.dtype], int(transa), int(transb), m, n, k, float(alpha), _ptr(A), A.stride(0),
+                           _ptr(B), B.stride(0), float(beta), _ptr(out), out.stride(0), _stream(A))
+    _lib.check(rc, "ccab_gemm")
+    return out
+
+
+def whiten_rows(lam, Vt, c, floor_add=0.0, floor_dev=None, scale=1.0, rank_tol=0.0, max_rank=None):
+    """(Wt, g, rank_dev) -- see ccab_whiten_rows."""
+    lib = _lib.load()
+    _require_cuda(Vt, "Vt")
+    d = Vt.shape[0]
+    Wt = torch.empty_like(Vt)
+    g = torch.empty(d, dtype=Vt.dtype, device=Vt.device)
+    rank = torch.zeros(1, dtype=torch.int32, device=Vt.device)
+    with torch.cuda.device(Vt.device):
+        rc = lib.ccab_whiten_rows(_DT[Vt.dtype], d, _ptr(lam), _ptr(Vt), Vt.stride(0), float(c), float(floor_add),
+                                  _ptr(floor_dev), float(scale), float(rank_tol),
+                                  int(d if max_rank is None else max_rank), _ptr(Wt), Wt.stride(0), _ptr(g),
+                                  _ptr(rank), _stream(Vt))
+    _lib.check(rc, "ccab_whiten_rows")
+    return Wt, g, rank
+
+
+def frobenius_norm(A):
+    lib = _lib.load()
+    _require_cuda(A, "A")
+    A = _row_major(A, False)
+    out = torch.empty(1, dtype=A.dtype, device=A.device)
+    with torch.cuda.device(A.device):
+        rc = lib.ccab_frobenius_norm(_DT[A.dtype], A.shape[0], A.shape[1], _ptr(A), A.stride(0), _ptr(out), _stream(A))
+    _lib.check(rc, "ccab_frobenius_norm")
+    return out
+
+
+def debug_set(key: str, value: int) -> None:
+    _lib.check(_lib.load().ccab_debug_set(key.encode(), int(value)), "ccab_debug_set")

@@ -1,0 +1,122 @@
+/* libccab200 -- C ABI of the B200-native CCA hot path.
+ *
+ * The reference (jameschapman19/cca_zoo) is pure Python and has NO FFI boundary for this path
+ * (SURVEY.md §8b); this header is the boundary a maintainer would bind with ctypes (see
+ * INTEGRATION.md).  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - every pointer marked "device" is a CUDA device pointer owned by the caller (PyTorch's caching
+ *     allocator in the Python binding); the library never allocates device memory, the caller passes
+ *     a workspace sized by the matching *_workspace_bytes call;
+ *   - matrices are row-major with an explicit leading dimension unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it, except ccab_syevj /
+ *     ccab_gesvj which synchronise it once per Jacobi sweep to read the convergence flag;
+ *   - return 0 = OK, <0 = bad argument / unsupported, >0 = cudaError_t.  ccab_last_error() gives the
+ *     message of the last failure on the calling thread.  No C++ exception crosses the ABI.
+ *   - dtype: CCAB_F32 / CCAB_F64.  There is no CPU fallback: without a sm_100a device every compute
+ *     entry point fails.
+ */
+#ifndef CCAB200_H
+#define CCAB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCAB_F32 0
+#define CCAB_F64 1
+
+/* arithmetic of the moment kernel (ccab_moments `precision`) */
+#define CCAB_PREC_TF32 0   /* fp32 in, one tcgen05 kind::tf32 pass, fp32 accumulate               */
+#define CCAB_PREC_TF32X3 1 /* fp32 in, hi/lo split + 3 tcgen05 passes: fp32-grade accuracy          */
+#define CCAB_PREC_EXACT 2  /* FMA in the input dtype on CUDA cores (the only choice for CCAB_F64)  */
+
+#define CCAB_MAX_VIEWS 8
+
+int ccab_version(void);
+const char* ccab_last_error(void);
+
+/* ---- K1: block moments --------------------------------------------------------------------------
+ * M = [X_1 .. X_m]^T [X_1 .. X_m] and s = 1^T [X_1 .. X_m] over the n_rows samples this process
+ * holds.  Output `moments` (device, double) has ccab_moments_size() entries: a Dp x Dp padded matrix
+ * (each view padded to a multiple of 128 columns; only the upper block triangle is meaningful, the rest
+ * is zero) followed by the Dp column sums.  The buffer is additive over row shards: all-reduce(sum) it
+ * across ranks before ccab_covariance.
+ * Replaces: np.linalg.svd(X) cca_zoo/_utils/_linalg.py:28, X1_w.T @ X2_w cca_zoo/linear/_rcca.py:96,
+ * np.cov(...) cca_zoo/linear/_mcca.py:150-152,166 and cca_zoo/linear/_gcca.py:101,
+ * z.T @ z cca_zoo/deep/objectives.py:86-92; the column sums replace v.mean(axis=0) cca_zoo/_base.py:97.
+ * views[v]: device pointer to an n_rows x dims[v] row-major array with leading dimension lds[v]
+ * (TF32 paths need 16-byte aligned pointers and lds[v] % 4 == 0). */
+int64_t ccab_moments_size(int n_views, const int64_t* dims);
+int64_t ccab_moments_padded_dim(int n_views, const int64_t* dims);
+size_t ccab_moments_workspace_bytes(int dtype, int precision, int n_views, const int64_t* dims, int64_t n_rows);
+int ccab_moments(int dtype, int precision, int n_views, const void* const* views, const int64_t* dims,
+                 const int64_t* lds, int64_t n_rows, double* moments, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
+/* ---- K2: covariance from (all-reduced) moments ---------------------------------------------------
+ * C = (M - s s^T / n_total) / (n_total - 1) (center != 0) or M / (n_total - 1), compact D x D
+ * (D = sum dims, hstack order), full symmetric, in out_dtype; mean = s / n_total (or 0).
+ * Replaces: the centring of cca_zoo/_base.py:96-99 plus the 1/(n-1) scalings listed above. */
+int ccab_covariance(int out_dtype, int n_views, const int64_t* dims, const double* moments, double n_total,
+                    int center, void* C, int64_t ldc, void* mean, void* stream);
+
+/* ---- K3: batched symmetric eigensolver (one-sided block Jacobi) ----------------------------------
+ * For each of `batch` symmetric n x n matrices A_b (device, row-major == column-major, lda, stride
+ * batch_stride elements): eigenvalues descending into evals[b*n ..], eigenvectors as ROWS of
+ * evecs_t[b] (n x n, ldv): evecs_t[b][j,:] is the unit eigenvector of the j-th largest eigenvalue.
+ * `shift` is added to the diagonal before solving and removed from the eigenvalues afterwards; pass a
+ * value >= -lambda_min for indefinite matrices (the one-sided method needs A + shift*I to be PSD to
+ * separate +/- pairs).  info[0] (host, may be NULL) = sweeps used, info_offdiag (host, may be NULL) =
+ * last normalised off-diagonal.
+ * Replaces: scipy.linalg.eigh cca_zoo/_utils/_linalg.py:64-71, np.linalg.eigvalsh
+ * cca_zoo/linear/_mcca.py:170,194 cca_zoo/linear/_gcca.py:102, sklearn PCA cca_zoo/linear/_mcca.py:117,
+ * torch.linalg.eigh cca_zoo/deep/objectives.py:19, and (via covariance form) the tall SVD of
+ * cca_zoo/_utils/_linalg.py:28. */
+size_t ccab_syevj_workspace_bytes(int dtype, int n, int batch);
+int ccab_syevj(int dtype, int n, int batch, const void* A, int64_t lda, int64_t batch_stride, double shift,
+               void* evals, void* evecs_t, int64_t ldv, int* info, float* info_offdiag, void* workspace,
+               size_t workspace_bytes, void* stream);
+
+/* ---- K4: singular value decomposition (one-sided Jacobi) -----------------------------------------
+ * G is m x n given by COLUMNS: column j is the contiguous array A + j*lda (length m) -- i.e. a
+ * row-major n x m buffer holds G^T.  Outputs (descending): sigma[n]; right_t (n x n, ldr): row j =
+ * j-th right singular vector; left_t (n x m, ldl): row j = j-th left singular vector (unit, length m;
+ * zero for sigma_j = 0).  Any output may be NULL.
+ * Replaces: np.linalg.svd(cross_cov) cca_zoo/linear/_rcca.py:97. */
+size_t ccab_gesvj_workspace_bytes(int dtype, int m, int n);
+int ccab_gesvj(int dtype, int m, int n, const void* A, int64_t lda, void* sigma, void* right_t, int64_t ldr,
+               void* left_t, int64_t ldl, int* info, float* info_offdiag, void* workspace, size_t workspace_bytes,
+               void* stream);
+
+/* ---- dense glue ----------------------------------------------------------------------------------
+ * C (m x n) = alpha * op(A) * op(B) + beta * C, row-major; transX != 0 means op(X) = X^T.
+ * Replaces the small products W1^T C12 W2, W @ U (cca_zoo/linear/_rcca.py:96,100), components_.T @ w
+ * (cca_zoo/linear/_mcca.py:131) and the S11^-1/2 S12 S22^-1/2 chain (cca_zoo/deep/objectives.py:97). */
+int ccab_gemm(int dtype, int transa, int transb, int m, int n, int k, double alpha, const void* A, int64_t lda,
+              const void* B, int64_t ldb, double beta, void* C, int64_t ldc, void* stream);
+
+/* Whitening rows from an eigendecomposition (covariance form of svd_whiten,
+ * cca_zoo/_utils/_linalg.py:30-38; also B^-1/2 of cca_zoo/linear/_mcca.py:163-173 and R_i of
+ * cca_zoo/linear/_gcca.py:101-105):
+ *   keep_j  = lam[j] > rank_tol * max(lam[0],0)  &&  j < max_rank
+ *   g_j     = keep_j ? ((1-c)*lam[j] + c + floor_add + (floor_dev ? *floor_dev : 0))^-1/2 * scale^-1/2 : 0
+ *   Wt[j,:] = g_j * Vt[j,:]            g_out[j] = g_j (may be NULL)      *rank_out = #kept (device int) */
+int ccab_whiten_rows(int dtype, int d, const void* lam, const void* Vt, int64_t ldv, double c, double floor_add,
+                     const void* floor_dev, double scale, double rank_tol, int max_rank, void* Wt, int64_t ldw,
+                     void* g_out, int* rank_out, void* stream);
+
+/* out[0] (device) = ||A||_F of an m x n row-major matrix */
+int ccab_frobenius_norm(int dtype, int m, int n, const void* A, int64_t lda, void* out, void* stream);
+
+/* Debug/tuning knobs of the tcgen05 kernel ("lbo_bytes", "sbo_bytes", "tma_dtype", "force_splits");
+ * value < 0 restores the default.  Not part of the stable surface. */
+int ccab_debug_set(const char* key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCAB200_H */

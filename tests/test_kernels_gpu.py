@@ -1,0 +1,184 @@
+"""GPU parity tests of the individual kernels (through the C ABI) against float64 numpy/torch.
+
+Tolerances are stated per test: exact / fp64 paths at round-off, TF32 at its 2^-11 input rounding,
+3xTF32 at fp32 grade.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _views(n, dims, dtype, seed=0, mean=0.0):
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(n, 4, generator=g, dtype=torch.float64)
+    out = []
+    for d in dims:
+        a = torch.randn(4, d, generator=g, dtype=torch.float64)
+        out.append((z @ a + torch.randn(n, d, generator=g, dtype=torch.float64) + mean).to(dtype))
+    return out
+
+
+def _ref_cov(views, center=True):
+    X = torch.cat([v.double() for v in views], dim=1).cpu().numpy()
+    n = X.shape[0]
+    if center:
+        X = X - X.mean(axis=0)
+    return X.T @ X / (n - 1)
+
+
+@pytest.mark.parametrize("precision,dtype,rtol", [
+    ("exact", torch.float64, 1e-12),
+    ("exact", torch.float32, 2e-5),
+    ("tf32x3", torch.float32, 2e-5),
+    ("tf32", torch.float32, 3e-3),
+])
+@pytest.mark.parametrize("n,dims", [
+    (200, [50, 50]),          # BASELINE config 1 shape
+    (1000, [128, 128]),
+    (777, [10, 8, 6]),        # ragged views, n not a multiple of the chunk
+    (4096, [300, 130]),       # views straddling 128-blocks
+    (33, [5, 7]),             # tiny
+])
+def test_moments_and_covariance(precision, dtype, rtol, n, dims):
+    from cca_zoo_b200 import ops
+
+    views = [v.cuda() for v in _views(n, dims, dtype, seed=n)]
+    mom = ops.moments(views, precision=precision)
+    Cm, mean = ops.covariance(mom, dims, n, center=True, dtype=torch.float64)
+    ref = _ref_cov(views)
+    scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+    err = np.abs(Cm.cpu().numpy() - ref) / scale
+    assert err.max() < rtol, f"max normalised covariance error {err.max():.3e}"
+    assert torch.equal(Cm, Cm.T), "covariance must be exactly symmetric"
+    ref_mean = torch.cat([v.double() for v in views], dim=1).mean(dim=0)
+    mtol = 1e-12 if dtype == torch.float64 else (3e-3 if precision == "tf32" else 1e-5)
+    assert (mean.cpu() - ref_mean.cpu()).abs().max() < mtol * (1 + ref_mean.abs().max())
+
+
+def test_moments_uncentred_and_nonzero_mean():
+    from cca_zoo_b200 import ops
+
+    views = [v.cuda() for v in _views(2000, [40, 24], torch.float64, seed=3, mean=5.0)]
+    mom = ops.moments(views, precision="exact")
+    C0, mean0 = ops.covariance(mom, [40, 24], 2000, center=False)
+    X = torch.cat(views, dim=1).cpu().numpy()
+    np.testing.assert_allclose(C0.cpu().numpy(), X.T @ X / 1999, rtol=1e-12)
+    assert float(mean0.abs().max()) == 0.0
+    C1, _ = ops.covariance(mom, [40, 24], 2000, center=True)
+    np.testing.assert_allclose(C1.cpu().numpy(), _ref_cov(views), rtol=1e-9, atol=1e-9)
+
+
+def test_moments_are_additive_over_row_shards():
+    """The multi-GPU contract: moments of row shards sum to the moments of the whole."""
+    from cca_zoo_b200 import ops
+
+    views = [v.cuda() for v in _views(3000, [96, 80], torch.float32, seed=5)]
+    whole = ops.moments(views, precision="tf32x3")
+    parts = ops.moments([v[:1700] for v in views], precision="tf32x3") + ops.moments(
+        [v[1700:] for v in views], precision="tf32x3")
+    Cw, _ = ops.covariance(whole, [96, 80], 3000)
+    Cp, _ = ops.covariance(parts, [96, 80], 3000)
+    assert (Cw - Cp).abs().max() < 1e-5 * Cw.abs().max()
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-11), (torch.float32, 2e-4)])
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+def test_gemm(dtype, tol, ta, tb):
+    from cca_zoo_b200 import ops
+
+    g = torch.Generator().manual_seed(1)
+    m, n, k = 70, 130, 45
+    A = torch.randn((k, m) if ta else (m, k), generator=g, dtype=torch.float64)
+    B = torch.randn((n, k) if tb else (k, n), generator=g, dtype=torch.float64)
+    ref = (A.T if ta else A) @ (B.T if tb else B)
+    out = ops.gemm(A.to(dtype).cuda(), B.to(dtype).cuda(), transa=ta, transb=tb)
+    assert (out.double().cpu() - ref).abs().max() < tol * ref.abs().max() * 10
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 5e-6)])
+@pytest.mark.parametrize("n", [8, 32, 50, 64, 100, 256])
+def test_syevj_psd(dtype, tol, n):
+    """A v = lambda v, orthonormal rows, descending order (tests/test_linalg.py:122-141 of the reference)."""
+    from cca_zoo_b200 import ops
+
+    g = torch.Generator().manual_seed(n)
+    X = torch.randn(3 * n, n, generator=g, dtype=torch.float64)
+    A = (X.T @ X / (3 * n)).to(dtype)
+    ev, Vt = ops.syevj(A.cuda())
+    ev, Vt = ev.double().cpu(), Vt.double().cpu()
+    A64 = A.double()
+    ref = torch.linalg.eigvalsh(A64).flip(0)
+    assert torch.all(ev[:-1] >= ev[1:])
+    assert (ev - ref).abs().max() < tol * ref.abs().max() * 20
+    assert (Vt @ Vt.T - torch.eye(n, dtype=torch.float64)).abs().max() < tol * 50
+    resid = A64 @ Vt.T - Vt.T * ev
+    assert resid.abs().max() < tol * ref.abs().max() * 50
+
+
+def test_syevj_batched_and_indefinite_with_shift():
+    from cca_zoo_b200 import ops
+
+    g = torch.Generator().manual_seed(7)
+    T = torch.randn(20, 12, generator=g, dtype=torch.float64) * 0.3
+    K = torch.zeros(32, 32, dtype=torch.float64)          # Jordan-Wielandt: eigenvalues +-sigma
+    K[:20, 20:] = T
+    K[20:, :20] = T.T
+    S = torch.randn(32, 32, generator=g, dtype=torch.float64)
+    S = (S + S.T) / 2
+    A = torch.stack([K, S]).cuda()
+    shift = float(max(torch.linalg.matrix_norm(K), torch.linalg.matrix_norm(S)))
+    ev, Vt = ops.syevj(A, shift=shift)
+    for b, M in enumerate([K, S]):
+        ref = torch.linalg.eigvalsh(M).flip(0)
+        np.testing.assert_allclose(ev[b].cpu().numpy(), ref.numpy(), atol=1e-11)
+        V = Vt[b].cpu()
+        assert (M @ V.T - V.T * ev[b].cpu()).abs().max() < 1e-10
+    sv = torch.linalg.svdvals(T)
+    np.testing.assert_allclose(ev[0, :12].cpu().numpy(), sv.numpy(), atol=1e-11)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 5e-6)])
+@pytest.mark.parametrize("m,n", [(40, 24), (24, 40), (96, 96), (130, 70)])
+def test_gesvj(dtype, tol, m, n):
+    from cca_zoo_b200 import ops
+
+    g = torch.Generator().manual_seed(m * n)
+    G = torch.randn(m, n, generator=g, dtype=torch.float64)
+    sig, Rt, Lt = ops.gesvj(G.T.contiguous().to(dtype).cuda())
+    sig, Rt, Lt = sig.double().cpu(), Rt.double().cpu(), Lt.double().cpu()
+    G = G.to(dtype).double()
+    ref = torch.linalg.svdvals(G)
+    r = min(m, n)
+    assert (sig[:r] - ref).abs().max() < tol * ref.max() * 20
+    if n > m:
+        assert sig[m:].abs().max() < tol * ref.max() * 50
+    recon = (Lt[:r].T * sig[:r]) @ Rt[:r]
+    assert (recon - G).abs().max() < tol * ref.max() * 50
+    assert (Rt @ Rt.T - torch.eye(n, dtype=torch.float64)).abs().max() < tol * 50
+
+
+def test_whiten_rows_matches_definition():
+    from cca_zoo_b200 import ops
+
+    g = torch.Generator().manual_seed(2)
+    X = torch.randn(200, 16, generator=g, dtype=torch.float64)
+    Cm = (X.T @ X / 199).cuda()
+    lam, Vt = ops.syevj(Cm)
+    Wt, gv, rank = ops.whiten_rows(lam, Vt, c=0.2)
+    W = Wt.T.cpu()
+    reg = 0.8 * Cm.cpu() + 0.2 * torch.eye(16, dtype=torch.float64)
+    assert (W.T @ reg @ W - torch.eye(16, dtype=torch.float64)).abs().max() < 1e-10
+    assert int(rank.item()) == 16
+
+
+def test_argument_errors_are_loud():
+    from cca_zoo_b200 import ops
+
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.moments([torch.zeros(4, 4), torch.zeros(4, 4)])
+    with pytest.raises(ValueError):
+        ops.moments([torch.zeros(4, 4, device="cuda"), torch.zeros(5, 4, device="cuda")])
+    with pytest.raises(ValueError):
+        ops.gemm(torch.zeros(4, 5, device="cuda"), torch.zeros(4, 5, device="cuda"))
