@@ -1,0 +1,181 @@
+"""Base class of the B200 estimators: the reference's sklearn surface (cca_zoo/_base.py:19-258) with
+the fit-time arithmetic moved to the GPU.
+
+Drop-in contract kept from the reference:
+  * ``__init__`` only stores keyword arguments (sklearn ``clone`` / ``get_params`` work);
+  * ``fit(views, y=None) -> self`` sets ``weights_`` (list of ``(d_i, k)`` numpy arrays),
+    ``means_``, ``n_views_``, ``n_features_in_``, ``n_samples_`` (_base.py:94-101);
+  * ``transform / fit_transform / score / pairwise_correlations / average_pairwise_correlations /
+    get_factor_loadings / weights`` behave as in the reference (numpy in, numpy out);
+  * parameter constraints are validated at ``fit`` time with sklearn's machinery
+    (``InvalidParameterError``), view errors are ``ValueError`` with the reference's messages.
+
+Added (all defaulting to reference behaviour): ``precision`` selects the arithmetic of the
+covariance kernel for float32 inputs, ``device`` the CUDA device.  Inputs may also be torch tensors
+(CPU or CUDA); CUDA tensors are consumed in place, without a host round trip.  When
+``torch.distributed`` is initialised with more than one rank, ``fit`` treats the views as this
+rank's ROW SHARD and all-reduces the moments.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from numbers import Integral
+from typing import Any, ClassVar
+
+import numpy as np
+import torch
+from sklearn.base import BaseEstimator
+from sklearn.utils._param_validation import Interval, StrOptions
+from sklearn.utils.validation import check_is_fitted
+
+from . import ops, parallel
+from ._validation import validate_views
+
+
+class BaseModel(BaseEstimator, ABC):
+    """Abstract base of all estimators (mirrors cca_zoo._base.BaseModel)."""
+
+    _parameter_constraints: ClassVar[dict[str, list[Any]]] = {
+        "latent_dimensions": [Interval(Integral, 1, None, closed="left")],
+        "center": ["boolean"],
+        "precision": [StrOptions({"tf32", "tf32x3", "exact"})],
+        "device": [None, str, int, torch.device],
+    }
+
+    #: dtype of the eigen-stage for float32 inputs: the reference keeps float32 in rCCA
+    #: (numpy SVD) but upcasts to float64 in MCCA/GCCA (np.cov), see SURVEY.md §7.3-7.
+    _solve_in_float64: ClassVar[bool] = False
+
+    def __init__(self, latent_dimensions: int = 1, center: bool = True, precision: str = "tf32x3",
+                 device=None) -> None:
+        self.latent_dimensions = latent_dimensions
+        self.center = center
+        self.precision = precision
+        self.device = device
+
+    # ------------------------------------------------------------------ abstract
+    @abstractmethod
+    def fit(self, views, y=None):
+        """Fit the model to multiview data (list of ``(n_samples, n_features_i)`` arrays)."""
+
+    @abstractmethod
+    def _solve(self, C: torch.Tensor, dims: list[int], n_total: int) -> list[torch.Tensor]:
+        """Weights from the block covariance (device tensors)."""
+
+    # ------------------------------------------------------------------ fit plumbing
+    def _device(self) -> torch.device:
+        if not torch.cuda.is_available():
+            raise RuntimeError(
+                "cca_zoo_b200 needs a CUDA device (sm_100a); there is no CPU fallback.  "
+                "Use the reference cca_zoo package on CPU-only machines."
+            )
+        if self.device is None:
+            return torch.device("cuda", torch.cuda.current_device())
+        return torch.device(self.device)
+
+    def _to_device(self, v, device):
+        if isinstance(v, torch.Tensor):
+            t = v
+        else:
+            arr = np.asarray(v)
+            if arr.dtype not in (np.float32, np.float64):
+                arr = arr.astype(np.float64)
+            t = torch.from_numpy(np.ascontiguousarray(arr))
+        if t.dtype not in (torch.float32, torch.float64):
+            t = t.to(torch.float64)
+        return t.to(device, non_blocking=True)
+
+    def _fit_device(self, views, min_views: int = 2):
+        """_setup_fit (cca_zoo/_base.py:78-102) + the covariance stage.  Returns (C, dims, n_total)."""
+        self._validate_params()
+        validated = validate_views(views, min_views)
+        device = self._device()
+        dev_views = [self._to_device(v, device) for v in validated]
+        if len({v.dtype for v in dev_views}) > 1:
+            dev_views = [v.to(torch.float64) for v in dev_views]
+        in_dtype = dev_views[0].dtype
+        dims = [int(v.shape[1]) for v in dev_views]
+        n_local = int(dev_views[0].shape[0])
+        mom = ops.moments(dev_views, precision=self.precision)
+        mom, n_total = parallel.allreduce_moments(mom, n_local)
+        solve_dtype = torch.float64 if (self._solve_in_float64 or in_dtype == torch.float64) else torch.float32
+        C, mean = ops.covariance(mom, dims, n_total, center=bool(self.center), dtype=solve_dtype)
+        self.n_views_ = len(dev_views)
+        self.n_features_in_ = dims
+        self.n_samples_ = n_total
+        off = np.concatenate([[0], np.cumsum(dims)]).astype(int)
+        mean_np = mean.to(torch.float64).cpu().numpy()
+        np_dtype = np.float32 if in_dtype == torch.float32 else np.float64
+        if self.center:
+            self.means_ = [mean_np[off[i]:off[i + 1]].astype(np_dtype) for i in range(len(dims))]
+        else:
+            self.means_ = [np.zeros(p) for p in dims]
+        return C, dims, n_total
+
+    def _finish(self, weights: list[torch.Tensor]):
+        self.weights_ = [w.cpu().numpy() for w in weights]
+        return self
+
+    # ------------------------------------------------------------------ public API (reference semantics)
+    @staticmethod
+    def _as_numpy_views(views):
+        out = []
+        for v in views:
+            out.append(v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v)
+        return out
+
+    def transform(self, views):
+        """Project views with the fitted weights (cca_zoo/_base.py:108-123)."""
+        check_is_fitted(self)
+        validated = validate_views(self._as_numpy_views(views))
+        centred = [v - m for v, m in zip(validated, self.means_)]
+        return [v @ w for v, w in zip(centred, self.weights_)]
+
+    def fit_transform(self, views, y=None):
+        return self.fit(views, y).transform(views)
+
+    def score(self, views, y=None):
+        """Average pairwise canonical correlations per dimension (cca_zoo/_base.py:140-151)."""
+        return self.average_pairwise_correlations(views)
+
+    def pairwise_correlations(self, views):
+        """(n_views, n_views, k) Pearson correlations of the variates (cca_zoo/_base.py:153-174)."""
+        transformed = self.transform(views)
+        T = np.stack(transformed, axis=0)
+        T = T - T.mean(axis=1, keepdims=True)
+        norms = np.sqrt((T**2).sum(axis=1, keepdims=True))
+        T_norm = T / np.where(norms > 1e-12, norms, 1.0)
+        return np.einsum("isd,jsd->ijd", T_norm, T_norm)
+
+    def average_pairwise_correlations(self, views):
+        """Mean off-diagonal pairwise correlation per dimension (cca_zoo/_base.py:176-194)."""
+        corrs = self.pairwise_correlations(views)
+        n_views = corrs.shape[0]
+        off_diag_sum = corrs.sum(axis=(0, 1)) - sum(corrs[i, i, :] for i in range(n_views))
+        return off_diag_sum / (n_views * (n_views - 1))
+
+    @property
+    def weights(self):
+        check_is_fitted(self)
+        return self.weights_
+
+    def get_factor_loadings(self, views):
+        """Feature/variate correlations (cca_zoo/_base.py:208-234)."""
+        validated = validate_views(self._as_numpy_views(views))
+        transformed = self.transform(views)
+        loadings = []
+        for v, t in zip(validated, transformed):
+            v_c = v - v.mean(axis=0)
+            t_c = t - t.mean(axis=0)
+            cov = v_c.T @ t_c / (v.shape[0] - 1)
+            std_v = np.maximum(v_c.std(axis=0, ddof=1), 1e-12)
+            std_t = np.maximum(t_c.std(axis=0, ddof=1), 1e-12)
+            loadings.append(cov / np.outer(std_v, std_t))
+        return loadings
+
+    def __sklearn_tags__(self):
+        tags = super().__sklearn_tags__()
+        tags.no_validation = True
+        tags.input_tags.two_d_array = False
+        tags._skip_test = True
+        return tags

@@ -38,7 +38,10 @@ SIGNATURES = {
     "ccab_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp, C.c_int64, _vp,
                             C.c_int64, C.c_double, _vp, C.c_int64, _vp]),
     "ccab_whiten_rows": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_double, C.c_double, _vp, C.c_double,
-                                   C.c_double, C.c_int, _vp, C.c_int64, _vp, _vp, _vp]),
+                                   C.c_double, C.c_int, C.c_double, _vp, C.c_int64, _vp, _vp, _vp]),
+    "ccab_scale": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int64,
+                             _vp]),
+    "ccab_center_columns": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp]),
     "ccab_frobenius_norm": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp]),
     "ccab_debug_set": (C.c_int, [C.c_char_p, C.c_int]),
 }

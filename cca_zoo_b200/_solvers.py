@@ -1,0 +1,137 @@
+"""Covariance-space solvers on the device (everything after the all-reduce; replicated per rank).
+
+Input: the compact block covariance ``C`` (D x D CUDA tensor) of the hstacked views.  All arithmetic
+runs in libccab200 kernels (Jacobi eigensolver / SVD, GEMM, scalings); torch supplies buffers, views
+and the handful of scalar read-backs (ranks, floors) that decide shapes on the host.
+Algebra: SURVEY.md §3.1-3.3, checked against the reference by oracle/restatement.py (cov_* forms).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def _slices(dims):
+    off = np.concatenate([[0], np.cumsum(dims)]).astype(int)
+    return [slice(int(off[i]), int(off[i + 1])) for i in range(len(dims))]
+
+
+def _eps(dtype):
+    return float(torch.finfo(dtype).eps)
+
+
+def _block_eigh(C, dims):
+    """Eigendecomposition of every diagonal block C_ii; equal-sized blocks go in one batched call."""
+    sl = _slices(dims)
+    lams, vts = [None] * len(dims), [None] * len(dims)
+    by_size = {}
+    for i, d in enumerate(dims):
+        by_size.setdefault(d, []).append(i)
+    for d, idx in by_size.items():
+        A = torch.stack([C[sl[i], sl[i]] for i in idx]).contiguous()
+        ev, evt = ops.syevj(A)
+        for b, i in enumerate(idx):
+            lams[i], vts[i] = ev[b], evt[b]
+    return lams, vts
+
+
+def rcca_weights(C, dims, n_samples, latent_dimensions, c):
+    """rCCA / CCA / PLS (cca_zoo/linear/_rcca.py:83-101 in covariance form).
+
+    C_ii = V_i L_i V_i^T ; Wt_i = diag(((1-c_i) L_i + c_i)^-1/2) V_i^T (directions with
+    lam <= tol*lam_max dropped = the reference's ``s > 0`` filter, _linalg.py:30) ;
+    T = Wt_1 C_12 Wt_2^T = U S V^T (one-sided Jacobi) ; weights = Wt_1^T U_k, Wt_2^T V_k.
+    """
+    s1, s2 = _slices(dims)
+    lams, vts = _block_eigh(C, dims)
+    wts, ranks = [], []
+    for i in range(2):
+        tol = max(dims[i], n_samples) * _eps(C.dtype)
+        Wt, _, rank = ops.whiten_rows(lams[i], vts[i], c[i], rank_tol=tol, max_rank=min(n_samples, dims[i]))
+        wts.append(Wt)
+        ranks.append(rank)
+    r1, r2 = (int(r.item()) for r in ranks)  # host read-back: decides k (_rcca.py:95)
+    k = min(latent_dimensions, r1, r2)
+    tmp = ops.gemm(wts[0], C[s1, s2])                 # (d1 x d2)
+    T = ops.gemm(tmp, wts[1], transb=True)            # (d1 x d2) in whitened coordinates
+    # gesvj factors G = T^T given by columns, i.e. the row-major buffer of T itself:
+    #   right vectors of G = left singular vectors U of T, left vectors of G = right singular vectors V of T
+    _, Ut, Vt = ops.gesvj(T)
+    w1 = ops.gemm(wts[0], Ut[:k], transa=True, transb=True)   # (d1 x k)
+    w2 = ops.gemm(wts[1], Vt[:k], transa=True, transb=True)   # (d2 x k)
+    return [w1, w2]
+
+
+def mcca_weights(C, dims, latent_dimensions, c, eps):
+    """MCCA (cca_zoo/linear/_mcca.py:113-135,141-173): top-k of A v = lam B v, v^T B v = 1 with
+    A = (C - blkdiag C_ii)/m, B = blkdiag((1-c_i) C_ii + c_i I)/m (+ eps floor).
+
+    With B_i = V_i diag(b_i) V_i^T and Wt_i = diag(b_i^-1/2) V_i^T the problem becomes the standard
+    symmetric one K y = lam y, K_ij = Wt_i A_ij Wt_j^T, v_i = Wt_i^T y_i.  K is indefinite (for two
+    views its spectrum is +-sigma), so it is solved shifted by ||K||_F to keep +-pairs apart.
+    """
+    m = len(dims)
+    sl = _slices(dims)
+    D = C.shape[0]
+    lams, vts = _block_eigh(C, dims)
+    # eps floor of _build_B (:170-172): lambda_min of the block-diagonal B is the min over blocks
+    min_eig = min(float(((1.0 - c[i]) * lams[i][-1] + c[i]).item()) for i in range(m))
+    floor = (eps - min_eig) if min_eig < eps else 0.0
+    wts = []
+    for i in range(m):
+        Wt, _, _ = ops.whiten_rows(lams[i], vts[i], c[i], floor_add=floor, scale=1.0 / m, rank_tol=-1.0)
+        wts.append(Wt)
+    K = torch.zeros((D, D), dtype=C.dtype, device=C.device)
+    for i in range(m):
+        for j in range(i + 1, m):
+            tmp = ops.gemm(wts[i], C[sl[i], sl[j]])
+            ops.gemm(tmp, wts[j], transb=True, alpha=1.0 / m, out=K[sl[i], sl[j]])
+            K[sl[j], sl[i]] = K[sl[i], sl[j]].T
+    shift = float(ops.frobenius_norm(K).item())
+    evals, evt = ops.syevj(K, shift=shift)
+    k = min(latent_dimensions, D)
+    return [ops.gemm(wts[i], evt[:k, sl[i]], transa=True, transb=True) for i in range(m)]
+
+
+def gcca_weights(C, dims, n_samples, latent_dimensions, c, mu, eps):
+    """GCCA in primal (D x D) form (cca_zoo/linear/_gcca.py:94-109).
+
+    reg_i = (1-c_i) L_i + c_i (+ per-view eps floor, :102-104) ; Wt_i = diag(sqrt(mu_i) reg_i^-1/2) V_i^T ;
+    G = (n-1) Wt C Wt^T (block-wise) ; top-k G u = sig u ;
+    W_i = pinv(C_ii) [C Wt^T u]_i sig^-1/2   (pinv from the same eigendecomposition).
+    """
+    m = len(dims)
+    sl = _slices(dims)
+    D = C.shape[0]
+    lams, vts = _block_eigh(C, dims)
+    wts = []
+    for i in range(m):
+        reg_min = float(((1.0 - c[i]) * lams[i][-1] + c[i]).item())
+        floor = (eps - reg_min) if reg_min < eps else 0.0
+        Wt, _, _ = ops.whiten_rows(lams[i], vts[i], c[i], floor_add=floor, scale=1.0 / mu[i], rank_tol=-1.0)
+        wts.append(Wt)
+    G = torch.empty((D, D), dtype=C.dtype, device=C.device)
+    for i in range(m):
+        for j in range(i, m):
+            tmp = ops.gemm(wts[i], C[sl[i], sl[j]])
+            ops.gemm(tmp, wts[j], transb=True, alpha=float(n_samples - 1), out=G[sl[i], sl[j]])
+            if j > i:
+                G[sl[j], sl[i]] = G[sl[i], sl[j]].T
+    sig, evt = ops.syevj(G)
+    k = min(latent_dimensions, D, n_samples)
+    # P = blkdiag(Wt_i^T) U_k   (D x k)
+    P = torch.empty((D, k), dtype=C.dtype, device=C.device)
+    for i in range(m):
+        ops.gemm(wts[i], evt[:k, sl[i]], transa=True, transb=True, out=P[sl[i]])
+    CP = ops.gemm(C, P)                                                   # (D x k)
+    out = []
+    for i in range(m):
+        tol = max(dims[i], n_samples) * _eps(C.dtype)
+        # pinv(C_ii) = V diag(1/lam | lam > tol lam_max) V^T  via whiten_rows with c=0 (g = lam^-1/2) twice
+        Pinv_half, _, _ = ops.whiten_rows(lams[i], vts[i], 0.0, rank_tol=tol)   # diag(lam^-1/2) V^T
+        t1 = ops.gemm(Pinv_half, CP[sl[i]])                                      # (d x k)
+        wi = ops.gemm(Pinv_half, t1, transa=True)                                # V lam^-1 V^T CP_i
+        out.append(ops.scale(wi, cols=sig[:k], cols_pow=-0.5))
+    return out

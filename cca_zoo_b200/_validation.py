@@ -1,0 +1,57 @@
+"""Input validation with the reference's semantics and error messages
+(cca_zoo/_utils/_validation.py:14-75), extended to accept torch tensors (CPU or CUDA)."""
+from __future__ import annotations
+
+from typing import TypeVar
+
+import numpy as np
+import torch
+from sklearn.utils.validation import check_array
+
+_T = TypeVar("_T")
+
+
+def validate_views(views, min_views: int = 2):
+    """Return a list of 2-D float arrays / tensors with equal row counts.
+
+    numpy / array-like inputs go through ``sklearn.utils.validation.check_array`` exactly as in the
+    reference (NaN/inf rejected, dtype kept); torch tensors are checked for shape and finiteness
+    and kept where they are (no host round trip for CUDA tensors).
+    """
+    if len(views) < min_views:
+        raise ValueError(f"At least {min_views} views are required, got {len(views)}.")
+    processed = []
+    for v in views:
+        if isinstance(v, torch.Tensor):
+            if v.dim() != 2:
+                raise ValueError(f"Expected 2D array, got {v.dim()}D tensor instead.")
+            if not v.dtype.is_floating_point:
+                v = v.to(torch.float64)
+            if v.numel() == 0:
+                raise ValueError("Found array with 0 sample(s) or 0 feature(s).")
+            if not bool(torch.isfinite(v).all()):
+                raise ValueError("Input contains NaN or infinity.")
+            processed.append(v)
+        else:
+            processed.append(check_array(v, ensure_2d=True, allow_nd=False, dtype="numeric"))
+    n = processed[0].shape[0]
+    if not all(v.shape[0] == n for v in processed):
+        raise ValueError(
+            "All views must have the same number of samples. "
+            f"Got shapes: {[tuple(v.shape) for v in processed]}."
+        )
+    return processed
+
+
+def perview_parameter(name: str, value, default, n_views: int):
+    """Broadcast a scalar / per-view list (cca_zoo/_utils/_validation.py:45-75)."""
+    if value is None:
+        return [default] * n_views
+    if isinstance(value, list):
+        if len(value) != n_views:
+            raise ValueError(
+                f"Parameter '{name}' must be a scalar or a list of length "
+                f"{n_views}, got length {len(value)}."
+            )
+        return value
+    return [value] * n_views

@@ -242,8 +242,8 @@ int ccab_gemm(int dtype, int transa, int transb, int m, int n, int k, double alp
 }
 
 int ccab_whiten_rows(int dtype, int d, const void* lam, const void* Vt, int64_t ldv, double c, double floor_add,
-                     const void* floor_dev, double scale, double rank_tol, int max_rank, void* Wt, int64_t ldw,
-                     void* g_out, int* rank_out, void* stream) {
+                     const void* floor_dev, double scale, double rank_tol, int max_rank, double lam_floor, void* Wt,
+                     int64_t ldw, void* g_out, int* rank_out, void* stream) {
   CCAB_TRY
   CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
   CCAB_CHECK_ARG(lam && Vt && Wt, "null pointer argument");
@@ -253,11 +253,40 @@ int ccab_whiten_rows(int dtype, int d, const void* lam, const void* Vt, int64_t 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == CCAB_F32)
     return whiten_rows<float>(d, static_cast<const float*>(lam), static_cast<const float*>(Vt), ldv, c, floor_add,
-                              static_cast<const float*>(floor_dev), scale, rank_tol, max_rank,
+                              static_cast<const float*>(floor_dev), scale, rank_tol, max_rank, lam_floor,
                               static_cast<float*>(Wt), ldw, static_cast<float*>(g_out), rank_out, s);
   return whiten_rows<double>(d, static_cast<const double*>(lam), static_cast<const double*>(Vt), ldv, c, floor_add,
-                             static_cast<const double*>(floor_dev), scale, rank_tol, max_rank,
+                             static_cast<const double*>(floor_dev), scale, rank_tol, max_rank, lam_floor,
                              static_cast<double*>(Wt), ldw, static_cast<double*>(g_out), rank_out, s);
+  CCAB_CATCH
+}
+
+int ccab_scale(int dtype, int m, int n, const void* A, int64_t lda, const void* r, int r_pow, const void* c,
+               int c_pow, void* B, int64_t ldb, void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(A && B, "null pointer argument");
+  CCAB_CHECK_ARG(r_pow >= 0 && r_pow <= 2 && c_pow >= 0 && c_pow <= 2, "bad power code");
+  int rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CCAB_F32)
+    return scale_rows_cols<float>(m, n, static_cast<const float*>(A), lda, static_cast<const float*>(r), r_pow,
+                                  static_cast<const float*>(c), c_pow, static_cast<float*>(B), ldb, s);
+  return scale_rows_cols<double>(m, n, static_cast<const double*>(A), lda, static_cast<const double*>(r), r_pow,
+                                 static_cast<const double*>(c), c_pow, static_cast<double*>(B), ldb, s);
+  CCAB_CATCH
+}
+
+int ccab_center_columns(int dtype, int m, int n, void* A, int64_t lda, void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(A != nullptr, "null pointer argument");
+  int rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CCAB_F32) return center_columns<float>(m, n, static_cast<float*>(A), lda, s);
+  return center_columns<double>(m, n, static_cast<double*>(A), lda, s);
   CCAB_CATCH
 }
 
@@ -281,6 +310,7 @@ int ccab_debug_set(const char* key, int value) {
   else if (!strcmp(key, "sbo_bytes")) d.sbo_bytes = value;
   else if (!strcmp(key, "tma_dtype")) d.tma_dtype = value;
   else if (!strcmp(key, "force_splits")) d.force_splits = value;
+  else if (!strcmp(key, "jacobi_inner_sweeps")) jacobi_inner_sweeps() = value;
   else {
     set_error("unknown debug key %s", key);
     return -1;

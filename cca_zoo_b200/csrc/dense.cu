@@ -100,14 +100,14 @@ template int gemm<double>(int, int, int, int, int, double, const double*, int64_
 template <typename T>
 __global__ void whiten_rows_kernel(int d, const T* __restrict__ lam, const T* __restrict__ Vt, int64_t ldv, double c,
                                    double floor_add, const T* __restrict__ floor_dev, double scale, double rank_tol,
-                                   int max_rank, T* __restrict__ Wt, int64_t ldw, T* __restrict__ g_out,
+                                   int max_rank, double lam_floor, T* __restrict__ Wt, int64_t ldw, T* __restrict__ g_out,
                                    int* __restrict__ rank_out) {
   const int j = blockIdx.x;
   const double l0 = fmax((double)lam[0], 0.0);
   const double lj = (double)lam[j];
   const bool keep = (lj > rank_tol * l0) && (j < max_rank);
   const double fl = floor_add + (floor_dev ? (double)floor_dev[0] : 0.0);
-  const double g = keep ? 1.0 / sqrt(((1.0 - c) * lj + c + fl) * scale) : 0.0;
+  const double g = keep ? 1.0 / sqrt(((1.0 - c) * fmax(lj, lam_floor) + c + fl) * scale) : 0.0;
   for (int i = threadIdx.x; i < d; i += blockDim.x) Wt[(size_t)j * ldw + i] = (T)(g * (double)Vt[(size_t)j * ldv + i]);
   if (threadIdx.x == 0) {
     if (g_out) g_out[j] = (T)g;
@@ -117,19 +117,85 @@ __global__ void whiten_rows_kernel(int d, const T* __restrict__ lam, const T* __
 
 template <typename T>
 int whiten_rows(int d, const T* lam, const T* Vt, int64_t ldv, double c, double floor_add, const T* floor_dev,
-                double scale, double rank_tol, int max_rank, T* Wt, int64_t ldw, T* g_out, int* rank_out,
-                cudaStream_t stream) {
+                double scale, double rank_tol, int max_rank, double lam_floor, T* Wt, int64_t ldw, T* g_out,
+                int* rank_out, cudaStream_t stream) {
   CCAB_CHECK_ARG(d >= 1, "bad dimension");
   if (rank_out) CCAB_CUDA(cudaMemsetAsync(rank_out, 0, sizeof(int), stream));
   whiten_rows_kernel<T><<<d, 128, 0, stream>>>(d, lam, Vt, ldv, c, floor_add, floor_dev, scale, rank_tol, max_rank,
-                                               Wt, ldw, g_out, rank_out);
+                                               lam_floor, Wt, ldw, g_out, rank_out);
   CCAB_CUDA(cudaGetLastError());
   return 0;
 }
 template int whiten_rows<float>(int, const float*, const float*, int64_t, double, double, const float*, double, double,
-                                int, float*, int64_t, float*, int*, cudaStream_t);
+                                int, double, float*, int64_t, float*, int*, cudaStream_t);
 template int whiten_rows<double>(int, const double*, const double*, int64_t, double, double, const double*, double,
-                                 double, int, double*, int64_t, double*, int*, cudaStream_t);
+                                 double, int, double, double*, int64_t, double*, int*, cudaStream_t);
+
+template <typename T>
+__device__ __forceinline__ T pow_code(T v, int code) {
+  if (code == 1) return T(1) / v;
+  if (code == 2) return T(1) / sqrt(v);
+  return v;
+}
+
+template <typename T>
+__global__ void scale_kernel(int m, int n, const T* __restrict__ A, int64_t lda, const T* __restrict__ r, int r_pow,
+                             const T* __restrict__ c, int c_pow, T* __restrict__ B, int64_t ldb) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= n) return;
+  T f = T(1);
+  if (r) f *= pow_code(r[i], r_pow);
+  if (c) f *= pow_code(c[j], c_pow);
+  B[(size_t)i * ldb + j] = A[(size_t)i * lda + j] * f;
+}
+
+template <typename T>
+int scale_rows_cols(int m, int n, const T* A, int64_t lda, const T* r, int r_pow, const T* c, int c_pow, T* B,
+                    int64_t ldb, cudaStream_t stream) {
+  if (m == 0 || n == 0) return 0;
+  CCAB_CHECK_ARG(m <= 65535 * 1024, "too many rows");
+  scale_kernel<T><<<dim3((unsigned)ceil_div(n, 128), (unsigned)m), 128, 0, stream>>>(m, n, A, lda, r, r_pow, c, c_pow,
+                                                                                     B, ldb);
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+template int scale_rows_cols<float>(int, int, const float*, int64_t, const float*, int, const float*, int, float*,
+                                    int64_t, cudaStream_t);
+template int scale_rows_cols<double>(int, int, const double*, int64_t, const double*, int, const double*, int, double*,
+                                     int64_t, cudaStream_t);
+
+// one block per 32 columns; fixed-order reduction over rows (deterministic)
+template <typename T>
+__global__ void center_columns_kernel(int m, int n, T* __restrict__ A, int64_t lda) {
+  __shared__ double part[32][33];
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rg = threadIdx.x >> 5;  // 32 row groups
+  double acc = 0.0;
+  if (j < n)
+    for (int i = rg; i < m; i += 32) acc += (double)A[(size_t)i * lda + j];
+  part[rg][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (rg == 0) {
+    double s = 0.0;
+    for (int k = 0; k < 32; ++k) s += part[k][threadIdx.x & 31];
+    part[0][threadIdx.x & 31] = s / (double)m;
+  }
+  __syncthreads();
+  const T mu = (T)part[0][threadIdx.x & 31];
+  if (j < n)
+    for (int i = rg; i < m; i += 32) A[(size_t)i * lda + j] -= mu;
+}
+
+template <typename T>
+int center_columns(int m, int n, T* A, int64_t lda, cudaStream_t stream) {
+  if (m == 0 || n == 0) return 0;
+  center_columns_kernel<T><<<(unsigned)ceil_div(n, 32), 1024, 0, stream>>>(m, n, A, lda);
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+template int center_columns<float>(int, int, float*, int64_t, cudaStream_t);
+template int center_columns<double>(int, int, double*, int64_t, cudaStream_t);
 
 template <typename T>
 __global__ void frobenius_kernel(int m, int n, const T* __restrict__ A, int64_t lda, T* __restrict__ out) {

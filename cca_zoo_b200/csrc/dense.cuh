@@ -14,13 +14,23 @@ int gemm(int transa, int transb, int m, int n, int k, T alpha, const T* A, int64
 // Whitening factors from an eigendecomposition (covariance form of svd_whiten,
 // cca_zoo/_utils/_linalg.py:30-38):  for eigenpair j (descending, rows of Vt)
 //   keep_j = lam_j > rank_tol * lam_0  and  j < max_rank
-//   g_j    = keep_j ? 1 / sqrt(((1 - c) * lam_j + c + floor_add) * scale) : 0
+//   g_j    = keep_j ? 1 / sqrt(((1 - c) * max(lam_j, lam_floor) + c + floor_add) * scale) : 0
 //   Wt[j,:] = g_j * Vt[j,:]
 // and *rank_out = #kept.  `floor_dev` (may be null) points at a device scalar added to floor_add.
 template <typename T>
 int whiten_rows(int d, const T* lam, const T* Vt, int64_t ldv, double c, double floor_add, const T* floor_dev,
-                double scale, double rank_tol, int max_rank, T* Wt, int64_t ldw, T* g_out, int* rank_out,
-                cudaStream_t stream);
+                double scale, double rank_tol, int max_rank, double lam_floor, T* Wt, int64_t ldw, T* g_out,
+                int* rank_out, cudaStream_t stream);
+
+// B[i,j] = A[i,j] * (r ? r[i] : 1) * (c ? c[j] : 1), optionally c_pow/r_pow applied first:
+// factor = pow(value, pow) with pow in {1, -1, -0.5} encoded as 0, 1, 2.   (m x n row-major, in place ok)
+template <typename T>
+int scale_rows_cols(int m, int n, const T* A, int64_t lda, const T* r, int r_pow, const T* c, int c_pow, T* B,
+                    int64_t ldb, cudaStream_t stream);
+
+// A[:, j] -= mean_i A[i, j]   (m x n row-major, in place)
+template <typename T>
+int center_columns(int m, int n, T* A, int64_t lda, cudaStream_t stream);
 
 // out[0] = ||A||_F (m x n, row-major)
 template <typename T>

@@ -1,7 +1,7 @@
 // K1: block moments M = X^T X (+ column sums) of the hstacked views, upper block triangle only.
 //
 //   * moments_tf32_kernel : tcgen05.mma kind::tf32, both operands MN-major straight out of row-major X
-//     (TMA 128B-swizzled boxes of 32 columns x KC rows), fp32 accumulators in TMEM, warp-specialised
+//     (TMA boxes of 32 columns x KC rows, 128B rows swizzled in 32B chunks), fp32 accumulators in TMEM, warp-specialised
 //     (TMA producer / single-thread MMA issuer / 4 epilogue warps), split over the sample axis.
 //     Optional 3xTF32 (hi/lo split operands, 3 MMAs per k-step) for fp32-grade accuracy.
 //     Column sums ride on the same pipeline as one extra N=16 MMA against a block of ones.
@@ -68,6 +68,11 @@ static_assert(sizeof(TcParams) <= 4096, "kernel parameter space");
 constexpr int kTcThreads = 192;  // warp0 TMA, warp1 MMA, warps2-5 epilogue
 constexpr int kTcStages = 4;
 constexpr int kSumCol = 256;     // TMEM column of the column-sum accumulator (N = 16)
+// MN-major TF32 operands admit exactly one shared-memory layout: 128-byte rows swizzled in 32-byte
+// chunks (descriptor layout type 1 = SWIZZLE_128B_BASE32B, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+// Canonical form (16-byte units): ((8,n),(4,k)) : ((1,LBO),(8,SBO)) -- a 32-float row per reduction
+// index, 4-row groups SBO apart, 32-column atoms LBO apart.  Verified on hardware by tools/umma_unit.cu.
+constexpr uint32_t kUmmaLayout = 1;
 
 template <int KC, bool X3>
 struct TcCfg {
@@ -173,7 +178,7 @@ moments_tf32_kernel(const __grid_constant__ TcParams p) {
       const uint32_t idesc_main = umma_idesc_tf32_mn(128, N);
       const uint32_t idesc_sum = umma_idesc_tf32_mn(128, 16);
       const uint32_t lbo = p.lbo_bytes, sbo = p.sbo_bytes;
-      const uint64_t ones_desc = umma_smem_desc(smem_u32(ones), lbo, sbo, 2);
+      const uint64_t ones_desc = umma_smem_desc(smem_u32(ones), lbo, sbo, kUmmaLayout);
       int stage = 0;
       uint32_t phase = 0;
       for (int c = c0; c < c1; ++c) {
@@ -185,11 +190,11 @@ moments_tf32_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
           for (int kk = 0; kk < KC / 8; ++kk) {
             const uint32_t acc = (c > c0 || kk > 0) ? 1u : 0u;
-            const uint64_t a_hi = umma_smem_desc(sA + kk * 1024, lbo, sbo, 2);
-            const uint64_t b_hi = umma_smem_desc(sB + kk * 1024, lbo, sbo, 2);
+            const uint64_t a_hi = umma_smem_desc(sA + kk * 1024, lbo, sbo, kUmmaLayout);
+            const uint64_t b_hi = umma_smem_desc(sB + kk * 1024, lbo, sbo, kUmmaLayout);
             if (X3) {
-              const uint64_t a_lo = umma_smem_desc(sA + Cfg::kSet + kk * 1024, lbo, sbo, 2);
-              const uint64_t b_lo = umma_smem_desc(sB + Cfg::kSet + kk * 1024, lbo, sbo, 2);
+              const uint64_t a_lo = umma_smem_desc(sA + Cfg::kSet + kk * 1024, lbo, sbo, kUmmaLayout);
+              const uint64_t b_lo = umma_smem_desc(sB + Cfg::kSet + kk * 1024, lbo, sbo, kUmmaLayout);
               // small cross terms first, then the leading term
               umma_tf32(tmem_base, a_lo, b_hi, idesc_main, acc);
               umma_tf32(tmem_base, a_hi, b_lo, idesc_main, 1u);
@@ -454,7 +459,7 @@ int encode_view_map(CUtensorMap* map, const void* ptr, int64_t n_rows, int64_t d
   CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   if (tc_debug().tma_dtype >= 0) dt = (CUtensorMapDataType)tc_debug().tma_dtype;
   CUresult r = enc(map, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (d=%lld n=%lld ld=%lld)", (int)r, (long long)d,
@@ -588,7 +593,7 @@ int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t*
   prm.nblocks = L.nblocks;
   prm.Dp = L.Dp;
   prm.lbo_bytes = tc_debug().lbo_bytes >= 0 ? tc_debug().lbo_bytes : P.kc * 128;
-  prm.sbo_bytes = tc_debug().sbo_bytes >= 0 ? tc_debug().sbo_bytes : 1024;
+  prm.sbo_bytes = tc_debug().sbo_bytes >= 0 ? tc_debug().sbo_bytes : 512;
   int b = 0;
   for (int v = 0; v < L.n_views; ++v)
     for (int c = 0; c < L.dims[v]; c += kBlk, ++b) {

@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <type_traits>
 
 namespace ccab {
@@ -186,8 +187,33 @@ __global__ void __launch_bounds__(256) jacobi_gram_kernel(const JacobiCtx<T> c, 
 // ---------------------------------------------------------------------------------------------
 // (b) small eigenproblem of the panel Gram matrix -> Q (columns sorted by descending eigenvalue)
 // ---------------------------------------------------------------------------------------------
+// One Newton-Schulz step Q <- Q + Q (I - Q^T Q) / 2: the product of hundreds of rotations drifts from
+// orthogonality by O(#rotations * eps) (tiny rotations round c to 1 and inflate norms systematically);
+// this pulls Q back to eps-level so that V and G = A V stay consistent over thousands of panel updates.
+// E: scratch S x S (stride SP).  All threads of the block call this.
+template <typename T, int S>
+__device__ void reorthonormalise(T* Q, T* E, T* Qn) {
+  constexpr int SP = S + 1;
+  for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+    const int i = e / S, j = e % S;
+    T acc = (i == j) ? T(1) : T(0);
+#pragma unroll 8
+    for (int k = 0; k < S; ++k) acc = fma(-Q[k * SP + i], Q[k * SP + j], acc);
+    E[i * SP + j] = acc;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+    const int i = e / S, j = e % S;
+    T acc = T(0);
+#pragma unroll 8
+    for (int k = 0; k < S; ++k) acc = fma(Q[i * SP + k], E[k * SP + j], acc);
+    Qn[i * SP + j] = Q[i * SP + j] + T(0.5) * acc;
+  }
+  __syncthreads();
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256) jacobi_solve_kernel(const JacobiCtx<T> c, T tol) {
+__global__ void __launch_bounds__(256) jacobi_solve_kernel(const JacobiCtx<T> c, T tol, int inner_sweeps) {
   __shared__ T Wa[kS * kSP];
   __shared__ T Wb[kS * kSP];
   __shared__ T Q[kS * kSP];
@@ -224,7 +250,7 @@ __global__ void __launch_bounds__(256) jacobi_solve_kernel(const JacobiCtx<T> c,
   }
   if (ratio <= (float)tol) return;  // panel already orthogonal: Q = I, apply kernel skips it
 
-  T* fin = small_syevj<T, kS>(Wa, Wb, Q, 10);
+  T* fin = small_syevj<T, kS>(Wa, Wb, Q, inner_sweeps);
   __syncthreads();
   if (threadIdx.x < kS) {
     const int i = threadIdx.x;
@@ -237,10 +263,13 @@ __global__ void __launch_bounds__(256) jacobi_solve_kernel(const JacobiCtx<T> c,
     rank_of[i] = rk;
   }
   __syncthreads();
+  T* other = (fin == Wa) ? Wb : Wa;   // free ping-pong buffer: scratch for I - Q^T Q
+  T* Qn = fin;                         // the diagonalised matrix is no longer needed after ranking
+  reorthonormalise<T, kS>(Q, other, Qn);
   T* Qo = c.Qm + ((size_t)b * c.npairs + pair) * (kS * kS);
   for (int e = threadIdx.x; e < kS * kS; e += blockDim.x) {
     const int r = e / kS, i = e % kS;
-    Qo[r * kS + rank_of[i]] = Q[r * kSP + i];
+    Qo[r * kS + rank_of[i]] = Qn[r * kSP + i];
   }
 }
 
@@ -327,23 +356,26 @@ __global__ void jacobi_reset_stat_kernel(unsigned* stat, int batch) {
 
 // one warp per column: value (Rayleigh quotient or norm), pad detection, optional normalisation of G
 template <typename T>
-__global__ void jacobi_values_kernel(JacobiCtx<T> c, int n, int svd_mode, T shift, T* __restrict__ vals) {
+__global__ void jacobi_values_kernel(JacobiCtx<T> c, int n, int svd_mode, T shift, T* __restrict__ vals,
+                                     T* __restrict__ vnorm) {
   const int b = blockIdx.y;
   const int col = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (col >= c.n_pad) return;
   T* g = c.G + (size_t)b * c.n_pad * c.ldg + (size_t)col * c.ldg;
   const T* v = c.V + (size_t)b * c.n_pad * c.n_pad + (size_t)col * c.n_pad;
-  T acc = 0, padw = 0;
+  T acc = 0, padw = 0, vv = 0;
   if (svd_mode) {
     for (int i = lane; i < c.m; i += 32) acc = fma(g[i], g[i], acc);
   } else {
     for (int i = lane; i < n; i += 32) acc = fma(v[i], g[i], acc);
   }
+  for (int i = lane; i < n; i += 32) vv = fma(v[i], v[i], vv);
   for (int i = n + lane; i < c.n_pad; i += 32) padw = fma(v[i], v[i], padw);
   for (int o = 16; o > 0; o >>= 1) {
     acc += __shfl_xor_sync(0xffffffffu, acc, o);
     padw += __shfl_xor_sync(0xffffffffu, padw, o);
+    vv += __shfl_xor_sync(0xffffffffu, vv, o);
   }
   T val;
   if (padw > T(0.5)) {
@@ -353,9 +385,12 @@ __global__ void jacobi_values_kernel(JacobiCtx<T> c, int n, int svd_mode, T shif
     const T inv = val > T(0) ? T(1) / val : T(0);
     for (int i = lane; i < c.m; i += 32) g[i] *= inv;
   } else {
-    val = acc - shift;
+    val = (vv > T(0) ? acc / vv : acc) - shift;  // Rayleigh quotient of the (re-normalised) vector
   }
-  if (lane == 0) vals[(size_t)b * c.n_pad + col] = val;
+  if (lane == 0) {
+    vals[(size_t)b * c.n_pad + col] = val;
+    vnorm[(size_t)b * c.n_pad + col] = vv > T(0) ? T(1) / sqrt(vv) : T(1);
+  }
 }
 
 // rank-by-counting sort (descending) + gather of the vectors as rows
@@ -376,7 +411,7 @@ __global__ void jacobi_rank_kernel(const T* __restrict__ vals, int n_pad, int* _
 
 template <typename T>
 __global__ void jacobi_gather_kernel(JacobiCtx<T> c, int n, const T* __restrict__ vals,
-                                     const int* __restrict__ rank, T* __restrict__ out_vals,
+                                     const T* __restrict__ vnorm, const int* __restrict__ rank, T* __restrict__ out_vals,
                                      int64_t vals_stride, T* __restrict__ out_right, int64_t ld_right,
                                      int64_t right_stride, T* __restrict__ out_left, int64_t ld_left,
                                      int64_t left_stride) {
@@ -387,7 +422,8 @@ __global__ void jacobi_gather_kernel(JacobiCtx<T> c, int n, const T* __restrict_
   if (out_right) {
     const T* v = c.V + (size_t)b * c.n_pad * c.n_pad + (size_t)col * c.n_pad;
     T* o = out_right + (size_t)b * right_stride + (size_t)rk * ld_right;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) o[i] = v[i];
+    const T sc = vnorm[(size_t)b * c.n_pad + col];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) o[i] = v[i] * sc;
   }
   if (out_left) {
     const T* g = c.G + (size_t)b * c.n_pad * c.ldg + (size_t)col * c.ldg;
@@ -399,6 +435,11 @@ __global__ void jacobi_gather_kernel(JacobiCtx<T> c, int n, const T* __restrict_
 // ---------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------
+int& jacobi_inner_sweeps() {
+  static int v = 0;
+  return v;
+}
+
 namespace {
 inline size_t al(size_t x) { return (x + 255) & ~size_t(255); }
 
@@ -406,7 +447,7 @@ template <typename T>
 struct Plan {
   int n_pad, nb, npairs, R, rows_per_part;
   int64_t ldg;
-  size_t oG, oV, oW, oQ, oSkip, oStat, oVals, oRank, total;
+  size_t oG, oV, oW, oQ, oSkip, oStat, oVals, oNorm, oRank, total;
 };
 
 template <typename T>
@@ -429,6 +470,7 @@ Plan<T> make_plan(int m, int n, int batch) {
   P.oSkip = o; o += al((size_t)batch * P.npairs * sizeof(int));
   P.oStat = o; o += al((size_t)batch * sizeof(unsigned));
   P.oVals = o; o += al((size_t)batch * P.n_pad * sizeof(T));
+  P.oNorm = o; o += al((size_t)batch * P.n_pad * sizeof(T));
   P.oRank = o; o += al((size_t)batch * P.n_pad * sizeof(int));
   P.total = o + 256;
   return P;
@@ -457,6 +499,7 @@ int jacobi_solve(const JacobiArgs<T>& a, void* ws, size_t ws_bytes, cudaStream_t
   c.skip = reinterpret_cast<int*>(w + P.oSkip);
   c.stat = reinterpret_cast<unsigned*>(w + P.oStat);
   T* vals = reinterpret_cast<T*>(w + P.oVals);
+  T* vnorm = reinterpret_cast<T*>(w + P.oNorm);
   int* rank = reinterpret_cast<int*>(w + P.oRank);
   c.m = m;
   c.n_pad = P.n_pad;
@@ -475,6 +518,7 @@ int jacobi_solve(const JacobiArgs<T>& a, void* ws, size_t ws_bytes, cudaStream_t
   }
   const T tol = a.tol > 0 ? (T)a.tol : (T)(4.0 * (double)Eps<T>::v * std::sqrt((double)m));
   const int max_sweeps = a.max_sweeps > 0 ? a.max_sweeps : (std::is_same<T, float>::value ? 16 : 24);
+  const int inner_sweeps = jacobi_inner_sweeps() > 0 ? jacobi_inner_sweeps() : 2;
   const int rounds = P.nb - 1;
   const int apply_chunks = (int)(ceil_div(m, 128) + ceil_div(P.n_pad, 128));
   int sweeps_done = 0;
@@ -485,7 +529,7 @@ int jacobi_solve(const JacobiArgs<T>& a, void* ws, size_t ws_bytes, cudaStream_t
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     for (int r = 0; r < rounds; ++r) {
       jacobi_gram_kernel<T><<<dim3(P.npairs, P.R, batch), 256, 0, stream>>>(c, r);
-      jacobi_solve_kernel<T><<<dim3(P.npairs, batch), 256, 0, stream>>>(c, tol);
+      jacobi_solve_kernel<T><<<dim3(P.npairs, batch), 256, 0, stream>>>(c, tol, inner_sweeps);
       jacobi_apply_kernel<T><<<dim3(P.npairs, apply_chunks, batch), 128, 0, stream>>>(c, r);
     }
     cudaError_t e = cudaGetLastError();
@@ -501,6 +545,7 @@ int jacobi_solve(const JacobiArgs<T>& a, void* ws, size_t ws_bytes, cudaStream_t
       worst = std::max(worst, f);
     }
     last_ratio = worst;
+    if (getenv("CCAB_JACOBI_VERBOSE")) fprintf(stderr, "[syevj] sweep %d worst offdiag %.3e (tol %.3e)\n", sweep, worst, (double)tol);
     if (worst <= (float)tol) break;
     jacobi_reset_stat_kernel<<<1, 1024, 0, stream>>>(c.stat, batch);
   }
@@ -509,10 +554,10 @@ int jacobi_solve(const JacobiArgs<T>& a, void* ws, size_t ws_bytes, cudaStream_t
   if (a.info) { a.info[0] = sweeps_done; }
   if (a.final_offdiag) *a.final_offdiag = last_ratio;
 
-  jacobi_values_kernel<T><<<dim3((unsigned)ceil_div(P.n_pad, 8), batch), 256, 0, stream>>>(c, n, a.svd_mode, shift, vals);
+  jacobi_values_kernel<T><<<dim3((unsigned)ceil_div(P.n_pad, 8), batch), 256, 0, stream>>>(c, n, a.svd_mode, shift, vals, vnorm);
   jacobi_rank_kernel<T><<<dim3((unsigned)ceil_div(P.n_pad, 256), batch), 256, 0, stream>>>(vals, P.n_pad, rank);
   jacobi_gather_kernel<T><<<dim3(P.n_pad, batch), 128, 0, stream>>>(
-      c, n, vals, rank, a.out_vals, a.vals_stride, a.out_right, a.ld_right, a.right_stride, a.out_left, a.ld_left,
+      c, n, vals, vnorm, rank, a.out_vals, a.vals_stride, a.out_right, a.ld_right, a.right_stride, a.out_left, a.ld_left,
       a.left_stride);
   CCAB_CUDA(cudaGetLastError());
   return 0;

@@ -25,6 +25,9 @@ struct JacobiArgs {
   float* final_offdiag;     // host: largest normalised off-diagonal Gram entry of the last sweep
 };
 
+// tuning knob: inner (panel) Jacobi sweeps per block visit; <=0 selects the default
+int& jacobi_inner_sweeps();
+
 template <typename T>
 size_t jacobi_workspace_bytes(int m, int n, int batch);
 

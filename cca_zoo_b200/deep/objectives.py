@@ -1,0 +1,110 @@
+"""Differentiable CCA objectives on the GPU (mirrors cca_zoo/deep/objectives.py:24-153).
+
+``CCALoss.forward([z1, z2])`` returns ``-|| S11^-1/2 S12 S22^-1/2 ||_F^2`` with
+``Sii = cov(zi) + eps I`` and eigenvalues clamped at ``eps`` exactly as the reference
+(objectives.py:86-102, ``_inv_sqrtm`` :9-21).  Plug into ``DCCA(objective=...)``
+(cca_zoo/deep/_dcca.py:61,73) unchanged: it is an ``nn.Module`` taking ``list[Tensor]`` and returning
+a 0-dim tensor.
+
+Forward  : K1 moments of [z1 z2] -> covariance -> two Jacobi eigendecompositions ->
+           T = (L1^-1/2 V1^T) S12 (L2^-1/2 V2^T)^T ; loss = -||T||_F^2 (= -sum eigvalsh(T^T T), the third
+           eigensolve of the reference is a trace).
+Backward : analytic, no eigh-backward:  with P = S11^-1 S12 S22^-1,
+           dL/dz1 = 2/(n-1) * center(z1 (P S21 S11^-1) - z2 P^T),  dL/dz2 symmetric.
+           Valid whenever the eigenvalue clamp is inactive, which ``+ eps I`` guarantees up to round-off.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+class _CCALossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z1, z2, eps, precision):
+        if not (z1.is_cuda and z2.is_cuda):
+            raise RuntimeError(
+                "cca_zoo_b200.CCALoss needs CUDA tensors (sm_100a); there is no CPU fallback."
+            )
+        if z1.dtype != z2.dtype or z1.dtype not in (torch.float32, torch.float64):
+            raise ValueError("representations must share a float32/float64 dtype")
+        n = z1.shape[0]
+        d1, d2 = z1.shape[1], z2.shape[1]
+        z1d, z2d = z1.detach(), z2.detach()
+        mom = ops.moments([z1d, z2d], precision=precision)
+        C, _ = ops.covariance(mom, [d1, d2], n, center=True, dtype=z1.dtype)
+        S12 = C[:d1, d1:]
+        whiten = []
+        for blk in (C[:d1, :d1], C[d1:, d1:]):
+            lam, Vt = ops.syevj(blk.contiguous())
+            # eigh(S + eps I) = (lam + eps, V); clamp(min=eps) <=> lam floored at 0
+            Wt, _, _ = ops.whiten_rows(lam, Vt, 0.0, floor_add=eps, rank_tol=-1.0, lam_floor=0.0)
+            whiten.append(Wt)
+        T = ops.gemm(ops.gemm(whiten[0], S12), whiten[1], transb=True)
+        fro = ops.frobenius_norm(T)
+        loss = -(fro * fro).reshape(())
+        ctx.save_for_backward(z1d, z2d, whiten[0], whiten[1], S12.contiguous())
+        ctx.n = n
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        z1, z2, W1t, W2t, S12 = ctx.saved_tensors
+        n = ctx.n
+        S1inv = ops.gemm(W1t, W1t, transa=True)          # S11^-1 = W1 W1^T
+        S2inv = ops.gemm(W2t, W2t, transa=True)
+        P = ops.gemm(ops.gemm(S1inv, S12), S2inv)        # d1 x d2
+        g11 = ops.gemm(ops.gemm(P, S12, transb=True), S1inv)   # P S21 S11^-1
+        g22 = ops.gemm(ops.gemm(S2inv, S12, transa=False, transb=True), P)  # S22^-1 S21 P
+        a = 2.0 / (n - 1)
+        g1 = ops.gemm(z1, g11, alpha=a)
+        ops.gemm(z2, P, transb=True, alpha=-a, beta=1.0, out=g1)
+        g2 = ops.gemm(z2, g22, alpha=a)
+        ops.gemm(z1, P, alpha=-a, beta=1.0, out=g2)
+        ops.center_columns_(g1)
+        ops.center_columns_(g2)
+        go = grad_out.to(g1.dtype)
+        return g1 * go, g2 * go, None, None
+
+
+class CCALoss(nn.Module):
+    r"""Andrew et al. (2013) deep-CCA loss for two views (cca_zoo/deep/objectives.py:24-102).
+
+    Args:
+        eps: ridge added to the within-view covariances and eigenvalue floor (default 1e-5).
+        precision: arithmetic of the covariance kernel for float32 inputs
+            (``"exact"`` default: mini-batches are HBM/latency bound, CUDA-core FMA is free).
+    """
+
+    def __init__(self, eps: float = 1e-5, precision: str = "exact") -> None:
+        super().__init__()
+        self.eps = eps
+        self.precision = precision
+
+    def forward(self, representations: list[torch.Tensor]) -> torch.Tensor:
+        if len(representations) != 2:
+            raise ValueError(
+                "CCALoss expects exactly 2 representations, "
+                f"got {len(representations)}."
+            )
+        z1, z2 = representations
+        return _CCALossFn.apply(z1, z2, float(self.eps), self.precision)
+
+
+class MCCALoss(nn.Module):
+    r"""Sum of pairwise CCA losses over all view pairs (cca_zoo/deep/objectives.py:105-153)."""
+
+    def __init__(self, eps: float = 1e-5, precision: str = "exact") -> None:
+        super().__init__()
+        self.eps = eps
+        self._cca_loss = CCALoss(eps=eps, precision=precision)
+
+    def forward(self, representations: list[torch.Tensor]) -> torch.Tensor:
+        n_views = len(representations)
+        total = torch.zeros((), device=representations[0].device, dtype=representations[0].dtype)
+        for i in range(n_views):
+            for j in range(i + 1, n_views):
+                total = total + self._cca_loss([representations[i], representations[j]])
+        return total

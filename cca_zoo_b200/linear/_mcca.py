@@ -1,0 +1,52 @@
+"""MCCA on the GPU (mirrors cca_zoo/linear/_mcca.py)."""
+from __future__ import annotations
+
+from numbers import Real
+from typing import Any, ClassVar
+
+from sklearn.utils._param_validation import Interval
+
+from .._base import BaseModel
+from .._solvers import mcca_weights
+from .._validation import perview_parameter
+from ._rcca import RIDGE_PARAMETER
+
+#: cca_zoo/_utils/_param_constraints.py:22 (POSITIVE_EPS)
+POSITIVE_EPS: list[Any] = [Interval(Real, 0, None, closed="neither")]
+
+
+class MCCA(BaseModel):
+    r"""Multiset CCA for two or more views (cca_zoo/linear/_mcca.py:16-135).
+
+    Solves :math:`A v = \lambda B v` with :math:`A` the between-view block covariance and
+    :math:`B` the ridge-regularised block-diagonal within-view covariance, eigenvectors normalised
+    to :math:`v^\top B v = 1`.  ``pca`` is accepted for signature compatibility: the reference's PCA
+    pre-rotation is an exact change of basis (identical weights for full-column-rank views), which
+    the covariance form here subsumes -- the per-view eigendecompositions ARE that rotation.
+
+    As in the reference (np.cov upcasts) the eigen-stage runs in float64 and
+    ``weights_`` are float64 even for float32 views.
+    """
+
+    _solve_in_float64 = True
+    _parameter_constraints: ClassVar[dict[str, list[Any]]] = {
+        **BaseModel._parameter_constraints,
+        "c": RIDGE_PARAMETER,
+        "pca": ["boolean"],
+        "eps": POSITIVE_EPS,
+    }
+
+    def __init__(self, latent_dimensions: int = 1, center: bool = True, c=0.0, pca: bool = True,
+                 eps: float = 1e-6, precision: str = "tf32x3", device=None) -> None:
+        super().__init__(latent_dimensions=latent_dimensions, center=center, precision=precision, device=device)
+        self.c = c
+        self.pca = pca
+        self.eps = eps
+
+    def fit(self, views, y=None):
+        C, dims, n_total = self._fit_device(views)
+        return self._finish(self._solve(C, dims, n_total))
+
+    def _solve(self, C, dims, n_total):
+        c_ = perview_parameter("c", self.c, 0.0, self.n_views_)
+        return mcca_weights(C, dims, self.latent_dimensions, [float(x) for x in c_], float(self.eps))

@@ -1,0 +1,75 @@
+"""rCCA / CCA / PLS on the GPU (mirrors cca_zoo/linear/_rcca.py, _cca.py, _pls.py)."""
+from __future__ import annotations
+
+from numbers import Real
+from typing import Any, ClassVar
+
+from sklearn.utils._param_validation import Interval
+
+from .._base import BaseModel
+from .._solvers import rcca_weights
+from .._validation import perview_parameter
+
+#: cca_zoo/_utils/_param_constraints.py:18 (RIDGE_PARAMETER)
+RIDGE_PARAMETER: list[Any] = [Interval(Real, 0, 1, closed="both"), "array-like"]
+
+
+class rCCA(BaseModel):
+    r"""Regularised CCA (canonical ridge) for exactly two views.
+
+    Same estimator as ``cca_zoo.linear.rCCA`` (cca_zoo/linear/_rcca.py:16-101): maximise
+    :math:`w_1^\top X_1^\top X_2 w_2` s.t. :math:`w_i^\top((1-c_i) X_i^\top X_i + c_i I) w_i = 1`.
+    The reference whitens each view with a tall SVD and takes the SVD of the whitened
+    cross-covariance; here the same weights come from the block covariance (one tcgen05 pass over
+    the data) and small Jacobi eigen/singular-value solves on the device.
+
+    Args:
+        latent_dimensions: number of latent dimensions (default 1).
+        center: subtract column means (default True).
+        c: ridge parameter(s) in [0, 1]; scalar or ``[c1, c2]``.
+        precision: covariance arithmetic for float32 inputs: ``"tf32x3"`` (default, float32-grade),
+            ``"tf32"`` (single tensor-core pass) or ``"exact"`` (CUDA-core FMA).
+        device: CUDA device (default: current).
+    """
+
+    _parameter_constraints: ClassVar[dict[str, list[Any]]] = {
+        **BaseModel._parameter_constraints,
+        "c": RIDGE_PARAMETER,
+    }
+
+    def __init__(self, latent_dimensions: int = 1, center: bool = True, c=0.0, precision: str = "tf32x3",
+                 device=None) -> None:
+        super().__init__(latent_dimensions=latent_dimensions, center=center, precision=precision, device=device)
+        self.c = c
+
+    def fit(self, views, y=None):
+        """Fit on a list of exactly two ``(n_samples, n_features_i)`` arrays (numpy or torch)."""
+        C, dims, n_total = self._fit_device(views)
+        if self.n_views_ != 2:
+            raise ValueError(
+                f"rCCA requires exactly 2 views, got {self.n_views_}. "
+                "Use MCCA for more than 2 views."
+            )
+        return self._finish(self._solve(C, dims, n_total))
+
+    def _solve(self, C, dims, n_total):
+        c_ = perview_parameter("c", self.c, 0.0, 2)
+        return rcca_weights(C, dims, n_total, self.latent_dimensions, [float(x) for x in c_])
+
+
+class CCA(rCCA):
+    """Canonical Correlation Analysis: ``rCCA`` with ``c=0`` (cca_zoo/linear/_cca.py:10-76)."""
+
+    def __init__(self, latent_dimensions: int = 1, center: bool = True, precision: str = "tf32x3",
+                 device=None) -> None:
+        super().__init__(latent_dimensions=latent_dimensions, center=center, c=0.0, precision=precision,
+                         device=device)
+
+
+class PLS(rCCA):
+    """Partial Least Squares: ``rCCA`` with ``c=1`` (cca_zoo/linear/_pls.py:10-77)."""
+
+    def __init__(self, latent_dimensions: int = 1, center: bool = True, precision: str = "tf32x3",
+                 device=None) -> None:
+        super().__init__(latent_dimensions=latent_dimensions, center=center, c=1.0, precision=precision,
+                         device=device)

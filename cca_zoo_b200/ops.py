@@ -184,7 +184,8 @@ def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, out=None):
     return out
 
 
-def whiten_rows(lam, Vt, c, floor_add=0.0, floor_dev=None, scale=1.0, rank_tol=0.0, max_rank=None):
+def whiten_rows(lam, Vt, c, floor_add=0.0, floor_dev=None, scale=1.0, rank_tol=0.0, max_rank=None,
+                lam_floor=-1e300):
     """(Wt, g, rank_dev) -- see ccab_whiten_rows."""
     lib = _lib.load()
     _require_cuda(Vt, "Vt")
@@ -195,10 +196,40 @@ def whiten_rows(lam, Vt, c, floor_add=0.0, floor_dev=None, scale=1.0, rank_tol=0
     with torch.cuda.device(Vt.device):
         rc = lib.ccab_whiten_rows(_DT[Vt.dtype], d, _ptr(lam), _ptr(Vt), Vt.stride(0), float(c), float(floor_add),
                                   _ptr(floor_dev), float(scale), float(rank_tol),
-                                  int(d if max_rank is None else max_rank), _ptr(Wt), Wt.stride(0), _ptr(g),
+                                  int(d if max_rank is None else max_rank), float(lam_floor), _ptr(Wt), Wt.stride(0),
+                                  _ptr(g),
                                   _ptr(rank), _stream(Vt))
     _lib.check(rc, "ccab_whiten_rows")
     return Wt, g, rank
+
+
+_POW = {None: 0, 1: 0, -1: 1, -0.5: 2}
+
+
+def scale(A, rows=None, rows_pow=1, cols=None, cols_pow=1, out=None):
+    """out[i,j] = A[i,j] * rows[i]**rows_pow * cols[j]**cols_pow (pow in {1, -1, -0.5})."""
+    lib = _lib.load()
+    _require_cuda(A, "A")
+    A = _row_major(A, False)
+    if out is None:
+        out = torch.empty_like(A)
+    with torch.cuda.device(A.device):
+        rc = lib.ccab_scale(_DT[A.dtype], A.shape[0], A.shape[1], _ptr(A), A.stride(0), _ptr(rows), _POW[rows_pow],
+                            _ptr(cols), _POW[cols_pow], _ptr(out), out.stride(0), _stream(A))
+    _lib.check(rc, "ccab_scale")
+    return out
+
+
+def center_columns_(A):
+    """In place: subtract the column means."""
+    lib = _lib.load()
+    _require_cuda(A, "A")
+    if A.stride(1) != 1:
+        raise ValueError("row-major tensor expected")
+    with torch.cuda.device(A.device):
+        rc = lib.ccab_center_columns(_DT[A.dtype], A.shape[0], A.shape[1], _ptr(A), A.stride(0), _stream(A))
+    _lib.check(rc, "ccab_center_columns")
+    return A
 
 
 def frobenius_norm(A):

@@ -1,0 +1,38 @@
+"""Sample-sharded fitting: one process per GPU, each holding a row shard of every view.
+
+The only exchange step of the path: the additive moment buffer
+``[M (Dp x Dp) | s (Dp) | n]`` is summed over ranks with ONE all-reduce; everything after it
+(covariance finalisation, eigensolves) is replicated and bit-identical on every rank.
+Backend-agnostic (NCCL on GPUs; the host logic is exercised with gloo on CPU in tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def is_distributed(group=None) -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def pack_moments(moments: torch.Tensor, n_local: int) -> torch.Tensor:
+    """Append the local row count so that it rides in the same message."""
+    tail = torch.tensor([float(n_local)], dtype=moments.dtype, device=moments.device)
+    return torch.cat([moments, tail])
+
+
+def allreduce_moments(moments: torch.Tensor, n_local: int, group=None):
+    """Sum (moments, n) over the ranks of ``group``.  Returns (moments_total, n_total)."""
+    if not is_distributed(group):
+        return moments, int(n_local)
+    packed = pack_moments(moments, n_local)
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    n_total = int(round(float(packed[-1].item())))
+    return packed[:-1], n_total
+
+
+def shard_rows(n_rows: int, rank: int, world: int):
+    """Contiguous row block [lo, hi) of rank ``rank``."""
+    base, rem = divmod(n_rows, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

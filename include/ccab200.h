@@ -103,11 +103,22 @@ int ccab_gemm(int dtype, int transa, int transb, int m, int n, int k, double alp
  * cca_zoo/_utils/_linalg.py:30-38; also B^-1/2 of cca_zoo/linear/_mcca.py:163-173 and R_i of
  * cca_zoo/linear/_gcca.py:101-105):
  *   keep_j  = lam[j] > rank_tol * max(lam[0],0)  &&  j < max_rank
- *   g_j     = keep_j ? ((1-c)*lam[j] + c + floor_add + (floor_dev ? *floor_dev : 0))^-1/2 * scale^-1/2 : 0
- *   Wt[j,:] = g_j * Vt[j,:]            g_out[j] = g_j (may be NULL)      *rank_out = #kept (device int) */
+ *   g_j     = keep_j ? ((1-c)*max(lam[j],lam_floor) + c + floor_add + (floor_dev ? *floor_dev : 0))^-1/2
+ *                      * scale^-1/2 : 0
+ *   Wt[j,:] = g_j * Vt[j,:]            g_out[j] = g_j (may be NULL)      *rank_out = #kept (device int)
+ * lam_floor = 0 with c = 0, floor_add = eps reproduces clamp(eigh(S + eps I), min=eps)
+ * (cca_zoo/deep/objectives.py:19-21); pass -inf-like (e.g. -1e300) to disable the clamp. */
 int ccab_whiten_rows(int dtype, int d, const void* lam, const void* Vt, int64_t ldv, double c, double floor_add,
-                     const void* floor_dev, double scale, double rank_tol, int max_rank, void* Wt, int64_t ldw,
-                     void* g_out, int* rank_out, void* stream);
+                     const void* floor_dev, double scale, double rank_tol, int max_rank, double lam_floor, void* Wt,
+                     int64_t ldw, void* g_out, int* rank_out, void* stream);
+
+/* B[i,j] = A[i,j] * f(r[i]) * f(c[j]); r / c may be NULL; *_pow: 0 -> x, 1 -> 1/x, 2 -> 1/sqrt(x).
+ * (column scalings such as diag(sigma)^-1/2 in the GCCA back-substitution, cca_zoo/linear/_gcca.py:109) */
+int ccab_scale(int dtype, int m, int n, const void* A, int64_t lda, const void* r, int r_pow, const void* c,
+               int c_pow, void* B, int64_t ldb, void* stream);
+
+/* A[:, j] -= mean_i A[i, j] in place (the centring Jacobian of cca_zoo/deep/objectives.py:83-84) */
+int ccab_center_columns(int dtype, int m, int n, void* A, int64_t lda, void* stream);
 
 /* out[0] (device) = ||A||_F of an m x n row-major matrix */
 int ccab_frobenius_norm(int dtype, int m, int n, const void* A, int64_t lda, void* out, void* stream);

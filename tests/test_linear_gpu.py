@@ -1,0 +1,134 @@
+"""GPU parity of the estimators against the golden vectors made from the reference (tests/golden)
+and against the oracle on fresh seeded inputs.  Tolerances follow BASELINE.json's north_star:
+1e-5 relative for float64 inputs, 1e-3 for float32 inputs (weights per vector, sign-aligned jointly
+across views, and canonical correlations)."""
+import numpy as np
+import pytest
+
+from oracle import restatement as R
+from tests import golden_io as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(case, **extra):
+    from cca_zoo_b200 import linear
+
+    return getattr(linear, case["model"])(**case["kwargs"], **extra)
+
+
+@pytest.mark.parametrize("name", sorted(G.CASES))
+def test_fit_matches_reference_golden(name):
+    case = G.CASES[name]
+    views = G.case_inputs(name)
+    w_ref, mu_ref, score_ref = G.case_outputs(name)
+    est = _model(case).fit(views)
+    tol = 1e-3 if case["dtype"] == "f32" else 1e-5
+    assert len(est.weights_) == len(w_ref)
+    for w, wr in zip(est.weights_, w_ref):
+        assert w.shape == wr.shape
+    err = R.max_rel_err_per_vector([w.astype(np.float64) for w in est.weights_], w_ref)
+    assert err < tol, f"weights rel err {err:.2e}"
+    np.testing.assert_allclose(est.score(views), score_ref, rtol=tol)
+    for a, b in zip(est.means_, mu_ref):
+        np.testing.assert_allclose(a, b, rtol=tol, atol=tol * 1e-2)
+    assert est.n_samples_ == views[0].shape[0]
+    assert est.n_features_in_ == [v.shape[1] for v in views]
+
+
+@pytest.mark.parametrize("precision,tol", [("tf32x3", 1e-3), ("exact", 1e-3), ("tf32", 2e-2)])
+def test_rcca_float32_precisions(precision, tol):
+    """float32 views through each covariance arithmetic; single-pass TF32 is reported, not gated at 1e-3."""
+    from cca_zoo_b200.linear import rCCA
+
+    views = G.case_inputs("rcca_med32")
+    w_ref, _, score_ref = G.case_outputs("rcca_med32")
+    est = rCCA(latent_dimensions=6, c=0.1, precision=precision).fit(views)
+    err = R.max_rel_err_per_vector([w.astype(np.float64) for w in est.weights_], w_ref)
+    assert err < tol, f"{precision}: weights rel err {err:.2e}"
+    np.testing.assert_allclose(est.score(views), score_ref, rtol=tol)
+    assert est.weights_[0].dtype == np.float32  # the reference keeps float32 in rCCA
+
+
+def test_quickstart_readme_scores():
+    """BASELINE config 1 (README.md:52-72): train and held-out scores."""
+    from cca_zoo_b200.linear import CCA
+
+    views = G.dataset("quickstart")
+    est = CCA(latent_dimensions=2).fit(views)
+    np.testing.assert_allclose(est.score(views), [0.99551056, 0.99407941], atol=1e-7)
+    test = [G.get("quickstart_test/v0"), G.get("quickstart_test/v1")]
+    np.testing.assert_allclose(est.score(test), [0.97681356, 0.97297565], atol=1e-7)
+
+
+def test_accepts_cuda_and_cpu_tensors():
+    import torch
+    from cca_zoo_b200.linear import rCCA
+
+    views = G.dataset("two_views")
+    ref = rCCA(latent_dimensions=2, c=0.1).fit(views)
+    for conv in (lambda v: torch.from_numpy(v), lambda v: torch.from_numpy(v).cuda()):
+        est = rCCA(latent_dimensions=2, c=0.1).fit([conv(v) for v in views])
+        assert R.max_rel_err_per_vector(est.weights_, ref.weights_) < 1e-9
+
+
+def test_medium_fresh_inputs_against_oracle_all_models():
+    """Seeded inputs the fixtures do not contain: oracle (numpy) vs CUDA path, float64."""
+    from cca_zoo_b200.datasets import joint_data
+    from cca_zoo_b200.linear import GCCA, MCCA, rCCA
+
+    views = joint_data(n_views=3, n_samples=4000, n_features=[150, 130, 70], latent_dimensions=8,
+                       signal_to_noise=0.02, random_state=7)
+    dims = [150, 130, 70]
+    M, s, n = R.moments(views)
+    C = R.covariance_from_moments(M, s, n)
+    w, _ = R.cov_rcca_fit(C[:280, :280], dims[:2], 8, [0.2, 0.05], n)
+    est = rCCA(latent_dimensions=8, c=[0.2, 0.05]).fit(views[:2])
+    assert R.max_rel_err_per_vector(est.weights_, w) < 1e-5
+    w, _ = R.cov_mcca_fit(C, dims, 8, 0.1)
+    est = MCCA(latent_dimensions=8, c=0.1).fit(views)
+    assert R.max_rel_err_per_vector(est.weights_, w) < 1e-5
+    w, _ = R.cov_gcca_fit(C, dims, n, 8, 0.1, [1.0, 2.0, 0.5])
+    est = GCCA(latent_dimensions=8, c=0.1, view_weights=[1.0, 2.0, 0.5]).fit(views)
+    assert R.max_rel_err_per_vector(est.weights_, w) < 1e-5
+
+
+def test_reference_property_checks():
+    """The equivalences the reference's own tests pin (tests/linear/test_eigendecomposition.py)."""
+    from cca_zoo_b200.linear import CCA, GCCA, MCCA, PLS, rCCA
+
+    two = G.dataset("two_views")
+    cca = CCA(latent_dimensions=2).fit(two)
+    # rCCA(c=0) == CCA (:345-353); MCCA(2 views) == CCA (:411-416), atol 1e-6 on |scores|
+    for other in (rCCA(latent_dimensions=2, c=0.0), MCCA(latent_dimensions=2)):
+        o = other.fit(two)
+        np.testing.assert_allclose(np.abs(o.score(two)), np.abs(cca.score(two)), atol=1e-6)
+    # identical views -> correlation 1 (:330-336)
+    ident = CCA(latent_dimensions=2).fit([two[0], two[0].copy()])
+    np.testing.assert_allclose(ident.score([two[0], two[0]]), 1.0, atol=1e-6)
+    # variates uncorrelated (:419-429)
+    z = cca.transform(two)
+    cc = np.corrcoef(z[0].T)
+    assert abs(cc[0, 1]) < 1e-6
+    # fit_transform == fit().transform() up to sign (:112-137)
+    ft = CCA(latent_dimensions=2).fit_transform(two)
+    np.testing.assert_allclose(np.abs(ft[0]), np.abs(z[0]), atol=1e-10)
+    # 3 views rejected by 2-view models (:67-73)
+    three = G.dataset("three_views")
+    for cls in (CCA, rCCA, PLS):
+        with pytest.raises(ValueError, match="exactly 2 views"):
+            cls().fit(three)
+    # GCCA == MCCA scores on three views (known answer)
+    np.testing.assert_allclose(GCCA(latent_dimensions=2).fit(three).score(three),
+                               MCCA(latent_dimensions=2).fit(three).score(three), atol=1e-8)
+
+
+def test_latent_dimensions_clamped_like_reference():
+    """k silently clamped to the smaller view width (_rcca.py:95, _linalg.py:65)."""
+    from cca_zoo_b200.linear import MCCA, rCCA
+
+    two = G.dataset("two_views")
+    est = rCCA(latent_dimensions=20, c=0.1).fit(two)
+    assert est.weights_[0].shape == (10, 8) and est.weights_[1].shape == (8, 8)
+    est = MCCA(latent_dimensions=30).fit(two)
+    assert est.weights_[0].shape == (10, 18)
