@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: rCCA.fit() on BASELINE.json configs[1]
+(2-view rCCA, n=100000 rows per GPU, d=[1024,1024], k=64, c=0.1, float32 inputs).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3            # our CUDA path
+    python bench.py --impl reference --steps 1 --warmup 0     # reference algorithm on the host cores
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   # sample-sharded, one all-reduce
+
+One "step" = one fit.  Under N ranks every rank holds its own 100000-row shard (weak scaling): the job
+is ONE fit over N*100000 samples per step, its throughput is reported in units of the 1-GPU workload
+(`value` = N fit-units / s; at N=1 this is plain fit()/s).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ROWS, DIMS, K, C_RIDGE = 100_000, [1024, 1024], 64, 0.1
+SNR = 2.0 / 1024
+WORKLOAD = "rCCA.fit 2 views n=100000 rows/GPU d=[1024,1024] k=64 c=0.1 float32 (JointData snr=2/1024)"
+
+
+def make_views(seed: int, n_rows: int = N_ROWS):
+    from cca_zoo_b200.datasets import joint_data
+
+    return joint_data(n_views=2, n_samples=n_rows, n_features=DIMS, latent_dimensions=K,
+                      signal_to_noise=SNR, random_state=seed, dtype=np.float32)
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t.start()
+        return self
+
+    def stop(self):
+        self._stop.set()
+        self._t.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 3 + i and r[3 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port: same LAPACK calls as cca_zoo/linear/_rcca.py:83-101)
+# ----------------------------------------------------------------------------------------------
+def cpu_fit_seconds(views):
+    from oracle import restatement as R
+
+    t0 = time.perf_counter()
+    R.ref_rcca_fit(views, K, C_RIDGE)
+    return time.perf_counter() - t0
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(budget_s: float = 20.0):
+    """Reference algorithm on a bounded row sample; tall-SVD cost is linear in n, so the full-size
+    time is extrapolated as t_sample * (N_ROWS / n_sample)."""
+    views = make_views(0, 12_500)
+    t_cal = cpu_fit_seconds([v[:4000] for v in views])          # calibration (also warms BLAS)
+    n_s = int(min(12_500, max(4000, 4000 * budget_s / max(t_cal, 1e-3))))
+    t = cpu_fit_seconds([v[:n_s] for v in views])
+    full = t * (N_ROWS / n_s)
+    return {"value": 1.0 / full, "unit": "fit/s", "cores": cpu_threads(), "kind": "port",
+            "sample": f"oracle.ref_rcca_fit (numpy LAPACK gesdd path of _rcca.py) on {n_s} of {N_ROWS} rows, "
+                      f"{t:.2f} s measured, x{N_ROWS / n_s:.1f} linear-in-n extrapolation"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    views = make_views(0, 12_500)
+    t_cal = cpu_fit_seconds([v[:3000] for v in views])
+    total_steps = max(args.steps + args.warmup, 1)
+    n_s = int(min(12_500, max(3000, 3000 * (150.0 / total_steps) / max(t_cal, 1e-3))))
+    sample = [v[:n_s] for v in views]
+    for _ in range(args.warmup):
+        cpu_fit_seconds(sample)
+    times = [cpu_fit_seconds(sample) for _ in range(max(args.steps, 1))]
+    t = float(np.mean(times)) * (N_ROWS / n_s)
+    val = args.gpus / t  # same unit as our arm: 100000-row fit-units per second (CPU does them serially)
+    val = 1.0 / t
+    line = {
+        "impl": "reference", "metric": "rcca_fit_per_s", "value": val, "unit": "fit/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD},
+        "cpu_baseline": {"value": val, "unit": "fit/s", "cores": cpu_threads(), "kind": "port",
+                         "sample": f"{n_s} of {N_ROWS} rows per step, linear-in-n extrapolation x{N_ROWS / n_s:.1f}"},
+        "e2e": {"value": val, "unit": "fit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from cca_zoo_b200 import _lib
+    from cca_zoo_b200.linear import rCCA
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: cca_zoo_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    dev = torch.device("cuda", local)
+
+    host = [torch.from_numpy(v).pin_memory() for v in make_views(1000 + rank)]
+    views = [h.to(dev) for h in host]
+    est = rCCA(latent_dimensions=K, c=C_RIDGE, precision=args.precision)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident arm (`value`) with live timing of the tcgen05 kernel ----
+    for _ in range(args.warmup):
+        est.fit(views)
+    lib.ccab_profile_moments(1)
+    k1_ms = []
+
+    def step_dev():
+        est.fit(views)
+        k1_ms.append(lib.ccab_profile_moments_last_ms())
+
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    l0 = lib.ccab_launch_count()
+    total_ms = timed(step_dev, args.steps)
+    launches = lib.ccab_launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    lib.ccab_profile_moments(0)
+    ms_per_step = total_ms / args.steps
+    value = world / (ms_per_step * 1e-3)
+
+    # ---- end-to-end arm: pinned host inputs -> fit -> numpy weights ----
+    def step_e2e():
+        est.fit(host)
+
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps) / args.steps
+    h2d = sum(h.numel() * h.element_size() for h in host)
+    d2h = sum(w.nbytes for w in est.weights_) + sum(m.nbytes for m in est.means_)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant data-parallel kernel (K1, moments_tf32_kernel) ----
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    bf16 = peaks.get("bf16_tflops", 1590.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops/2 (TF32 runs at half the dense bf16 rate)" if peaks else \
+        "fallback 1590/2 TFLOP/s (B200_PROFILING.md)"
+    D = sum(DIMS)
+    flops = N_ROWS * D * (D + 1)  # algorithmic: symmetric product, SURVEY.md §8d
+    k1 = float(np.mean([m for m in k1_ms if m and m > 0])) if any(m and m > 0 for m in k1_ms) else None
+    passes = 3 if args.precision == "tf32x3" else 1
+    roof = None
+    if k1:
+        ach = flops / (k1 * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "moments_tf32_kernel", "achieved": ach, "peak": bf16 / 2, "unit": "TFLOP/s",
+                "frac": ach / (bf16 / 2), "traffic": None, "kernel_ms": k1, "mma_passes": passes,
+                "frac_of_issued": passes * ach / (bf16 / 2), "peak_source": peak_src,
+                "share_of_step": k1 / ms_per_step}
+
+    line = {
+        "metric": "rcca_fit_per_s", "value": value, "unit": "fit/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "tf32x3+f32" if args.precision == "tf32x3" else args.precision + "+f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rows_per_gpu": N_ROWS, "total_rows": N_ROWS * world,
+                   "parallelism": f"sample-sharded x{world}, one all-reduce of the moment buffer" if world > 1 else "single GPU",
+                   "l2": "inputs (819 MB per GPU) exceed the 126 MB L2; no explicit flush",
+                   "unit_note": "value = (n_gpus x 100000-row fit-units) / step time"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": world / (e2e_ms * 1e-3), "unit": "fit/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "roofline": roof,
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="tf32x3", choices=["tf32", "tf32x3", "exact"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

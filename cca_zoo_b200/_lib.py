@@ -23,6 +23,7 @@ _vp = C.c_void_p
 SIGNATURES = {
     "ccab_version": (C.c_int, []),
     "ccab_last_error": (C.c_char_p, []),
+    "ccab_launch_count": (C.c_int64, []),
     "ccab_moments_size": (C.c_int64, [C.c_int, _i64p]),
     "ccab_moments_padded_dim": (C.c_int64, [C.c_int, _i64p]),
     "ccab_moments_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, _i64p, C.c_int64]),
@@ -43,6 +44,8 @@ SIGNATURES = {
                              _vp]),
     "ccab_center_columns": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp]),
     "ccab_frobenius_norm": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp]),
+    "ccab_profile_moments": (C.c_int, [C.c_int]),
+    "ccab_profile_moments_last_ms": (C.c_double, []),
     "ccab_debug_set": (C.c_int, [C.c_char_p, C.c_int]),
 }
 

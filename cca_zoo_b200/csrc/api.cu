@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstring>
+#include <atomic>
 #include <exception>
 
 #include "common.cuh"
@@ -19,6 +20,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static std::atomic<long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
   return (int)e;
@@ -55,6 +59,7 @@ static int require_device() {
 extern "C" {
 
 int ccab_version(void) { return 100; }
+int64_t ccab_launch_count(void) { return (int64_t)launch_count(); }
 const char* ccab_last_error(void) { return g_err; }
 
 int64_t ccab_moments_size(int n_views, const int64_t* dims) {
@@ -302,6 +307,12 @@ int ccab_frobenius_norm(int dtype, int m, int n, const void* A, int64_t lda, voi
   return frobenius_norm<double>(m, n, static_cast<const double*>(A), lda, static_cast<double*>(out), s);
   CCAB_CATCH
 }
+
+int ccab_profile_moments(int enable) {
+  moments_profile_enable(enable);
+  return 0;
+}
+double ccab_profile_moments_last_ms(void) { return (double)moments_profile_last_ms(); }
 
 int ccab_debug_set(const char* key, int value) {
   if (!key) return -1;

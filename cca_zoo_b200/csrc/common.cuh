@@ -31,6 +31,10 @@ int cuda_fail(cudaError_t e, const char* what);  // records message, returns (in
     }                                    \
   } while (0)
 
+// number of kernels launched by the library since load (bench.py reports it as gpu_launches)
+void count_launches(int n);
+long launch_count();
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 #ifdef __CUDACC__

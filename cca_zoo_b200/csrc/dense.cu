@@ -89,6 +89,7 @@ int gemm(int transa, int transb, int m, int n, int k, T alpha, const T* A, int64
   else if (transa && !transb) gemm_kernel<T, 1, 0><<<grid, 256, 0, stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
   else if (!transa && transb) gemm_kernel<T, 0, 1><<<grid, 256, 0, stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
   else gemm_kernel<T, 1, 1><<<grid, 256, 0, stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  count_launches(1);
   CCAB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -122,7 +123,7 @@ int whiten_rows(int d, const T* lam, const T* Vt, int64_t ldv, double c, double 
   CCAB_CHECK_ARG(d >= 1, "bad dimension");
   if (rank_out) CCAB_CUDA(cudaMemsetAsync(rank_out, 0, sizeof(int), stream));
   whiten_rows_kernel<T><<<d, 128, 0, stream>>>(d, lam, Vt, ldv, c, floor_add, floor_dev, scale, rank_tol, max_rank,
-                                               lam_floor, Wt, ldw, g_out, rank_out);
+                                               lam_floor, Wt, ldw, g_out, rank_out); count_launches(1);
   CCAB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -156,7 +157,7 @@ int scale_rows_cols(int m, int n, const T* A, int64_t lda, const T* r, int r_pow
   if (m == 0 || n == 0) return 0;
   CCAB_CHECK_ARG(m <= 65535 * 1024, "too many rows");
   scale_kernel<T><<<dim3((unsigned)ceil_div(n, 128), (unsigned)m), 128, 0, stream>>>(m, n, A, lda, r, r_pow, c, c_pow,
-                                                                                     B, ldb);
+                                                                                     B, ldb); count_launches(1);
   CCAB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -190,7 +191,7 @@ __global__ void center_columns_kernel(int m, int n, T* __restrict__ A, int64_t l
 template <typename T>
 int center_columns(int m, int n, T* A, int64_t lda, cudaStream_t stream) {
   if (m == 0 || n == 0) return 0;
-  center_columns_kernel<T><<<(unsigned)ceil_div(n, 32), 1024, 0, stream>>>(m, n, A, lda);
+  center_columns_kernel<T><<<(unsigned)ceil_div(n, 32), 1024, 0, stream>>>(m, n, A, lda); count_launches(1);
   CCAB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -218,7 +219,7 @@ __global__ void frobenius_kernel(int m, int n, const T* __restrict__ A, int64_t 
 
 template <typename T>
 int frobenius_norm(int m, int n, const T* A, int64_t lda, T* out, cudaStream_t stream) {
-  frobenius_kernel<T><<<1, 1024, 0, stream>>>(m, n, A, lda, out);  // deterministic single-block reduction
+  frobenius_kernel<T><<<1, 1024, 0, stream>>>(m, n, A, lda, out); count_launches(1);  // deterministic single-block reduction
   CCAB_CUDA(cudaGetLastError());
   return 0;
 }

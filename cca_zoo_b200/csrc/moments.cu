@@ -44,6 +44,26 @@ int make_layout(int n_views, const int64_t* dims, ColumnLayout* L) {
   return 0;
 }
 
+// optional timing of the tcgen05 kernel alone (bench.py roofline): events on the launching stream
+static bool g_prof_on = false;
+static cudaEvent_t g_prof_e0 = nullptr, g_prof_e1 = nullptr;
+static bool g_prof_valid = false;
+void moments_profile_enable(int on) {
+  g_prof_on = on != 0;
+  g_prof_valid = false;
+  if (g_prof_on && !g_prof_e0) {
+    cudaEventCreate(&g_prof_e0);
+    cudaEventCreate(&g_prof_e1);
+  }
+}
+float moments_profile_last_ms() {
+  if (!g_prof_valid) return -1.f;
+  float ms = -1.f;
+  if (cudaEventSynchronize(g_prof_e1) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, g_prof_e0, g_prof_e1) != cudaSuccess) return -1.f;
+  return ms;
+}
+
 TcDebug& tc_debug() {
   static TcDebug d = {-1, -1, -1, 0};
   return d;
@@ -569,7 +589,7 @@ int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t*
       splitbuf += 2 * (size_t)n_rows * ldo * sizeof(float);
       const int64_t total = n_rows * (int64_t)L.dims[v];
       int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
-      split_tf32_kernel<<<blocks, 256, 0, stream>>>(x, n_rows, L.dims[v], lds[v], hi, lo, ldo);
+      split_tf32_kernel<<<blocks, 256, 0, stream>>>(x, n_rows, L.dims[v], lds[v], hi, lo, ldo); count_launches(1);
       CCAB_CUDA(cudaGetLastError());
       int rc = encode_view_map(&prm.maps[v], hi, n_rows, L.dims[v], ldo, P.kc);
       if (rc) return rc;
@@ -605,6 +625,7 @@ int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t*
   for (int i = L.nblocks + 1; i <= kMaxBlocks; ++i) prm.row_tile_start[i] = 0x7fffffff;
 
   dim3 grid(P.ntiles, P.num_splits);
+  if (g_prof_on) cudaEventRecord(g_prof_e0, stream);
   if (x3) {
     using Cfg = TcCfg<16, true>;
     static bool attr = false;
@@ -613,7 +634,7 @@ int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t*
                                      Cfg::kSmem));
       attr = true;
     }
-    moments_tf32_kernel<16, true><<<grid, kTcThreads, Cfg::kSmem, stream>>>(prm);
+    moments_tf32_kernel<16, true><<<grid, kTcThreads, Cfg::kSmem, stream>>>(prm); count_launches(1);
   } else {
     using Cfg = TcCfg<32, false>;
     static bool attr = false;
@@ -622,14 +643,18 @@ int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t*
                                      Cfg::kSmem));
       attr = true;
     }
-    moments_tf32_kernel<32, false><<<grid, kTcThreads, Cfg::kSmem, stream>>>(prm);
+    moments_tf32_kernel<32, false><<<grid, kTcThreads, Cfg::kSmem, stream>>>(prm); count_launches(1);
   }
   CCAB_CUDA(cudaGetLastError());
+  if (g_prof_on) {
+    cudaEventRecord(g_prof_e1, stream);
+    g_prof_valid = true;
+  }
 
   const size_t total = (size_t)L.Dp * L.Dp + L.Dp;
   int rblocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
   reduce_partials_kernel<float><<<rblocks, 256, 0, stream>>>(prm.partial, prm.partial_sum, P.num_splits, L.Dp,
-                                                            kBlk, moments_out);
+                                                            kBlk, moments_out); count_launches(1);
   CCAB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -661,13 +686,13 @@ int moments_simt(const ColumnLayout& L, const void* const* views, const int64_t*
   // partial sums of non-diagonal 64-blocks inside a 128-block are never written by the kernel: the
   // reducer only reads what a tile wrote (block-triangle test at 64 granularity).
   dim3 grid(P.ntiles, P.num_splits);
-  moments_simt_kernel<T><<<grid, 256, 0, stream>>>(prm);
+  moments_simt_kernel<T><<<grid, 256, 0, stream>>>(prm); count_launches(1);
   CCAB_CUDA(cudaGetLastError());
   const size_t total = (size_t)L.Dp * L.Dp + L.Dp;
   int rblocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
   reduce_partials_kernel<T><<<rblocks, 256, 0, stream>>>(static_cast<const T*>(prm.partial),
                                                         static_cast<const T*>(prm.partial_sum), P.num_splits,
-                                                        L.Dp, 64, moments_out);
+                                                        L.Dp, 64, moments_out); count_launches(1);
   CCAB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -693,7 +718,7 @@ int covariance_from_moments(const ColumnLayout& L, const double* moments, double
   }
   dim3 block(32, 8);
   dim3 grid((unsigned)ceil_div(L.D, 32), (unsigned)ceil_div(L.D, 8));
-  covariance_kernel<Tout><<<grid, block, 0, stream>>>(p, moments, n_total, center, C, ldc, mean);
+  covariance_kernel<Tout><<<grid, block, 0, stream>>>(p, moments, n_total, center, C, ldc, mean); count_launches(1);
   CCAB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -48,4 +48,8 @@ struct TcDebug {
 };
 TcDebug& tc_debug();
 
+// CUDA-event timing of the tcgen05 kernel launch alone (for bench.py's roofline line)
+void moments_profile_enable(int on);
+float moments_profile_last_ms();
+
 }  // namespace ccab

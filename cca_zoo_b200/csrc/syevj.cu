@@ -513,7 +513,7 @@ int jacobi_solve(const JacobiArgs<T>& a, void* ws, size_t ws_bytes, cudaStream_t
   {
     const int rows = std::max(m, P.n_pad);
     dim3 grid((unsigned)std::min<int64_t>(ceil_div(rows, 256), 64), P.n_pad, batch);
-    jacobi_init_kernel<T><<<grid, 256, 0, stream>>>(a.in, a.ld_in, a.batch_stride_in, a.colmajor_in, m, n, c, shift);
+    jacobi_init_kernel<T><<<grid, 256, 0, stream>>>(a.in, a.ld_in, a.batch_stride_in, a.colmajor_in, m, n, c, shift); count_launches(1);
     CCAB_CUDA(cudaGetLastError());
   }
   const T tol = a.tol > 0 ? (T)a.tol : (T)(4.0 * (double)Eps<T>::v * std::sqrt((double)m));
@@ -528,9 +528,9 @@ int jacobi_solve(const JacobiArgs<T>& a, void* ws, size_t ws_bytes, cudaStream_t
   int rc = 0;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     for (int r = 0; r < rounds; ++r) {
-      jacobi_gram_kernel<T><<<dim3(P.npairs, P.R, batch), 256, 0, stream>>>(c, r);
-      jacobi_solve_kernel<T><<<dim3(P.npairs, batch), 256, 0, stream>>>(c, tol, inner_sweeps);
-      jacobi_apply_kernel<T><<<dim3(P.npairs, apply_chunks, batch), 128, 0, stream>>>(c, r);
+      jacobi_gram_kernel<T><<<dim3(P.npairs, P.R, batch), 256, 0, stream>>>(c, r); count_launches(1);
+      jacobi_solve_kernel<T><<<dim3(P.npairs, batch), 256, 0, stream>>>(c, tol, inner_sweeps); count_launches(1);
+      jacobi_apply_kernel<T><<<dim3(P.npairs, apply_chunks, batch), 128, 0, stream>>>(c, r); count_launches(1);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { rc = cuda_fail(e, "jacobi sweep launch"); break; }
@@ -547,18 +547,18 @@ int jacobi_solve(const JacobiArgs<T>& a, void* ws, size_t ws_bytes, cudaStream_t
     last_ratio = worst;
     if (getenv("CCAB_JACOBI_VERBOSE")) fprintf(stderr, "[syevj] sweep %d worst offdiag %.3e (tol %.3e)\n", sweep, worst, (double)tol);
     if (worst <= (float)tol) break;
-    jacobi_reset_stat_kernel<<<1, 1024, 0, stream>>>(c.stat, batch);
+    jacobi_reset_stat_kernel<<<1, 1024, 0, stream>>>(c.stat, batch); count_launches(1);
   }
   cudaFreeHost(h_stat);
   if (rc) return rc;
   if (a.info) { a.info[0] = sweeps_done; }
   if (a.final_offdiag) *a.final_offdiag = last_ratio;
 
-  jacobi_values_kernel<T><<<dim3((unsigned)ceil_div(P.n_pad, 8), batch), 256, 0, stream>>>(c, n, a.svd_mode, shift, vals, vnorm);
-  jacobi_rank_kernel<T><<<dim3((unsigned)ceil_div(P.n_pad, 256), batch), 256, 0, stream>>>(vals, P.n_pad, rank);
+  jacobi_values_kernel<T><<<dim3((unsigned)ceil_div(P.n_pad, 8), batch), 256, 0, stream>>>(c, n, a.svd_mode, shift, vals, vnorm); count_launches(1);
+  jacobi_rank_kernel<T><<<dim3((unsigned)ceil_div(P.n_pad, 256), batch), 256, 0, stream>>>(vals, P.n_pad, rank); count_launches(1);
   jacobi_gather_kernel<T><<<dim3(P.n_pad, batch), 128, 0, stream>>>(
       c, n, vals, vnorm, rank, a.out_vals, a.vals_stride, a.out_right, a.ld_right, a.right_stride, a.out_left, a.ld_left,
-      a.left_stride);
+      a.left_stride); count_launches(1);
   CCAB_CUDA(cudaGetLastError());
   return 0;
 }

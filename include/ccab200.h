@@ -38,6 +38,8 @@ extern "C" {
 
 int ccab_version(void);
 const char* ccab_last_error(void);
+/* kernels launched by this library since it was loaded (bench.py's gpu_launches) */
+int64_t ccab_launch_count(void);
 
 /* ---- K1: block moments --------------------------------------------------------------------------
  * M = [X_1 .. X_m]^T [X_1 .. X_m] and s = 1^T [X_1 .. X_m] over the n_rows samples this process
@@ -122,6 +124,12 @@ int ccab_center_columns(int dtype, int m, int n, void* A, int64_t lda, void* str
 
 /* out[0] (device) = ||A||_F of an m x n row-major matrix */
 int ccab_frobenius_norm(int dtype, int m, int n, const void* A, int64_t lda, void* out, void* stream);
+
+/* Measurement hook: when enabled, CUDA events are recorded on the caller's stream immediately around the
+ * tcgen05 moment-kernel launch of ccab_moments (TF32 paths); ccab_profile_moments_last_ms() waits for the
+ * last pair and returns the kernel's duration in ms (-1 if none). */
+int ccab_profile_moments(int enable);
+double ccab_profile_moments_last_ms(void);
 
 /* Debug/tuning knobs of the tcgen05 kernel ("lbo_bytes", "sbo_bytes", "tma_dtype", "force_splits");
  * value < 0 restores the default.  Not part of the stable surface. */
