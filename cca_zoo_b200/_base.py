@@ -98,6 +98,10 @@ class BaseModel(BaseEstimator, ABC):
         n_local = int(dev_views[0].shape[0])
         mom = ops.moments(dev_views, precision=self.precision)
         mom, n_total = parallel.allreduce_moments(mom, n_local)
+        # NaN / inf anywhere in the inputs poisons the moments: one tiny device-side check replaces the
+        # reference's host scan (check_array) for tensors that never visit the host
+        if any(isinstance(v, torch.Tensor) for v in validated) and not bool(torch.isfinite(mom).all()):
+            raise ValueError("Input contains NaN or infinity.")
         solve_dtype = torch.float64 if (self._solve_in_float64 or in_dtype == torch.float64) else torch.float32
         C, mean = ops.covariance(mom, dims, n_total, center=bool(self.center), dtype=solve_dtype)
         self.n_views_ = len(dev_views)

@@ -29,8 +29,8 @@ def validate_views(views, min_views: int = 2):
                 v = v.to(torch.float64)
             if v.numel() == 0:
                 raise ValueError("Found array with 0 sample(s) or 0 feature(s).")
-            if not bool(torch.isfinite(v).all()):
-                raise ValueError("Input contains NaN or infinity.")
+            # finiteness of torch inputs is checked on the device after the copy (see
+            # BaseModel._fit_device): a host-side scan of a large pinned tensor would dominate fit()
             processed.append(v)
         else:
             processed.append(check_array(v, ensure_2d=True, allow_nd=False, dtype="numeric"))

@@ -322,6 +322,7 @@ int ccab_debug_set(const char* key, int value) {
   else if (!strcmp(key, "tma_dtype")) d.tma_dtype = value;
   else if (!strcmp(key, "force_splits")) d.force_splits = value;
   else if (!strcmp(key, "jacobi_inner_sweeps")) jacobi_inner_sweeps() = value;
+  else if (!strcmp(key, "jacobi_force_unfused")) jacobi_force_unfused() = value;
   else {
     set_error("unknown debug key %s", key);
     return -1;

@@ -19,6 +19,8 @@
 // cca_zoo/linear/_mcca.py:117,170, cca_zoo/linear/_gcca.py:102, cca_zoo/deep/objectives.py:19.
 #include "syevj.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -60,72 +62,102 @@ __host__ __device__ __forceinline__ void rr_pair(int np, int r, int i, int& p, i
   q = a < b ? b : a;
 }
 
-template <typename T>
-__device__ __forceinline__ void jacobi_cs(T app, T aqq, T apq, T& c, T& s, bool& rotated) {
-  const T thresh = Eps<T>::v * sqrt(fabs(app) * fabs(aqq));
-  if (fabs(apq) <= thresh || apq == T(0)) {
-    c = T(1);
-    s = T(0);
+// Rotation (c, s) that annihilates a_pq of [[app, apq], [apq, aqq]]:  t = h / (d + sgn(d) sqrt(d^2 + h^2))
+// with d = aqq - app, h = 2 apq; c = 1/sqrt(1 + t^2), s = t c.  Fast reciprocal / rsqrt are enough: the
+// accumulated Q is re-orthonormalised before it is applied (reorthonormalise below).
+__device__ __forceinline__ void jacobi_cs(float app, float aqq, float apq, float& c, float& s, bool& rotated) {
+  const float e = Eps<float>::v;
+  if (apq * apq <= e * e * fabsf(app * aqq) || apq == 0.f) {
+    c = 1.f;
+    s = 0.f;
     return;
   }
-  const T tau = (aqq - app) / (T(2) * apq);
-  const T t = (tau >= T(0) ? T(1) : T(-1)) / (fabs(tau) + sqrt(T(1) + tau * tau));
-  c = T(1) / sqrt(T(1) + t * t);
+  const float d = aqq - app, h = 2.f * apq;
+  const float r = sqrtf(fmaf(d, d, h * h));
+  const float t = __fdividef(h, d + copysignf(r, d));
+  c = rsqrtf(fmaf(t, t, 1.f));
+  s = t * c;
+  rotated = true;
+}
+__device__ __forceinline__ void jacobi_cs(double app, double aqq, double apq, double& c, double& s, bool& rotated) {
+  const double e = Eps<double>::v;
+  if (apq * apq <= e * e * fabs(app * aqq) || apq == 0.0) {
+    c = 1.0;
+    s = 0.0;
+    return;
+  }
+  const double d = aqq - app, h = 2.0 * apq;
+  const double r = sqrt(fma(d, d, h * h));
+  const double t = h / (d + copysign(r, d));
+  c = rsqrt(fma(t, t, 1.0));
   s = t * c;
   rotated = true;
 }
 
-// Parallel cyclic two-sided Jacobi on an S x S symmetric matrix in shared memory.
-// Wa/Wb: ping-pong copies (stride S+1), Q: accumulated rotations (stride S+1, starts as I).
-// Returns with the diagonalised matrix in the buffer pointed to by the return value.
+// Parallel cyclic two-sided Jacobi on a 32 x 32 symmetric matrix in shared memory, 256 threads.
+// Thread (i, j) owns the 2x2 block of rotation pairs (i, j) in each of the 31 tournament steps; lanes
+// 0..15 of every warp each compute the rotation of pair `lane` once and the warp shares them by shuffle.
+// Wa/Wb: ping-pong copies (stride 33), Q: accumulated rotations (stride 33, starts as I), pairs: the
+// (S-1) x 16 tournament table.  Returns the buffer holding the (nearly) diagonal result.
 template <typename T, int S>
-__device__ T* small_syevj(T* Wa, T* Wb, T* Q, int max_sweeps) {
+__device__ T* small_syevj(T* Wa, T* Wb, T* Q, const uchar2* pairs, int max_sweeps) {
+  static_assert(S == 32, "the thread mapping below is written for 32 x 32 panels and 256 threads");
   constexpr int H = S / 2;
   constexpr int SP = S + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = lane & 15;
+  const int i = 2 * warp + (lane >> 4);
   T* cur = Wa;
   T* nxt = Wb;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     int any = 0;
     for (int step = 0; step < S - 1; ++step) {
-      bool rot = false;
-      for (int blk = threadIdx.x; blk < H * H; blk += blockDim.x) {
-        const int i = blk / H, j = blk % H;
-        int pi, qi, pj, qj;
-        rr_pair(S, step, i, pi, qi);
-        rr_pair(S, step, j, pj, qj);
-        T ci, si, cj, sj;
-        bool ri = false, rj = false;
-        jacobi_cs(cur[pi * SP + pi], cur[qi * SP + qi], cur[pi * SP + qi], ci, si, ri);
-        jacobi_cs(cur[pj * SP + pj], cur[qj * SP + qj], cur[pj * SP + qj], cj, sj, rj);
-        const T x00 = cur[pi * SP + pj], x01 = cur[pi * SP + qj];
-        const T x10 = cur[qi * SP + pj], x11 = cur[qi * SP + qj];
-        const T y00 = cj * x00 - sj * x01, y01 = sj * x00 + cj * x01;
-        const T y10 = cj * x10 - sj * x11, y11 = sj * x10 + cj * x11;
-        T z00 = ci * y00 - si * y10, z10 = si * y00 + ci * y10;
-        T z01 = ci * y01 - si * y11, z11 = si * y01 + ci * y11;
-        if (i == j && ri) { z01 = T(0); z10 = T(0); }
-        nxt[pi * SP + pj] = z00;
-        nxt[pi * SP + qj] = z01;
-        nxt[qi * SP + pj] = z10;
-        nxt[qi * SP + qj] = z11;
-        // Q <- Q J_i for rows j and j+H (each (row, pair) owned by exactly one thread)
-        if (ri) {
+      const uchar2 pq = pairs[step * H + j];
+      const int pj = pq.x, qj = pq.y;
+      T cj, sj;
+      bool rj = false;
+      jacobi_cs(cur[pj * SP + pj], cur[qj * SP + qj], cur[pj * SP + qj], cj, sj, rj);
+      const T ci = __shfl_sync(0xffffffffu, cj, i);
+      const T si = __shfl_sync(0xffffffffu, sj, i);
+      const int pi = __shfl_sync(0xffffffffu, pj, i);
+      const int qi = __shfl_sync(0xffffffffu, qj, i);
+      const bool ri = __shfl_sync(0xffffffffu, (int)rj, i) != 0;
+      const T x00 = cur[pi * SP + pj], x01 = cur[pi * SP + qj];
+      const T x10 = cur[qi * SP + pj], x11 = cur[qi * SP + qj];
+      const T y00 = cj * x00 - sj * x01, y01 = sj * x00 + cj * x01;
+      const T y10 = cj * x10 - sj * x11, y11 = sj * x10 + cj * x11;
+      T z00 = ci * y00 - si * y10, z10 = si * y00 + ci * y10;
+      T z01 = ci * y01 - si * y11, z11 = si * y01 + ci * y11;
+      if (i == j && ri) { z01 = T(0); z10 = T(0); }
+      nxt[pi * SP + pj] = z00;
+      nxt[pi * SP + qj] = z01;
+      nxt[qi * SP + pj] = z10;
+      nxt[qi * SP + qj] = z11;
+      if (ri) {  // Q <- Q J_i for rows j and j+H (each (row, pair) owned by exactly one thread)
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int r = j + h * H;
-            const T a = Q[r * SP + pi], b = Q[r * SP + qi];
-            Q[r * SP + pi] = ci * a - si * b;
-            Q[r * SP + qi] = si * a + ci * b;
-          }
+        for (int hh = 0; hh < 2; ++hh) {
+          const int r = j + hh * H;
+          const T a = Q[r * SP + pi], b = Q[r * SP + qi];
+          Q[r * SP + pi] = ci * a - si * b;
+          Q[r * SP + qi] = si * a + ci * b;
         }
-        rot |= (ri && i == j);
       }
-      any |= __syncthreads_or(rot ? 1 : 0);
+      any |= __syncthreads_or((ri && i == j) ? 1 : 0);
       T* tmp = cur; cur = nxt; nxt = tmp;
     }
     if (!any) break;
   }
   return cur;
+}
+
+// tournament table in shared memory: pairs[step * 16 + i] = (p, q), p < q
+template <int S>
+__device__ void fill_pair_table(uchar2* pairs) {
+  for (int e = threadIdx.x; e < (S - 1) * (S / 2); e += blockDim.x) {
+    int p, q;
+    rr_pair(S, e / (S / 2), e % (S / 2), p, q);
+    pairs[e] = make_uchar2((unsigned char)p, (unsigned char)q);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -219,6 +251,8 @@ __global__ void __launch_bounds__(256) jacobi_solve_kernel(const JacobiCtx<T> c,
   __shared__ T Q[kS * kSP];
   __shared__ int rank_of[kS];
   __shared__ float ratio_s;
+  __shared__ uchar2 pairs[(kS - 1) * (kS / 2)];
+  fill_pair_table<kS>(pairs);
   const int pair = blockIdx.x, b = blockIdx.y;
   const T* Wp = c.Wpart + ((size_t)b * c.npairs + pair) * c.R * (kS * kS);
   if (threadIdx.x == 0) ratio_s = 0.f;
@@ -250,7 +284,7 @@ __global__ void __launch_bounds__(256) jacobi_solve_kernel(const JacobiCtx<T> c,
   }
   if (ratio <= (float)tol) return;  // panel already orthogonal: Q = I, apply kernel skips it
 
-  T* fin = small_syevj<T, kS>(Wa, Wb, Q, inner_sweeps);
+  T* fin = small_syevj<T, kS>(Wa, Wb, Q, pairs, inner_sweeps);
   __syncthreads();
   if (threadIdx.x < kS) {
     const int i = threadIdx.x;
@@ -321,6 +355,159 @@ __global__ void __launch_bounds__(128) jacobi_apply_kernel(const JacobiCtx<T> c,
     const int gcol = (k < kB ? p * kB + k : q * kB + k - kB);
     base[(size_t)gcol * ld + row] = y[k];
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused round: one thread-block CLUSTER per block pair.  Each CTA of the cluster keeps its row slice of
+// the [G;V] panel in shared memory, the partial Gram matrices are summed over the cluster through
+// distributed shared memory (fixed order => every CTA holds the identical W and derives the identical Q),
+// the small eigenproblem is solved redundantly per CTA and applied to the resident slice.  One launch per
+// round, the panel is read once and written once.
+// ---------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+
+template <typename T>
+__global__ void __launch_bounds__(256) jacobi_round_fused_kernel(const JacobiCtx<T> c, int round, T tol,
+                                                                 int inner_sweeps, int cs, int rows_g,
+                                                                 int rows_v) {
+  extern __shared__ __align__(16) unsigned char fused_smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int pair = blockIdx.x / cs, b = blockIdx.y;
+  const int rows = rows_g + rows_v;
+  const int LS = rows | 1;  // odd leading dimension: conflict-free column access
+  T* Ps = reinterpret_cast<T*>(fused_smem);                 // [kS][LS]
+  T* Wpart = Ps + (size_t)kS * LS;                          // [kS*kS] dense partial Gram
+  T* Wa = Wpart + kS * kS;                                  // [kS*kSP]
+  T* Wb = Wa + kS * kSP;
+  T* Q = Wb + kS * kSP;
+  uchar2* pairs = reinterpret_cast<uchar2*>(Q + kS * kSP);  // [(kS-1)*16]
+  int* rank_of = reinterpret_cast<int*>(pairs + (kS - 1) * (kS / 2));
+  float* ratio_s = reinterpret_cast<float*>(rank_of + kS);
+
+  int p, q;
+  rr_pair(c.nb, round, pair, p, q);
+  T* Gb = c.G + (size_t)b * c.n_pad * c.ldg;
+  T* Vb = c.V + (size_t)b * c.n_pad * c.n_pad;
+  const int g0 = rank * rows_g, v0 = rank * rows_v;
+  const int gn = max(0, min(rows_g, c.m - g0)), vn = max(0, min(rows_v, c.n_pad - v0));
+
+  fill_pair_table<kS>(pairs);
+  if (threadIdx.x == 0) *ratio_s = 0.f;
+  // ---- load the slice (coalesced along rows) ----
+  for (int k = 0; k < kS; ++k) {
+    const int gcol = (k < kB ? p * kB + k : q * kB + k - kB);
+    const T* gsrc = Gb + (size_t)gcol * c.ldg + g0;
+    const T* vsrc = Vb + (size_t)gcol * c.n_pad + v0;
+    T* dst = Ps + (size_t)k * LS;
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+      T v = T(0);
+      if (r < rows_g) { if (r < gn) v = gsrc[r]; }
+      else if (r - rows_g < vn) v = vsrc[r - rows_g];
+      dst[r] = v;
+    }
+  }
+  __syncthreads();
+  // ---- partial Gram over the G rows of this CTA ----
+  {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const T* a0p = Ps + (size_t)(2 * ty) * LS;
+    const T* a1p = a0p + LS;
+    const T* b0p = Ps + (size_t)(2 * tx) * LS;
+    const T* b1p = b0p + LS;
+    T acc00 = 0, acc01 = 0, acc10 = 0, acc11 = 0;
+#pragma unroll 4
+    for (int r = 0; r < gn; ++r) {
+      const T a0 = a0p[r], a1 = a1p[r], b0 = b0p[r], b1 = b1p[r];
+      acc00 = fma(a0, b0, acc00);
+      acc01 = fma(a0, b1, acc01);
+      acc10 = fma(a1, b0, acc10);
+      acc11 = fma(a1, b1, acc11);
+    }
+    Wpart[(2 * ty) * kS + 2 * tx] = acc00;
+    Wpart[(2 * ty) * kS + 2 * tx + 1] = acc01;
+    Wpart[(2 * ty + 1) * kS + 2 * tx] = acc10;
+    Wpart[(2 * ty + 1) * kS + 2 * tx + 1] = acc11;
+  }
+  cluster.sync();
+  // ---- cluster-wide sum through distributed shared memory, same order in every CTA ----
+  for (int e = threadIdx.x; e < kS * kS; e += blockDim.x) {
+    T acc = 0;
+    for (int r = 0; r < cs; ++r) acc += cluster.map_shared_rank(Wpart, r)[e];
+    const int i = e / kS, j = e % kS;
+    Wa[i * kSP + j] = acc;
+    Q[i * kSP + j] = (i == j) ? T(1) : T(0);
+  }
+  cluster.sync();  // all remote reads done: CTAs are independent from here on
+  // ---- convergence statistic of this panel ----
+  float myr = 0.f;
+  for (int e = threadIdx.x; e < kS * kS; e += blockDim.x) {
+    const int i = e / kS, j = e % kS;
+    if (i < j) {
+      const T d = Wa[i * kSP + i] * Wa[j * kSP + j];
+      const T w = fabs(Wa[i * kSP + j]);
+      if (d > T(0) && w > T(0)) myr = fmaxf(myr, (float)(w / sqrt(d)));
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) myr = fmaxf(myr, __shfl_xor_sync(0xffffffffu, myr, o));
+  if ((threadIdx.x & 31) == 0 && myr > 0.f) atomicMax(reinterpret_cast<int*>(ratio_s), __float_as_int(myr));
+  __syncthreads();
+  const float ratio = *ratio_s;
+  if (rank == 0 && threadIdx.x == 0) atomicMax(c.stat + b, __float_as_uint(ratio));
+  if (ratio <= (float)tol) return;  // uniform over the cluster (identical W everywhere)
+
+  T* fin = small_syevj<T, kS>(Wa, Wb, Q, pairs, inner_sweeps);
+  __syncthreads();
+  if (threadIdx.x < kS) {
+    const int i = threadIdx.x;
+    const T li = fin[i * kSP + i];
+    int rk = 0;
+    for (int j = 0; j < kS; ++j) {
+      const T lj = fin[j * kSP + j];
+      rk += (lj > li || (lj == li && j < i)) ? 1 : 0;
+    }
+    rank_of[i] = rk;
+  }
+  __syncthreads();
+  T* other = (fin == Wa) ? Wb : Wa;
+  reorthonormalise<T, kS>(Q, other, fin);  // fin <- orthonormalised Q (stride kSP)
+  // Qs: dense, column-permuted (sorted) copy for the apply loop, reuse Wpart
+  for (int e = threadIdx.x; e < kS * kS; e += blockDim.x) {
+    const int r = e / kS, i = e % kS;
+    Wpart[r * kS + rank_of[i]] = fin[r * kSP + i];
+  }
+  __syncthreads();
+  // ---- apply to the resident slice, write back (coalesced along rows) ----
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    const bool isg = r < rows_g;
+    const int lr = isg ? r : r - rows_g;
+    if (lr >= (isg ? gn : vn)) continue;
+    T x[kS], y[kS];
+#pragma unroll
+    for (int k = 0; k < kS; ++k) {
+      x[k] = Ps[(size_t)k * LS + r];
+      y[k] = T(0);
+    }
+#pragma unroll
+    for (int k = 0; k < kS; ++k) {
+#pragma unroll
+      for (int j = 0; j < kS; ++j) y[j] = fma(x[k], Wpart[k * kS + j], y[j]);
+    }
+    T* dstbase = isg ? (Gb + g0 + lr) : (Vb + v0 + lr);
+    const int64_t ld = isg ? c.ldg : (int64_t)c.n_pad;
+#pragma unroll
+    for (int k = 0; k < kS; ++k) {
+      const int gcol = (k < kB ? p * kB + k : q * kB + k - kB);
+      dstbase[(size_t)gcol * ld] = y[k];
+    }
+  }
+}
+
+template <typename T>
+static size_t fused_smem_bytes(int rows) {
+  const int LS = rows | 1;
+  return ((size_t)kS * LS + kS * kS + 3 * kS * kSP) * sizeof(T) + (kS - 1) * (kS / 2) * sizeof(uchar2) +
+         kS * sizeof(int) + 64;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -439,6 +626,10 @@ int& jacobi_inner_sweeps() {
   static int v = 0;
   return v;
 }
+int& jacobi_force_unfused() {
+  static int v = 0;
+  return v;
+}
 
 namespace {
 inline size_t al(size_t x) { return (x + 255) & ~size_t(255); }
@@ -518,7 +709,27 @@ int jacobi_solve(const JacobiArgs<T>& a, void* ws, size_t ws_bytes, cudaStream_t
   }
   const T tol = a.tol > 0 ? (T)a.tol : (T)(4.0 * (double)Eps<T>::v * std::sqrt((double)m));
   const int max_sweeps = a.max_sweeps > 0 ? a.max_sweeps : (std::is_same<T, float>::value ? 16 : 24);
-  const int inner_sweeps = jacobi_inner_sweeps() > 0 ? jacobi_inner_sweeps() : 2;
+  const int inner_sweeps = jacobi_inner_sweeps() > 0 ? jacobi_inner_sweeps() : 1;
+  // fused cluster path: smallest cluster (<= 8 CTAs) whose row slice fits comfortably in shared memory
+  int cs = 0, rows_g = 0, rows_v = 0;
+  size_t fused_bytes = 0;
+  if (!jacobi_force_unfused()) {
+    for (int cand = 1; cand <= 8; cand *= 2) {
+      const int rg = (int)ceil_div(m, cand), rv = (int)ceil_div(P.n_pad, cand);
+      const size_t bytes = fused_smem_bytes<T>(rg + rv);
+      const size_t limit = (size_t)P.npairs * batch * cand >= 296 ? 100 * 1024 : 200 * 1024;
+      if (bytes <= limit) {
+        cs = cand; rows_g = rg; rows_v = rv; fused_bytes = bytes;
+        // prefer more CTAs per pair while the machine is not full
+        if ((size_t)P.npairs * batch * cand >= 148 || cand == 8) break;
+      }
+    }
+  }
+  if (cs) {
+    cudaError_t e = cudaFuncSetAttribute(jacobi_round_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)fused_bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(jacobi_round_fused_kernel)");
+  }
   const int rounds = P.nb - 1;
   const int apply_chunks = (int)(ceil_div(m, 128) + ceil_div(P.n_pad, 128));
   int sweeps_done = 0;
@@ -528,10 +739,31 @@ int jacobi_solve(const JacobiArgs<T>& a, void* ws, size_t ws_bytes, cudaStream_t
   int rc = 0;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     for (int r = 0; r < rounds; ++r) {
-      jacobi_gram_kernel<T><<<dim3(P.npairs, P.R, batch), 256, 0, stream>>>(c, r); count_launches(1);
-      jacobi_solve_kernel<T><<<dim3(P.npairs, batch), 256, 0, stream>>>(c, tol, inner_sweeps); count_launches(1);
-      jacobi_apply_kernel<T><<<dim3(P.npairs, apply_chunks, batch), 128, 0, stream>>>(c, r); count_launches(1);
+      if (cs) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(P.npairs * cs, batch, 1);
+        cfg.blockDim = dim3(256, 1, 1);
+        cfg.dynamicSmemBytes = fused_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, jacobi_round_fused_kernel<T>, c, r, tol, inner_sweeps, cs, rows_g,
+                                            rows_v);
+        if (le != cudaSuccess) { rc = cuda_fail(le, "jacobi_round_fused_kernel launch"); break; }
+        count_launches(1);
+      } else {
+        jacobi_gram_kernel<T><<<dim3(P.npairs, P.R, batch), 256, 0, stream>>>(c, r); count_launches(1);
+        jacobi_solve_kernel<T><<<dim3(P.npairs, batch), 256, 0, stream>>>(c, tol, inner_sweeps); count_launches(1);
+        jacobi_apply_kernel<T><<<dim3(P.npairs, apply_chunks, batch), 128, 0, stream>>>(c, r); count_launches(1);
+      }
     }
+    if (rc) break;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { rc = cuda_fail(e, "jacobi sweep launch"); break; }
     e = cudaMemcpyAsync(h_stat, c.stat, sizeof(unsigned) * batch, cudaMemcpyDeviceToHost, stream);
