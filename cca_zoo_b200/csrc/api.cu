@@ -321,6 +321,9 @@ int ccab_debug_set(const char* key, int value) {
   else if (!strcmp(key, "sbo_bytes")) d.sbo_bytes = value;
   else if (!strcmp(key, "tma_dtype")) d.tma_dtype = value;
   else if (!strcmp(key, "force_splits")) d.force_splits = value;
+  else if (!strcmp(key, "tc_variant")) d.variant = value < 0 ? 0 : value;
+  else if (!strcmp(key, "tc_kc")) d.kc = value < 0 ? 0 : value;
+  else if (!strcmp(key, "tc_dry_run")) d.dry_run = value < 0 ? 0 : value;
   else if (!strcmp(key, "jacobi_inner_sweeps")) jacobi_inner_sweeps() = value;
   else if (!strcmp(key, "jacobi_force_unfused")) jacobi_force_unfused() = value;
   else {

@@ -65,7 +65,7 @@ float moments_profile_last_ms() {
 }
 
 TcDebug& tc_debug() {
-  static TcDebug d = {-1, -1, -1, 0};
+  static TcDebug d = {-1, -1, -1, 0, 0, 0, 0};
   return d;
 }
 
@@ -160,7 +160,7 @@ moments_tf32_kernel(const __grid_constant__ TcParams p) {
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0 && has_work) {
+    if (has_work && elect_one()) {
       const int vA = p.blk_view[bi], colA = p.blk_col0[bi];
       int vB[2], colB[2];
       for (int b = 0; b < 2; ++b) {
@@ -199,22 +199,23 @@ moments_tf32_kernel(const __grid_constant__ TcParams p) {
       const uint32_t idesc_sum = umma_idesc_tf32_mn(128, 16);
       const uint32_t lbo = p.lbo_bytes, sbo = p.sbo_bytes;
       const uint64_t ones_desc = umma_smem_desc(smem_u32(ones), lbo, sbo, kUmmaLayout);
+      const uint64_t descA0 = umma_smem_desc(smem_u32(smem), lbo, sbo, kUmmaLayout);
+      const uint64_t descB0 = umma_smem_desc(smem_u32(smem) + 4 * Cfg::kAtom, lbo, sbo, kUmmaLayout);
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t acc = 0u;
       for (int c = c0; c < c1; ++c) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sA = smem_u32(smem + stage * Cfg::kStage);
-          const uint32_t sB = sA + 4 * Cfg::kAtom;
+        if (elect_one()) {
+          const uint64_t so = (uint64_t)((stage * Cfg::kStage) >> 4);
 #pragma unroll
           for (int kk = 0; kk < KC / 8; ++kk) {
-            const uint32_t acc = (c > c0 || kk > 0) ? 1u : 0u;
-            const uint64_t a_hi = umma_smem_desc(sA + kk * 1024, lbo, sbo, kUmmaLayout);
-            const uint64_t b_hi = umma_smem_desc(sB + kk * 1024, lbo, sbo, kUmmaLayout);
+            const uint64_t a_hi = descA0 + so + (uint64_t)(kk * 64);
+            const uint64_t b_hi = descB0 + so + (uint64_t)(kk * 64);
             if (X3) {
-              const uint64_t a_lo = umma_smem_desc(sA + Cfg::kSet + kk * 1024, lbo, sbo, kUmmaLayout);
-              const uint64_t b_lo = umma_smem_desc(sB + Cfg::kSet + kk * 1024, lbo, sbo, kUmmaLayout);
+              const uint64_t a_lo = a_hi + (uint64_t)(Cfg::kSet >> 4);
+              const uint64_t b_lo = b_hi + (uint64_t)(Cfg::kSet >> 4);
               // small cross terms first, then the leading term
               umma_tf32(tmem_base, a_lo, b_hi, idesc_main, acc);
               umma_tf32(tmem_base, a_hi, b_lo, idesc_main, 1u);
@@ -227,13 +228,15 @@ moments_tf32_kernel(const __grid_constant__ TcParams p) {
               umma_tf32(tmem_base, a_hi, b_hi, idesc_main, acc);
               if (do_sum) umma_tf32(tmem_base + kSumCol, a_hi, ones_desc, idesc_sum, acc);
             }
+            acc = 1u;
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
         }
+        acc = 1u;
         __syncwarp();
         if (++stage == kTcStages) { stage = 0; phase ^= 1; }
       }
-      if (lane == 0) umma_commit(tmem_full_bar);
+      if (elect_one()) umma_commit(tmem_full_bar);
       __syncwarp();
     }
   } else {
@@ -276,6 +279,210 @@ moments_tf32_kernel(const __grid_constant__ TcParams p) {
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =============================================================================================
+// CTA-pair variant: tcgen05.mma.cta_group::2, 256 x 256 output tiles (pair-blocks of two 128-column
+// blocks).  CTA r of the cluster loads A block 2I+r and B block 2J+r (32 KB per stage instead of 48 KB),
+// the leader's single MMA thread drives both tensor cores, every B half is read from shared memory once for
+// both SMs: shared-memory and L2->SM traffic per MAC drop by 1.5x against the 1-CTA 128x256 tile.
+// =============================================================================================
+struct alignas(64) TcParams2 {
+  CUtensorMap maps[2 * kMaxViews];
+  float* partial;      // [S][Dp2][Dp2]
+  float* partial_sum;  // [S][Dp2]
+  int total_chunks, chunks_per_split, num_splits;
+  int nblocks, nb2, Dp2;
+  int lbo_bytes, sbo_bytes;
+  int dry_run;  // debug: after the first ring fill, recycle stale stages without TMA (isolates the MMA rate)
+  int blk_col0[kMaxBlocks + 2];      // entry nblocks (and nblocks+1) = dummy block: out-of-bounds -> zeros
+  uint8_t blk_view[kMaxBlocks + 2];
+};
+static_assert(sizeof(TcParams2) <= 4096, "kernel parameter space");
+
+template <int KC, bool X3, int NS>
+struct Tc2Cfg {
+  static constexpr int kStages = NS;
+  static constexpr int kAtom = KC * 128;
+  static constexpr int kSet = 8 * kAtom;  // A (4 atoms) + B half (4 atoms)
+  static constexpr int kStage = (X3 ? 2 : 1) * kSet;
+  static constexpr int kSmem = NS * kStage + 1024 + 1024 + 256;
+};
+
+template <int KC, bool X3, int NS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+moments_tf32_2cta_kernel(const __grid_constant__ TcParams2 p) {
+  using Cfg = Tc2Cfg<KC, X3, NS>;
+  constexpr int kTc2Stages = NS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ones = smem + kTc2Stages * Cfg::kStage;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ones + 1024);
+  uint64_t* empty_bar = full_bar + kTc2Stages;
+  uint64_t* tmem_full_bar = empty_bar + kTc2Stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  int t = blockIdx.x >> 1, I = 0, rowlen = p.nb2;
+  while (t >= rowlen) { t -= rowlen; ++I; --rowlen; }
+  const int J = I + t;
+  const bool do_sum = (I == J);
+  const int blkA = min(2 * I + (int)rank, p.nblocks);  // index nblocks = dummy (zeros)
+  const int blkB = min(2 * J + (int)rank, p.nblocks);
+  const int split = blockIdx.y;
+  const int c0 = split * p.chunks_per_split;
+  const int c1 = min(c0 + p.chunks_per_split, p.total_chunks);
+  const bool has_work = c1 > c0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTc2Stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int v = 0; v < kMaxViews; ++v) {
+      tma_prefetch_desc(&p.maps[v]);
+      if (X3) tma_prefetch_desc(&p.maps[kMaxViews + v]);
+    }
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
+  if (warp >= 2) {
+    float* o = reinterpret_cast<float*>(ones);
+    for (int i = threadIdx.x - 64; i < 256; i += 128) o[i] = 1.0f;
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any cross-CTA arrive / TMA credit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs, each loads its own halves) =================
+    if (has_work && elect_one()) {
+      const int vA = p.blk_view[blkA], colA = p.blk_col0[blkA];
+      const int vB = p.blk_view[blkB], colB = p.blk_col0[blkB];
+      const uint32_t bytes_pair = 2u * (X3 ? 2u : 1u) * 8u * Cfg::kAtom;  // both CTAs credit the leader's barrier
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = c0; c < c1; ++c) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (p.dry_run && c - c0 >= kTc2Stages) {
+          if (leader) mbar_arrive(&full_bar[stage]);
+          if (++stage == kTc2Stages) { stage = 0; phase ^= 1; }
+          continue;
+        }
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], bytes_pair);
+        uint8_t* st = smem + stage * Cfg::kStage;
+        const int row = c * KC;
+#pragma unroll
+        for (int o = 0; o < (X3 ? 2 : 1); ++o) {
+          uint8_t* base = st + o * Cfg::kSet;
+          const CUtensorMap* mA = &p.maps[o * kMaxViews + vA];
+          const CUtensorMap* mB = &p.maps[o * kMaxViews + vB];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) tma_load_2d_2sm(base + a * Cfg::kAtom, mA, &full_bar[stage], colA + 32 * a, row);
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            tma_load_2d_2sm(base + (4 + a) * Cfg::kAtom, mB, &full_bar[stage], colB + 32 * a, row);
+        }
+        if (++stage == kTc2Stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: one thread of the LEADER CTA drives both SMs =================
+    if (leader && has_work) {
+      const uint32_t idesc_main = umma_idesc_tf32_mn(256, 256);
+      const uint32_t idesc_sum = umma_idesc_tf32_mn(256, 16);
+      const uint32_t lbo = p.lbo_bytes, sbo = p.sbo_bytes;
+      const uint64_t ones_desc = umma_smem_desc(smem_u32(ones), lbo, sbo, kUmmaLayout);
+      // descriptor of stage 0 / k-step 0; later ones differ only in the 14-bit start-address field
+      const uint64_t descA0 = umma_smem_desc(smem_u32(smem), lbo, sbo, kUmmaLayout);
+      const uint64_t descB0 = umma_smem_desc(smem_u32(smem) + 4 * Cfg::kAtom, lbo, sbo, kUmmaLayout);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t acc = 0u;
+      for (int c = c0; c < c1; ++c) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t so = (uint64_t)((stage * Cfg::kStage) >> 4);
+#pragma unroll
+          for (int kk = 0; kk < KC / 8; ++kk) {
+            const uint64_t a_hi = descA0 + so + (uint64_t)(kk * 64);
+            const uint64_t b_hi = descB0 + so + (uint64_t)(kk * 64);
+            if (X3) {
+              const uint64_t a_lo = a_hi + (uint64_t)(Cfg::kSet >> 4);
+              const uint64_t b_lo = b_hi + (uint64_t)(Cfg::kSet >> 4);
+              umma_tf32_2sm(tmem_base, a_lo, b_hi, idesc_main, acc);
+              umma_tf32_2sm(tmem_base, a_hi, b_lo, idesc_main, 1u);
+              umma_tf32_2sm(tmem_base, a_hi, b_hi, idesc_main, 1u);
+              if (do_sum) {
+                umma_tf32_2sm(tmem_base + kSumCol, a_lo, ones_desc, idesc_sum, acc);
+                umma_tf32_2sm(tmem_base + kSumCol, a_hi, ones_desc, idesc_sum, 1u);
+              }
+            } else {
+              umma_tf32_2sm(tmem_base, a_hi, b_hi, idesc_main, acc);
+              if (do_sum) umma_tf32_2sm(tmem_base + kSumCol, a_hi, ones_desc, idesc_sum, acc);
+            }
+            acc = 1u;
+          }
+          umma_commit_2sm(&empty_bar[stage], 3);  // frees this stage in BOTH CTAs
+        }
+        acc = 1u;
+        __syncwarp();
+        if (++stage == kTc2Stages) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit_2sm(tmem_full_bar, 3);
+      __syncwarp();
+    }
+  } else {
+    // ================= epilogue (both CTAs): own 128 accumulator rows x 256 columns =================
+    const int g = warp & 3;
+    const int m = g * 32 + lane;
+    const size_t prow_idx = (size_t)(2 * I + rank) * 128 + m;
+    float* prow = p.partial + ((size_t)split * p.Dp2 + prow_idx) * p.Dp2;
+    if (has_work) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    for (int cc = 0; cc < 8; ++cc) {
+      uint32_t r[32];
+      if (has_work) {
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + cc * 32, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = 0u;
+      }
+      float4* dst = reinterpret_cast<float4*>(prow + (size_t)(2 * J + (cc >> 2)) * 128 + (cc & 3) * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                             __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+    }
+    if (do_sum) {
+      uint32_t sv = 0u;
+      if (has_work) {
+        sv = tmem_ld_32x32b_x1(tmem_base + ((uint32_t)(g * 32) << 16) + kSumCol);
+        tmem_ld_wait();
+      }
+      p.partial_sum[(size_t)split * p.Dp2 + prow_idx] = __uint_as_float(sv);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody frees TMEM / exits while the pair is still using either CTA's resources
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
   }
 }
 
@@ -392,20 +599,22 @@ __global__ void __launch_bounds__(256) moments_simt_kernel(const SimtParams p) {
 // K2: reduce split partials (fixed order => deterministic) and finalise the covariance
 // =============================================================================================
 // valid_blk: partial tiles exist for block-row <= block-col where blocks are `blk` wide.
+// ldp: leading dimension (and row count) of each partial slab, >= Dp
 template <typename T>
 __global__ void reduce_partials_kernel(const T* __restrict__ partial, const T* __restrict__ partial_sum,
-                                       int S, int Dp, int blk, double* __restrict__ out) {
+                                       int S, int Dp, int ldp, int blk, double* __restrict__ out) {
   const size_t total = (size_t)Dp * Dp + Dp;
+  const size_t slab = (size_t)ldp * ldp;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     double acc = 0.0;
     if (i < (size_t)Dp * Dp) {
       const int r = (int)(i / Dp), c = (int)(i % Dp);
       if (r / blk <= c / blk)
-        for (int s = 0; s < S; ++s) acc += (double)partial[(size_t)s * Dp * Dp + i];
+        for (int s = 0; s < S; ++s) acc += (double)partial[(size_t)s * slab + (size_t)r * ldp + c];
     } else {
       const size_t j = i - (size_t)Dp * Dp;
-      for (int s = 0; s < S; ++s) acc += (double)partial_sum[(size_t)s * Dp + j];
+      for (int s = 0; s < S; ++s) acc += (double)partial_sum[(size_t)s * ldp + j];
     }
     out[i] = acc;
   }
@@ -502,18 +711,29 @@ int sm_count() {
 
 struct TcPlan {
   int kc, total_chunks, num_splits, chunks_per_split, ntiles;
+  int two_cta, nb2, ldp;  // ldp: leading dimension of the partial slabs (Dp, or nb2*256 for the CTA-pair kernel)
   size_t partial_bytes, sum_bytes, split_bytes;  // split_bytes: hi/lo operand copies (3xTF32)
 };
 
 TcPlan plan_tc(const ColumnLayout& L, int64_t n_rows, bool x3) {
   TcPlan P;
   P.kc = x3 ? 16 : 32;
+  if (!x3 && tc_debug().variant != 1 && (tc_debug().kc == 16 || tc_debug().kc == 64)) P.kc = tc_debug().kc;
   P.total_chunks = (int)ceil_div(n_rows, P.kc);
+  P.two_cta = tc_debug().variant != 1;
+  P.nb2 = (L.nblocks + 1) / 2;
   int nt = 0;
-  for (int i = 0; i < L.nblocks; ++i) nt += (L.nblocks - i + 1) / 2;
+  if (P.two_cta) {
+    nt = P.nb2 * (P.nb2 + 1) / 2;
+    P.ldp = P.nb2 * 256;
+  } else {
+    for (int i = 0; i < L.nblocks; ++i) nt += (L.nblocks - i + 1) / 2;
+    P.ldp = L.Dp;
+  }
   P.ntiles = nt;
+  const int slots = P.two_cta ? sm_count() / 2 : sm_count();  // CTA pairs occupy two SMs
   int S = 1;
-  if (nt < sm_count()) S = sm_count() / nt;
+  if (nt < slots) S = slots / nt;
   const int min_chunks = 8;  // keep the pipeline prologue/epilogue amortised
   S = (int)std::min<int64_t>(S, std::max<int64_t>(1, P.total_chunks / min_chunks));
   S = std::min(S, 64);
@@ -521,8 +741,8 @@ TcPlan plan_tc(const ColumnLayout& L, int64_t n_rows, bool x3) {
   S = std::max(1, std::min(S, P.total_chunks));
   P.chunks_per_split = (int)ceil_div(P.total_chunks, S);
   P.num_splits = (int)ceil_div(P.total_chunks, P.chunks_per_split);
-  P.partial_bytes = (size_t)P.num_splits * L.Dp * L.Dp * sizeof(float);
-  P.sum_bytes = (size_t)P.num_splits * L.Dp * sizeof(float);
+  P.partial_bytes = (size_t)P.num_splits * P.ldp * P.ldp * sizeof(float);
+  P.sum_bytes = (size_t)P.num_splits * P.ldp * sizeof(float);
   P.split_bytes = 0;
   if (x3) {
     for (int v = 0; v < L.n_views; ++v) {
@@ -573,13 +793,12 @@ int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t*
   CCAB_CHECK_ARG(ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
   uint8_t* w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
 
-  TcParams prm;
-  memset(&prm, 0, sizeof(prm));
-  prm.partial = reinterpret_cast<float*>(w);
-  prm.partial_sum = reinterpret_cast<float*>(w + align256(P.partial_bytes));
+  float* d_partial = reinterpret_cast<float*>(w);
+  float* d_partial_sum = reinterpret_cast<float*>(w + align256(P.partial_bytes));
   uint8_t* splitbuf = w + align256(P.partial_bytes) + align256(P.sum_bytes);
 
   // operands (raw, or hi/lo copies for 3xTF32) and their tensor maps
+  CUtensorMap maps[2 * kMaxViews];
   for (int v = 0; v < L.n_views; ++v) {
     const float* x = static_cast<const float*>(views[v]);
     if (x3) {
@@ -591,59 +810,115 @@ int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t*
       int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
       split_tf32_kernel<<<blocks, 256, 0, stream>>>(x, n_rows, L.dims[v], lds[v], hi, lo, ldo); count_launches(1);
       CCAB_CUDA(cudaGetLastError());
-      int rc = encode_view_map(&prm.maps[v], hi, n_rows, L.dims[v], ldo, P.kc);
+      int rc = encode_view_map(&maps[v], hi, n_rows, L.dims[v], ldo, P.kc);
       if (rc) return rc;
-      rc = encode_view_map(&prm.maps[kMaxViews + v], lo, n_rows, L.dims[v], ldo, P.kc);
+      rc = encode_view_map(&maps[kMaxViews + v], lo, n_rows, L.dims[v], ldo, P.kc);
       if (rc) return rc;
     } else {
-      int rc = encode_view_map(&prm.maps[v], x, n_rows, L.dims[v], lds[v], P.kc);
+      int rc = encode_view_map(&maps[v], x, n_rows, L.dims[v], lds[v], P.kc);
       if (rc) return rc;
+      maps[kMaxViews + v] = maps[v];
     }
   }
   for (int v = L.n_views; v < kMaxViews; ++v) {
-    prm.maps[v] = prm.maps[0];
-    prm.maps[kMaxViews + v] = prm.maps[x3 ? kMaxViews : 0];
+    maps[v] = maps[0];
+    maps[kMaxViews + v] = maps[kMaxViews];
   }
-  if (!x3)
-    for (int v = 0; v < kMaxViews; ++v) prm.maps[kMaxViews + v] = prm.maps[0];
+  const int lbo = tc_debug().lbo_bytes >= 0 ? tc_debug().lbo_bytes : P.kc * 128;
+  const int sbo = tc_debug().sbo_bytes >= 0 ? tc_debug().sbo_bytes : 512;
 
-  prm.total_chunks = P.total_chunks;
-  prm.chunks_per_split = P.chunks_per_split;
-  prm.num_splits = P.num_splits;
-  prm.nblocks = L.nblocks;
-  prm.Dp = L.Dp;
-  prm.lbo_bytes = tc_debug().lbo_bytes >= 0 ? tc_debug().lbo_bytes : P.kc * 128;
-  prm.sbo_bytes = tc_debug().sbo_bytes >= 0 ? tc_debug().sbo_bytes : 512;
-  int b = 0;
-  for (int v = 0; v < L.n_views; ++v)
-    for (int c = 0; c < L.dims[v]; c += kBlk, ++b) {
-      prm.blk_view[b] = (uint8_t)v;
-      prm.blk_col0[b] = c;
-    }
-  prm.row_tile_start[0] = 0;
-  for (int i = 0; i < L.nblocks; ++i) prm.row_tile_start[i + 1] = prm.row_tile_start[i] + (L.nblocks - i + 1) / 2;
-  for (int i = L.nblocks + 1; i <= kMaxBlocks; ++i) prm.row_tile_start[i] = 0x7fffffff;
-
-  dim3 grid(P.ntiles, P.num_splits);
   if (g_prof_on) cudaEventRecord(g_prof_e0, stream);
-  if (x3) {
-    using Cfg = TcCfg<16, true>;
-    static bool attr = false;
-    if (!attr) {
-      CCAB_CUDA(cudaFuncSetAttribute(moments_tf32_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg::kSmem));
-      attr = true;
+  if (P.two_cta) {
+    TcParams2 prm;
+    memset(&prm, 0, sizeof(prm));
+    memcpy(prm.maps, maps, sizeof(maps));
+    prm.partial = d_partial;
+    prm.partial_sum = d_partial_sum;
+    prm.total_chunks = P.total_chunks;
+    prm.chunks_per_split = P.chunks_per_split;
+    prm.num_splits = P.num_splits;
+    prm.nblocks = L.nblocks;
+    prm.nb2 = P.nb2;
+    prm.Dp2 = P.ldp;
+    prm.lbo_bytes = lbo;
+    prm.sbo_bytes = sbo;
+    int b = 0;
+    for (int v = 0; v < L.n_views; ++v)
+      for (int c = 0; c < L.dims[v]; c += kBlk, ++b) {
+        prm.blk_view[b] = (uint8_t)v;
+        prm.blk_col0[b] = c;
+      }
+    for (; b < kMaxBlocks + 2; ++b) {  // dummy blocks: every coordinate out of bounds -> TMA zero fill
+      prm.blk_view[b] = 0;
+      prm.blk_col0[b] = 1 << 30;
     }
-    moments_tf32_kernel<16, true><<<grid, kTcThreads, Cfg::kSmem, stream>>>(prm); count_launches(1);
+    prm.dry_run = tc_debug().dry_run;
+    dim3 grid(2 * P.ntiles, P.num_splits);
+#define CCAB_LAUNCH_2CTA(KC_, X3_, NS_)                                                                      \
+  do {                                                                                                       \
+    using Cfg = Tc2Cfg<KC_, X3_, NS_>;                                                                       \
+    static bool attr = false;                                                                                \
+    if (!attr) {                                                                                             \
+      CCAB_CUDA(cudaFuncSetAttribute(moments_tf32_2cta_kernel<KC_, X3_, NS_>,                                \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));              \
+      attr = true;                                                                                           \
+    }                                                                                                        \
+    moments_tf32_2cta_kernel<KC_, X3_, NS_><<<grid, kTcThreads, Cfg::kSmem, stream>>>(prm);                  \
+  } while (0)
+    if (x3) {
+      CCAB_LAUNCH_2CTA(16, true, 6);
+    } else if (P.kc == 64) {
+      CCAB_LAUNCH_2CTA(64, false, 3);
+    } else if (P.kc == 16) {
+      CCAB_LAUNCH_2CTA(16, false, 12);
+    } else {
+      CCAB_LAUNCH_2CTA(32, false, 6);
+    }
+#undef CCAB_LAUNCH_2CTA
+    count_launches(1);
   } else {
-    using Cfg = TcCfg<32, false>;
-    static bool attr = false;
-    if (!attr) {
-      CCAB_CUDA(cudaFuncSetAttribute(moments_tf32_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg::kSmem));
-      attr = true;
+    TcParams prm;
+    memset(&prm, 0, sizeof(prm));
+    memcpy(prm.maps, maps, sizeof(maps));
+    prm.partial = d_partial;
+    prm.partial_sum = d_partial_sum;
+    prm.total_chunks = P.total_chunks;
+    prm.chunks_per_split = P.chunks_per_split;
+    prm.num_splits = P.num_splits;
+    prm.nblocks = L.nblocks;
+    prm.Dp = L.Dp;
+    prm.lbo_bytes = lbo;
+    prm.sbo_bytes = sbo;
+    int b = 0;
+    for (int v = 0; v < L.n_views; ++v)
+      for (int c = 0; c < L.dims[v]; c += kBlk, ++b) {
+        prm.blk_view[b] = (uint8_t)v;
+        prm.blk_col0[b] = c;
+      }
+    prm.row_tile_start[0] = 0;
+    for (int i = 0; i < L.nblocks; ++i) prm.row_tile_start[i + 1] = prm.row_tile_start[i] + (L.nblocks - i + 1) / 2;
+    for (int i = L.nblocks + 1; i <= kMaxBlocks; ++i) prm.row_tile_start[i] = 0x7fffffff;
+    dim3 grid(P.ntiles, P.num_splits);
+    if (x3) {
+      using Cfg = TcCfg<16, true>;
+      static bool attr = false;
+      if (!attr) {
+        CCAB_CUDA(cudaFuncSetAttribute(moments_tf32_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmem));
+        attr = true;
+      }
+      moments_tf32_kernel<16, true><<<grid, kTcThreads, Cfg::kSmem, stream>>>(prm);
+    } else {
+      using Cfg = TcCfg<32, false>;
+      static bool attr = false;
+      if (!attr) {
+        CCAB_CUDA(cudaFuncSetAttribute(moments_tf32_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmem));
+        attr = true;
+      }
+      moments_tf32_kernel<32, false><<<grid, kTcThreads, Cfg::kSmem, stream>>>(prm);
     }
-    moments_tf32_kernel<32, false><<<grid, kTcThreads, Cfg::kSmem, stream>>>(prm); count_launches(1);
+    count_launches(1);
   }
   CCAB_CUDA(cudaGetLastError());
   if (g_prof_on) {
@@ -653,7 +928,7 @@ int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t*
 
   const size_t total = (size_t)L.Dp * L.Dp + L.Dp;
   int rblocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
-  reduce_partials_kernel<float><<<rblocks, 256, 0, stream>>>(prm.partial, prm.partial_sum, P.num_splits, L.Dp,
+  reduce_partials_kernel<float><<<rblocks, 256, 0, stream>>>(d_partial, d_partial_sum, P.num_splits, L.Dp, P.ldp,
                                                             kBlk, moments_out); count_launches(1);
   CCAB_CUDA(cudaGetLastError());
   return 0;
@@ -692,7 +967,7 @@ int moments_simt(const ColumnLayout& L, const void* const* views, const int64_t*
   int rblocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
   reduce_partials_kernel<T><<<rblocks, 256, 0, stream>>>(static_cast<const T*>(prm.partial),
                                                         static_cast<const T*>(prm.partial_sum), P.num_splits,
-                                                        L.Dp, 64, moments_out); count_launches(1);
+                                                        L.Dp, L.Dp, 64, moments_out); count_launches(1);
   CCAB_CUDA(cudaGetLastError());
   return 0;
 }

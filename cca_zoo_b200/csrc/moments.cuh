@@ -45,6 +45,9 @@ struct TcDebug {
   int sbo_bytes;    // <0: default
   int tma_dtype;    // <0: default (FLOAT32); else a CUtensorMapDataType value
   int force_splits; // <=0: heuristic
+  int variant;      // 0: CTA-pair kernel (cta_group::2, default), 1: single-CTA kernel
+  int kc;           // CTA-pair kernel, 1-pass: rows per stage 16 / 32 (default) / 64
+  int dry_run;      // CTA-pair kernel: skip TMA after the first ring fill (MMA-rate experiment; wrong results)
 };
 TcDebug& tc_debug();
 
