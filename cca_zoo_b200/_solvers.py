@@ -37,13 +37,97 @@ def _block_eigh(C, dims):
     return lams, vts
 
 
-def rcca_weights(C, dims, n_samples, latent_dimensions, c):
+def _cholqr_(Y):
+    """Orthonormalise the columns of Y (n x p) in place by CholQR applied twice.  Returns False when the
+    Gram matrix is not numerically positive definite (rank-deficient block)."""
+    ok = True
+    for _ in range(2):
+        G = ops.gemm(Y, Y, transa=True)
+        info = ops.potrf_(G)
+        ops.trsm_(G, Y, side="right", trans=True)
+        ok = ok and int(info.item()) == 0
+    return ok
+
+
+def topk_svd(T, k, max_rounds=4, iters_per_round=6, oversample=None, seed=1234):
+    """Leading k singular triplets of T (d1 x d2) by blocked subspace iteration + Rayleigh-Ritz.
+
+    Z <- orth(T^T orth(T Z)) repeated; then the Jacobi SVD of the thin block Y = T Z (d1 x p) gives
+    U, sigma and V = Z V_y.  Converged when max_j ||T^T u_j - sigma_j v_j|| <= tol * sigma_1 (the other
+    residual T v_j - sigma_j u_j vanishes by construction).  Returns (sigma[k], Ut[k,d1], Vt[k,d2]) or None
+    if it does not converge (flat spectrum): the caller then runs the full Jacobi SVD.
+    """
+    d1, d2 = T.shape
+    p = min(min(d1, d2), max(2 * k, k + 32) if oversample is None else k + oversample)
+    gen = torch.Generator(device=T.device).manual_seed(seed)
+    Z = torch.randn((d2, p), generator=gen, device=T.device, dtype=T.dtype)
+    if not _cholqr_(Z):
+        return None
+    tol = 200.0 * _eps(T.dtype)
+    for _ in range(max_rounds):
+        for _ in range(iters_per_round):
+            Y = ops.gemm(T, Z)                      # d1 x p
+            if not _cholqr_(Y):
+                return None
+            Z = ops.gemm(T, Y, transa=True)         # d2 x p
+            if not _cholqr_(Z):
+                return None
+        Yt = ops.gemm(Z, T, transa=True, transb=True)       # (T Z)^T : p x d1, rows = columns of Y
+        sig, Vy_t, Ut = ops.gesvj(Yt)                       # Y = U diag(sig) Vy^T
+        Vt = ops.gemm(Vy_t[:k], Z, transb=True)             # k x d2 : rows of (Z Vy)^T
+        E = ops.gemm(Ut[:k], T)                             # rows: u_j^T T
+        E -= ops.scale(Vt, rows=sig[:k])
+        resid = float(ops.frobenius_norm(E).item())
+        if resid <= tol * float(sig[0].item()) * (k ** 0.5):
+            return sig[:k], Ut[:k], Vt
+        # not yet: continue the iteration from the Ritz basis (all p vectors)
+        Z = ops.gemm(Z, Vy_t, transb=True)
+    return None
+
+
+def rcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c):
+    """rCCA through the Cholesky form of the whitening (same weights as ``rcca_weights`` up to sign):
+    R_i = (1-c_i) C_ii + c_i I = L_i L_i^T ; T = L_1^-1 C_12 L_2^-T ; weights = L_i^-T U_k / V_k.
+    Returns None when a regularised block is not numerically positive definite (the eigen route, which
+    reproduces the reference's rank handling, is used instead)."""
+    s1, s2 = _slices(dims)
+    Ls = []
+    for i, s in enumerate((s1, s2)):
+        R = (1.0 - c[i]) * C[s, s]
+        R.diagonal().add_(c[i])
+        dmax = float(R.diagonal().max().item())
+        info = ops.potrf_(R, pivot_tol=max(dims[i], n_samples) * _eps(C.dtype) * dmax)
+        if int(info.item()) != 0:
+            return None
+        Ls.append(R)
+    T = C[s1, s2].contiguous()
+    ops.trsm_(Ls[0], T, side="left")                 # L1^-1 C12
+    ops.trsm_(Ls[1], T, side="right", trans=True)    # ... L2^-T
+    k = min(latent_dimensions, dims[0], dims[1])
+    res = topk_svd(T, k) if 4 * k <= min(dims) else None
+    if res is None:
+        _, Ut, Vt = ops.gesvj(T)
+        Ut, Vt = Ut[:k], Vt[:k]
+    else:
+        _, Ut, Vt = res
+    w1 = Ut.T.contiguous()
+    w2 = Vt.T.contiguous()
+    ops.trsm_(Ls[0], w1, side="left", trans=True)    # L1^-T U_k
+    ops.trsm_(Ls[1], w2, side="left", trans=True)
+    return [w1, w2]
+
+
+def rcca_weights(C, dims, n_samples, latent_dimensions, c, solver="auto"):
     """rCCA / CCA / PLS (cca_zoo/linear/_rcca.py:83-101 in covariance form).
 
     C_ii = V_i L_i V_i^T ; Wt_i = diag(((1-c_i) L_i + c_i)^-1/2) V_i^T (directions with
     lam <= tol*lam_max dropped = the reference's ``s > 0`` filter, _linalg.py:30) ;
     T = Wt_1 C_12 Wt_2^T = U S V^T (one-sided Jacobi) ; weights = Wt_1^T U_k, Wt_2^T V_k.
     """
+    if solver == "cholesky" or (solver == "auto" and min(dims) >= 256 and n_samples > max(dims)):
+        w = rcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c)
+        if w is not None:
+            return w
     s1, s2 = _slices(dims)
     lams, vts = _block_eigh(C, dims)
     wts, ranks = [], []

@@ -7,6 +7,7 @@
 #include <atomic>
 #include <exception>
 
+#include "chol.cuh"
 #include "common.cuh"
 #include "dense.cuh"
 #include "moments.cuh"
@@ -263,6 +264,38 @@ int ccab_whiten_rows(int dtype, int d, const void* lam, const void* Vt, int64_t 
   return whiten_rows<double>(d, static_cast<const double*>(lam), static_cast<const double*>(Vt), ldv, c, floor_add,
                              static_cast<const double*>(floor_dev), scale, rank_tol, max_rank, lam_floor,
                              static_cast<double*>(Wt), ldw, static_cast<double*>(g_out), rank_out, s);
+  CCAB_CATCH
+}
+
+int ccab_potrf(int dtype, int n, void* A, int64_t lda, double pivot_tol, int* info_dev, void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(A && info_dev, "null pointer argument");
+  int rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CCAB_F32) return potrf<float>(n, static_cast<float*>(A), lda, pivot_tol, info_dev, s);
+  return potrf<double>(n, static_cast<double*>(A), lda, pivot_tol, info_dev, s);
+  CCAB_CATCH
+}
+
+int ccab_trsm(int dtype, int side, int trans, int n, int m, const void* L, int64_t ldl, void* B, int64_t ldb,
+              void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(L && B, "null pointer argument");
+  CCAB_CHECK_ARG(side == 0 || (side == 1 && trans == 1), "supported: left (trans 0/1) and right with trans=1");
+  int rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (side == 0) {
+    if (dtype == CCAB_F32)
+      return trsm_left<float>(trans, n, m, static_cast<const float*>(L), ldl, static_cast<float*>(B), ldb, s);
+    return trsm_left<double>(trans, n, m, static_cast<const double*>(L), ldl, static_cast<double*>(B), ldb, s);
+  }
+  if (dtype == CCAB_F32)
+    return trsm_right_lt<float>(n, m, static_cast<const float*>(L), ldl, static_cast<float*>(B), ldb, s);
+  return trsm_right_lt<double>(n, m, static_cast<const double*>(L), ldl, static_cast<double*>(B), ldb, s);
   CCAB_CATCH
 }
 

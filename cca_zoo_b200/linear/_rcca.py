@@ -4,7 +4,7 @@ from __future__ import annotations
 from numbers import Real
 from typing import Any, ClassVar
 
-from sklearn.utils._param_validation import Interval
+from sklearn.utils._param_validation import Interval, StrOptions
 
 from .._base import BaseModel
 from .._solvers import rcca_weights
@@ -30,17 +30,24 @@ class rCCA(BaseModel):
         precision: covariance arithmetic for float32 inputs: ``"tf32x3"`` (default, float32-grade),
             ``"tf32"`` (single tensor-core pass) or ``"exact"`` (CUDA-core FMA).
         device: CUDA device (default: current).
+        solver: ``"eigen"`` mirrors the reference step by step (eigendecomposition of each view's
+            covariance, Jacobi SVD of the whitened cross-covariance); ``"cholesky"`` whitens with Cholesky
+            factors and extracts the leading ``latent_dimensions`` singular triplets by subspace iteration
+            (identical weights, much less work when ``latent_dimensions << n_features``); ``"auto"`` picks
+            the latter for large full-rank problems and falls back to ``"eigen"`` otherwise.
     """
 
     _parameter_constraints: ClassVar[dict[str, list[Any]]] = {
         **BaseModel._parameter_constraints,
         "c": RIDGE_PARAMETER,
+        "solver": [StrOptions({"auto", "eigen", "cholesky"})],
     }
 
     def __init__(self, latent_dimensions: int = 1, center: bool = True, c=0.0, precision: str = "tf32x3",
-                 device=None) -> None:
+                 device=None, solver: str = "auto") -> None:
         super().__init__(latent_dimensions=latent_dimensions, center=center, precision=precision, device=device)
         self.c = c
+        self.solver = solver
 
     def fit(self, views, y=None):
         """Fit on a list of exactly two ``(n_samples, n_features_i)`` arrays (numpy or torch)."""
@@ -54,7 +61,7 @@ class rCCA(BaseModel):
 
     def _solve(self, C, dims, n_total):
         c_ = perview_parameter("c", self.c, 0.0, 2)
-        return rcca_weights(C, dims, n_total, self.latent_dimensions, [float(x) for x in c_])
+        return rcca_weights(C, dims, n_total, self.latent_dimensions, [float(x) for x in c_], solver=self.solver)
 
 
 class CCA(rCCA):
@@ -63,7 +70,7 @@ class CCA(rCCA):
     def __init__(self, latent_dimensions: int = 1, center: bool = True, precision: str = "tf32x3",
                  device=None) -> None:
         super().__init__(latent_dimensions=latent_dimensions, center=center, c=0.0, precision=precision,
-                         device=device)
+                         device=device, solver="auto")
 
 
 class PLS(rCCA):
@@ -72,4 +79,4 @@ class PLS(rCCA):
     def __init__(self, latent_dimensions: int = 1, center: bool = True, precision: str = "tf32x3",
                  device=None) -> None:
         super().__init__(latent_dimensions=latent_dimensions, center=center, c=1.0, precision=precision,
-                         device=device)
+                         device=device, solver="auto")

@@ -203,6 +203,40 @@ def whiten_rows(lam, Vt, c, floor_add=0.0, floor_dev=None, scale=1.0, rank_tol=0
     return Wt, g, rank
 
 
+def potrf_(A, pivot_tol=0.0):
+    """In place lower Cholesky of a square row-major CUDA matrix.  Returns the device info flag (int32[1])."""
+    lib = _lib.load()
+    _require_cuda(A, "A")
+    if A.dim() != 2 or A.shape[0] != A.shape[1] or A.stride(1) != 1:
+        raise ValueError("square row-major matrix expected")
+    info = torch.zeros(1, dtype=torch.int32, device=A.device)
+    with torch.cuda.device(A.device):
+        rc = lib.ccab_potrf(_DT[A.dtype], A.shape[0], _ptr(A), A.stride(0), float(pivot_tol), _ptr(info), _stream(A))
+    _lib.check(rc, "ccab_potrf")
+    return info
+
+
+def trsm_(L, B, side="left", trans=False):
+    """In place triangular solve with the lower factor L: left: B <- L^-1 B / L^-T B; right: B <- B L^-T."""
+    lib = _lib.load()
+    _require_cuda(B, "B")
+    if B.stride(1) != 1 or L.stride(1) != 1:
+        raise ValueError("row-major matrices expected")
+    n = L.shape[0]
+    if side == "left":
+        if B.shape[0] != n:
+            raise ValueError("shape mismatch")
+        args = (0, int(trans), n, B.shape[1])
+    else:
+        if B.shape[1] != n or not trans:
+            raise ValueError("right side supports B <- B L^-T only")
+        args = (1, 1, n, B.shape[0])
+    with torch.cuda.device(B.device):
+        rc = lib.ccab_trsm(_DT[B.dtype], *args, _ptr(L), L.stride(0), _ptr(B), B.stride(0), _stream(B))
+    _lib.check(rc, "ccab_trsm")
+    return B
+
+
 _POW = {None: 0, 1: 0, -1: 1, -0.5: 2}
 
 

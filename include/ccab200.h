@@ -114,6 +114,19 @@ int ccab_whiten_rows(int dtype, int d, const void* lam, const void* Vt, int64_t 
                      const void* floor_dev, double scale, double rank_tol, int max_rank, double lam_floor, void* Wt,
                      int64_t ldw, void* g_out, int* rank_out, void* stream);
 
+/* ---- Cholesky route of the generalised problem ----------------------------------------------------
+ * ccab_potrf: lower triangle of A (n x n, row-major, device) <- L with A = L L^T, in place (the strict
+ * upper triangle is not referenced).  *info_dev (device int): 0, or the 1-based index of the first pivot
+ * <= pivot_tol (matrix not numerically positive definite: callers fall back to the eigen route).
+ * ccab_trsm: side 0: B (n x m) <- L^-1 B (trans 0) or L^-T B (trans 1); side 1 (trans must be 1):
+ * B (m x n) <- B L^-T.  L is n x n lower triangular.
+ * Replaces the Cholesky + back-substitution inside scipy.linalg.eigh(A, B) (LAPACK *sygvx,
+ * cca_zoo/_utils/_linalg.py:67-71) and, in Cholesky form, the whitening of _linalg.py:30-38:
+ * with R_i = (1-c) C_ii + c I = L_i L_i^T,  T = L_1^-1 C_12 L_2^-T and weights_i = L_i^-T U_k. */
+int ccab_potrf(int dtype, int n, void* A, int64_t lda, double pivot_tol, int* info_dev, void* stream);
+int ccab_trsm(int dtype, int side, int trans, int n, int m, const void* L, int64_t ldl, void* B, int64_t ldb,
+              void* stream);
+
 /* B[i,j] = A[i,j] * f(r[i]) * f(c[j]); r / c may be NULL; *_pow: 0 -> x, 1 -> 1/x, 2 -> 1/sqrt(x).
  * (column scalings such as diag(sigma)^-1/2 in the GCCA back-substitution, cca_zoo/linear/_gcca.py:109) */
 int ccab_scale(int dtype, int m, int n, const void* A, int64_t lda, const void* r, int r_pow, const void* c,

@@ -182,3 +182,57 @@ def test_argument_errors_are_loud():
         ops.moments([torch.zeros(4, 4, device="cuda"), torch.zeros(5, 4, device="cuda")])
     with pytest.raises(ValueError):
         ops.gemm(torch.zeros(4, 5, device="cuda"), torch.zeros(4, 5, device="cuda"))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 2e-5)])
+@pytest.mark.parametrize("n", [5, 64, 100, 300])
+def test_potrf_and_trsm(dtype, tol, n):
+    """A = L L^T and the three triangular solves against float64 torch (cca_zoo/_utils/_linalg.py:67-71 route)."""
+    from cca_zoo_b200 import ops
+
+    g = torch.Generator().manual_seed(n)
+    X = torch.randn(2 * n + 3, n, generator=g, dtype=torch.float64)
+    A64 = X.T @ X / (2 * n) + 0.1 * torch.eye(n, dtype=torch.float64)
+    A = A64.to(dtype).cuda()
+    L = A.clone()
+    info = ops.potrf_(L)
+    assert int(info.item()) == 0
+    Lr = torch.tril(L).double().cpu()
+    assert (Lr @ Lr.T - A.double().cpu()).abs().max() < tol * 10
+    B64 = torch.randn(n, 37, generator=g, dtype=torch.float64)
+    for trans in (False, True):
+        Bs = B64.to(dtype).cuda()
+        ops.trsm_(L, Bs, side="left", trans=trans)
+        ref = torch.linalg.solve_triangular(Lr.T if trans else Lr, B64, upper=trans)
+        assert (Bs.double().cpu() - ref).abs().max() < tol * 200 * ref.abs().max()
+    Br = torch.randn(45, n, generator=g, dtype=torch.float64)
+    Bs = Br.to(dtype).cuda()
+    ops.trsm_(L, Bs, side="right", trans=True)
+    ref = torch.linalg.solve_triangular(Lr, Br.T, upper=False).T
+    assert (Bs.double().cpu() - ref).abs().max() < tol * 200 * ref.abs().max()
+
+
+def test_potrf_flags_indefinite_matrix():
+    from cca_zoo_b200 import ops
+
+    A = torch.eye(80, dtype=torch.float64)
+    A[70, 70] = -1.0
+    info = ops.potrf_(A.cuda())
+    assert int(info.item()) == 71
+
+
+def test_topk_svd_matches_full_svd():
+    from cca_zoo_b200 import _solvers
+
+    g = torch.Generator().manual_seed(3)
+    U, _ = torch.linalg.qr(torch.randn(300, 300, generator=g, dtype=torch.float64))
+    V, _ = torch.linalg.qr(torch.randn(260, 260, generator=g, dtype=torch.float64))
+    s = torch.cat([torch.linspace(0.9, 0.5, 20, dtype=torch.float64), 0.1 * torch.rand(240, generator=g, dtype=torch.float64)])
+    T = (U[:, :260] * s) @ V.T
+    sig, Ut, Vt = _solvers.topk_svd(T.cuda(), 20)
+    np.testing.assert_allclose(sig.cpu().numpy(), s[:20].numpy(), rtol=1e-10)
+    assert ((Ut.cpu() @ U[:, :20]).abs() - torch.eye(20, dtype=torch.float64)).abs().max() < 1e-8
+    assert ((Vt.cpu() @ V[:, :20]).abs() - torch.eye(20, dtype=torch.float64)).abs().max() < 1e-8
+    # slowly decaying spectrum: no gap to exploit -> reports failure, callers fall back to the full Jacobi SVD
+    slow = (U[:, :260] * (1.0 - 1e-4 * torch.arange(260, dtype=torch.float64))) @ V.T
+    assert _solvers.topk_svd(slow.cuda(), 20, max_rounds=1, iters_per_round=2) is None

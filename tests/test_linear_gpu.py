@@ -132,3 +132,38 @@ def test_latent_dimensions_clamped_like_reference():
     assert est.weights_[0].shape == (10, 8) and est.weights_[1].shape == (8, 8)
     est = MCCA(latent_dimensions=30).fit(two)
     assert est.weights_[0].shape == (10, 18)
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-5), ("f32", 1e-3)])
+def test_rcca_cholesky_route_equals_eigen_route(dtype, tol):
+    """solver="cholesky" (Cholesky whitening + top-k subspace SVD) gives the weights of the eigen route
+    (which is the one checked against the reference goldens) on a problem large enough to use it."""
+    from cca_zoo_b200.datasets import joint_data
+    from cca_zoo_b200.linear import rCCA
+
+    views = joint_data(n_views=2, n_samples=6000, n_features=[320, 288], latent_dimensions=10,
+                       signal_to_noise=0.02, random_state=11,
+                       dtype=np.float32 if dtype == "f32" else np.float64)
+    a = rCCA(latent_dimensions=10, c=0.1, solver="eigen").fit(views)
+    b = rCCA(latent_dimensions=10, c=0.1, solver="cholesky").fit(views)
+    auto = rCCA(latent_dimensions=10, c=0.1).fit(views)
+    wa = [w.astype(np.float64) for w in a.weights_]
+    assert R.max_rel_err_per_vector([w.astype(np.float64) for w in b.weights_], wa) < tol
+    assert R.max_rel_err_per_vector([w.astype(np.float64) for w in auto.weights_], wa) < tol
+    np.testing.assert_allclose(b.score(views), a.score(views), rtol=tol)
+    if dtype == "f64":
+        M, s, n = R.moments(views)
+        w, _ = R.cov_rcca_fit(R.covariance_from_moments(M, s, n), [320, 288], 10, 0.1, n)
+        assert R.max_rel_err_per_vector(b.weights_, w) < 1e-5
+
+
+def test_rcca_cholesky_route_falls_back_when_rank_deficient():
+    from cca_zoo_b200.linear import rCCA
+
+    rng = np.random.default_rng(0)
+    base = rng.standard_normal((900, 150))
+    x1 = np.hstack([base, base @ rng.standard_normal((150, 150))])      # 300 columns of rank 150
+    x2 = rng.standard_normal((900, 260)) + x1[:, :260]
+    a = rCCA(latent_dimensions=3, c=0.0, solver="eigen").fit([x1, x2])
+    b = rCCA(latent_dimensions=3, c=0.0, solver="cholesky").fit([x1, x2])
+    np.testing.assert_allclose(b.score([x1, x2]), a.score([x1, x2]), rtol=1e-6)
