@@ -37,51 +37,52 @@ def _block_eigh(C, dims):
     return lams, vts
 
 
-def _cholqr_(Y):
-    """Orthonormalise the columns of Y (n x p) in place by CholQR applied twice.  Returns False when the
-    Gram matrix is not numerically positive definite (rank-deficient block)."""
-    ok = True
-    for _ in range(2):
+def _cholqr_(Y, flags, passes=1):
+    """Orthonormalise the columns of Y (n x p) in place by CholQR (Gram matrix, Cholesky, triangular solve).
+    The device-side Cholesky status flags are appended to ``flags`` (checked once, later, by the caller):
+    a non-zero flag means the block lost rank."""
+    for _ in range(passes):
         G = ops.gemm(Y, Y, transa=True)
-        info = ops.potrf_(G)
+        flags.append(ops.potrf_(G))
         ops.trsm_(G, Y, side="right", trans=True)
-        ok = ok and int(info.item()) == 0
-    return ok
+    return Y
 
 
-def topk_svd(T, k, max_rounds=4, iters_per_round=6, oversample=None, seed=1234):
+def topk_svd(T, k, max_rounds=4, iters_per_round=5, oversample=None, seed=1234):
     """Leading k singular triplets of T (d1 x d2) by blocked subspace iteration + Rayleigh-Ritz.
 
-    Z <- orth(T^T orth(T Z)) repeated; then the Jacobi SVD of the thin block Y = T Z (d1 x p) gives
-    U, sigma and V = Z V_y.  Converged when max_j ||T^T u_j - sigma_j v_j|| <= tol * sigma_1 (the other
-    residual T v_j - sigma_j u_j vanishes by construction).  Returns (sigma[k], Ut[k,d1], Vt[k,d2]) or None
-    if it does not converge (flat spectrum): the caller then runs the full Jacobi SVD.
+    Z <- orth(T^T orth(T Z)) repeated (one CholQR pass per product: enough to keep the block
+    well-conditioned; the last one is done twice); then the Jacobi SVD of the thin block Y = T Z (d1 x p)
+    gives U, sigma and V = Z V_y.  Converged when ||T^T U_k - V_k diag(sigma)||_F <= tol sigma_1 sqrt(k) (the
+    other residual T v_j - sigma_j u_j vanishes by construction).  Returns (sigma[k], Ut[k,d1], Vt[k,d2]) or
+    None if it does not converge (no spectral gap after the block) or a block loses rank: the caller then
+    runs the full Jacobi SVD.  One host read-back per round.
     """
     d1, d2 = T.shape
     p = min(min(d1, d2), max(2 * k, k + 32) if oversample is None else k + oversample)
     gen = torch.Generator(device=T.device).manual_seed(seed)
     Z = torch.randn((d2, p), generator=gen, device=T.device, dtype=T.dtype)
-    if not _cholqr_(Z):
-        return None
+    flags = []
+    _cholqr_(Z, flags, passes=2)
     tol = 200.0 * _eps(T.dtype)
     for _ in range(max_rounds):
-        for _ in range(iters_per_round):
-            Y = ops.gemm(T, Z)                      # d1 x p
-            if not _cholqr_(Y):
-                return None
-            Z = ops.gemm(T, Y, transa=True)         # d2 x p
-            if not _cholqr_(Z):
-                return None
+        for it in range(iters_per_round):
+            Y = _cholqr_(ops.gemm(T, Z), flags)                   # d1 x p
+            Z = _cholqr_(ops.gemm(T, Y, transa=True), flags,      # d2 x p
+                         passes=2 if it == iters_per_round - 1 else 1)
         Yt = ops.gemm(Z, T, transa=True, transb=True)       # (T Z)^T : p x d1, rows = columns of Y
         sig, Vy_t, Ut = ops.gesvj(Yt)                       # Y = U diag(sig) Vy^T
         Vt = ops.gemm(Vy_t[:k], Z, transb=True)             # k x d2 : rows of (Z Vy)^T
         E = ops.gemm(Ut[:k], T)                             # rows: u_j^T T
         E -= ops.scale(Vt, rows=sig[:k])
-        resid = float(ops.frobenius_norm(E).item())
-        if resid <= tol * float(sig[0].item()) * (k ** 0.5):
+        stats = torch.stack([ops.frobenius_norm(E)[0], sig[0], torch.stack(flags).max().to(T.dtype).reshape(())])
+        resid, s1, bad = (float(x) for x in stats.cpu())    # the round's single host read-back
+        if bad != 0.0 or not (s1 > 0.0):
+            return None
+        if resid <= tol * s1 * (k ** 0.5):
             return sig[:k], Ut[:k], Vt
-        # not yet: continue the iteration from the Ritz basis (all p vectors)
-        Z = ops.gemm(Z, Vy_t, transb=True)
+        flags = []
+        Z = ops.gemm(Z, Vy_t, transb=True)                  # continue from the Ritz basis (all p vectors)
     return None
 
 
