@@ -22,6 +22,15 @@ def _eps(dtype):
     return float(torch.finfo(dtype).eps)
 
 
+def _rank_tol(d, dtype):
+    """Relative eigenvalue threshold below which a direction of a d x d covariance block is treated as
+    numerically null: the covariance-space image of the reference's ``s > 0`` filter
+    (cca_zoo/_utils/_linalg.py:30).  d * eps is the noise level of the computed spectrum (entries carry
+    O(eps) relative error, the spectral norm of that perturbation grows like d); it does NOT grow with the
+    number of samples."""
+    return d * _eps(dtype)
+
+
 def _block_eigh(C, dims):
     """Eigendecomposition of every diagonal block C_ii; equal-sized blocks go in one batched call."""
     sl = _slices(dims)
@@ -97,7 +106,7 @@ def rcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c):
         R = (1.0 - c[i]) * C[s, s]
         R.diagonal().add_(c[i])
         dmax = float(R.diagonal().max().item())
-        info = ops.potrf_(R, pivot_tol=max(dims[i], n_samples) * _eps(C.dtype) * dmax)
+        info = ops.potrf_(R, pivot_tol=_rank_tol(dims[i], C.dtype) * dmax)
         if int(info.item()) != 0:
             return None
         Ls.append(R)
@@ -133,8 +142,8 @@ def rcca_weights(C, dims, n_samples, latent_dimensions, c, solver="auto"):
     lams, vts = _block_eigh(C, dims)
     wts, ranks = [], []
     for i in range(2):
-        tol = max(dims[i], n_samples) * _eps(C.dtype)
-        Wt, _, rank = ops.whiten_rows(lams[i], vts[i], c[i], rank_tol=tol, max_rank=min(n_samples, dims[i]))
+        Wt, _, rank = ops.whiten_rows(lams[i], vts[i], c[i], rank_tol=_rank_tol(dims[i], C.dtype),
+                                      max_rank=min(n_samples, dims[i]))
         wts.append(Wt)
         ranks.append(rank)
     r1, r2 = (int(r.item()) for r in ranks)  # host read-back: decides k (_rcca.py:95)
@@ -213,7 +222,7 @@ def gcca_weights(C, dims, n_samples, latent_dimensions, c, mu, eps):
     CP = ops.gemm(C, P)                                                   # (D x k)
     out = []
     for i in range(m):
-        tol = max(dims[i], n_samples) * _eps(C.dtype)
+        tol = _rank_tol(dims[i], C.dtype)
         # pinv(C_ii) = V diag(1/lam | lam > tol lam_max) V^T  via whiten_rows with c=0 (g = lam^-1/2) twice
         Pinv_half, _, _ = ops.whiten_rows(lams[i], vts[i], 0.0, rank_tol=tol)   # diag(lam^-1/2) V^T
         t1 = ops.gemm(Pinv_half, CP[sl[i]])                                      # (d x k)

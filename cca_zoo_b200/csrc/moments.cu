@@ -734,6 +734,13 @@ TcPlan plan_tc(const ColumnLayout& L, int64_t n_rows, bool x3) {
   const int slots = P.two_cta ? sm_count() / 2 : sm_count();  // CTA pairs occupy two SMs
   int S = 1;
   if (nt < slots) S = slots / nt;
+  if (x3) {
+    // tcgen05 accumulates in fp32 with round-toward-zero: a monotone sum (every diagonal entry of M) drifts
+    // low by ~0.5 ulp per accumulation step.  The 3xTF32 mode exists for fp32-grade results, so bound one
+    // accumulator run to 8192 samples (1024 steps, < 6e-5 relative) and let the fixed-order double reduction
+    // of the partials do the long sum.
+    S = std::max<int64_t>(S, ceil_div(n_rows, 8192));
+  }
   const int min_chunks = 8;  // keep the pipeline prologue/epilogue amortised
   S = (int)std::min<int64_t>(S, std::max<int64_t>(1, P.total_chunks / min_chunks));
   S = std::min(S, 64);
