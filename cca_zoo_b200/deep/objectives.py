@@ -6,9 +6,11 @@
 (cca_zoo/deep/_dcca.py:61,73) unchanged: it is an ``nn.Module`` taking ``list[Tensor]`` and returning
 a 0-dim tensor.
 
-Forward  : K1 moments of [z1 z2] -> covariance -> two Jacobi eigendecompositions ->
-           T = (L1^-1/2 V1^T) S12 (L2^-1/2 V2^T)^T ; loss = -||T||_F^2 (= -sum eigvalsh(T^T T), the third
-           eigensolve of the reference is a trace).
+Forward  : K1 moments of [z1 z2] -> covariance S -> whitening of each view -> T -> loss = -||T||_F^2
+           (= -sum eigvalsh(T^T T): the third eigensolve of the reference is a trace).  Whitening uses the
+           Cholesky factors S_ii + eps I = L_i L_i^T (T = L_1^-1 S_12 L_2^-T, same Frobenius norm as
+           S_11^-1/2 S_12 S_22^-1/2) whenever lambda_min is provably above the clamp; otherwise two Jacobi
+           eigendecompositions reproduce clamp(eigh(.), min=eps) literally.
 Backward : analytic, no eigh-backward:  with P = S11^-1 S12 S22^-1,
            dL/dz1 = 2/(n-1) * center(z1 (P S21 S11^-1) - z2 P^T),  dL/dz2 symmetric.
            Valid whenever the eigenvalue clamp is inactive, which ``+ eps I`` guarantees up to round-off.
@@ -19,6 +21,23 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+
+
+def _whiteners_cholesky(C, d1, eps):
+    """Cholesky route: S_ii = C_ii + eps I = L_i L_i^T, returns (L_1, L_2) or None.
+
+    Accepted only when every pivot^2 exceeds 4 eps, i.e. lambda_min(S_ii) is safely above the reference's
+    eigenvalue clamp (objectives.py:20) so that the clamp is provably inactive and
+    S_ii^-1/2 S_12 S_jj^-1/2 has the same Frobenius norm as L_i^-1 S_12 L_j^-T."""
+    Ls, flags = [], []
+    for blk in (C[:d1, :d1], C[d1:, d1:]):
+        S = blk.contiguous()
+        S.diagonal().add_(eps)
+        flags.append(ops.potrf_(S, pivot_tol=4.0 * eps))
+        Ls.append(S)
+    if int(torch.stack(flags).max().item()) != 0:   # one host read-back decides the route
+        return None
+    return Ls
 
 
 class _CCALossFn(torch.autograd.Function):
@@ -35,17 +54,30 @@ class _CCALossFn(torch.autograd.Function):
         z1d, z2d = z1.detach(), z2.detach()
         mom = ops.moments([z1d, z2d], precision=precision)
         C, _ = ops.covariance(mom, [d1, d2], n, center=True, dtype=z1.dtype)
-        S12 = C[:d1, d1:]
-        whiten = []
-        for blk in (C[:d1, :d1], C[d1:, d1:]):
-            lam, Vt = ops.syevj(blk.contiguous())
-            # eigh(S + eps I) = (lam + eps, V); clamp(min=eps) <=> lam floored at 0
-            Wt, _, _ = ops.whiten_rows(lam, Vt, 0.0, floor_add=eps, rank_tol=-1.0, lam_floor=0.0)
-            whiten.append(Wt)
-        T = ops.gemm(ops.gemm(whiten[0], S12), whiten[1], transb=True)
+        S12 = C[:d1, d1:].contiguous()
+        Ls = _whiteners_cholesky(C, d1, eps)
+        if Ls is not None:
+            T = S12.clone()
+            ops.trsm_(Ls[0], T, side="left")                  # L1^-1 S12
+            ops.trsm_(Ls[1], T, side="right", trans=True)     # ... L2^-T
+            # S_ii^-1 = Linv_i^T Linv_i with Linv_i = L_i^-1 (small: d x d)
+            inv = []
+            for L in Ls:
+                E = torch.eye(L.shape[0], dtype=L.dtype, device=L.device)
+                inv.append(ops.trsm_(L, E, side="left"))
+            W1t, W2t = inv
+        else:
+            # eigen route: reproduces clamp(eigh(S + eps I), min=eps) exactly (rank-deficient batches)
+            whiten = []
+            for blk in (C[:d1, :d1], C[d1:, d1:]):
+                lam, Vt = ops.syevj(blk.contiguous())
+                Wt, _, _ = ops.whiten_rows(lam, Vt, 0.0, floor_add=eps, rank_tol=-1.0, lam_floor=0.0)
+                whiten.append(Wt)
+            W1t, W2t = whiten
+            T = ops.gemm(ops.gemm(W1t, S12), W2t, transb=True)
         fro = ops.frobenius_norm(T)
         loss = -(fro * fro).reshape(())
-        ctx.save_for_backward(z1d, z2d, whiten[0], whiten[1], S12.contiguous())
+        ctx.save_for_backward(z1d, z2d, W1t, W2t, S12)
         ctx.n = n
         return loss
 
@@ -53,7 +85,7 @@ class _CCALossFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         z1, z2, W1t, W2t, S12 = ctx.saved_tensors
         n = ctx.n
-        S1inv = ops.gemm(W1t, W1t, transa=True)          # S11^-1 = W1 W1^T
+        S1inv = ops.gemm(W1t, W1t, transa=True)          # S11^-1 = W1 W1^T  (W_i^T = L_i^-1 or Lam^-1/2 V^T)
         S2inv = ops.gemm(W2t, W2t, transa=True)
         P = ops.gemm(ops.gemm(S1inv, S12), S2inv)        # d1 x d2
         g11 = ops.gemm(ops.gemm(P, S12, transb=True), S1inv)   # P S21 S11^-1

@@ -69,3 +69,17 @@ def test_loss_trains_an_encoder():
         opt.step()
         first = loss.item() if first is None else first
     assert loss.item() < first - 0.1
+
+
+def test_loss_rank_deficient_batch_uses_eigen_route_and_matches_reference_forward():
+    """Fewer samples than features: S is singular, the eigenvalue clamp of the reference is active and the
+    Cholesky shortcut must not be taken.  Forward value against the oracle's literal restatement."""
+    from cca_zoo_b200.deep import CCALoss
+    from oracle import restatement as R
+
+    g = torch.Generator().manual_seed(4)
+    z1 = torch.randn(6, 9, generator=g, dtype=torch.float64)
+    z2 = torch.randn(6, 7, generator=g, dtype=torch.float64)
+    loss = CCALoss(eps=1e-3)([z1.cuda(), z2.cuda()])
+    ref = R.ref_ccaloss(z1.numpy(), z2.numpy(), 1e-3)
+    assert abs(loss.item() - ref) < 1e-6 * abs(ref)
