@@ -31,10 +31,18 @@ WORKLOAD = "rCCA.fit 2 views n=100000 rows/GPU d=[1024,1024] k=64 c=0.1 float32 
 
 
 def make_views(seed: int, n_rows: int = N_ROWS):
-    from cca_zoo_b200.datasets import joint_data
-
-    return joint_data(n_views=2, n_samples=n_rows, n_features=DIMS, latent_dimensions=K,
-                      signal_to_noise=SNR, random_state=seed, dtype=np.float32)
+    """Rows of ONE JointData-style population (cca_zoo/datasets/_simulated.py:113-125): the loading matrices
+    W_i come from a fixed stream shared by every rank, the latent draws and the noise from `seed`, so that
+    the row shards of different ranks are samples of the same model (a sharded data set, not N unrelated ones)."""
+    rng_w = np.random.default_rng(20240924)
+    weights = [rng_w.standard_normal((p, K)) for p in DIMS]
+    rng = np.random.default_rng(seed)
+    z = rng.standard_normal((n_rows, K))
+    views = []
+    for w in weights:
+        noise = rng.standard_normal((n_rows, w.shape[0])) * (1.0 / np.sqrt(SNR))
+        views.append((z @ w.T + noise).astype(np.float32))
+    return views
 
 
 # ----------------------------------------------------------------------------------------------

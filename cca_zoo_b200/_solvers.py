@@ -95,6 +95,143 @@ def topk_svd(T, k, max_rounds=4, iters_per_round=5, oversample=None, seed=1234):
     return None
 
 
+def topk_eigsh(K, k, shift, max_rounds=6, iters_per_round=8, seed=4321):
+    """Largest-k (algebraic) eigenpairs of the symmetric matrix K by blocked subspace iteration on
+    K + shift*I (shift >= -lambda_min(K) so that the shifted matrix is PSD) with Rayleigh-Ritz through the
+    Jacobi eigensolver.  Returns (evals[k] descending, evecs_t[k, D]) or None when the residual
+    ||K Z_k - Z_k diag(theta)||_F does not reach tol (no gap after the block): callers then run the full
+    Jacobi solve.  One host read-back per round."""
+    D = K.shape[0]
+    p = min(D, max(2 * k, k + 32))
+    gen = torch.Generator(device=K.device).manual_seed(seed)
+    Z = torch.randn((D, p), generator=gen, device=K.device, dtype=K.dtype)
+    flags = []
+    _cholqr_(Z, flags, passes=2)
+    tol = 200.0 * _eps(K.dtype)
+    for _ in range(max_rounds):
+        for it in range(iters_per_round):
+            Y = ops.gemm(K, Z)
+            if shift != 0.0:
+                Y.add_(Z, alpha=shift)
+            Z = _cholqr_(Y, flags, passes=2 if it == iters_per_round - 1 else 1)
+        KZ = ops.gemm(K, Z)                                   # D x p
+        H = ops.gemm(Z, KZ, transa=True)                      # p x p Rayleigh quotient matrix
+        H = 0.5 * (H + H.T)
+        nrm = ops.frobenius_norm(H)
+        theta, Qt = ops.syevj(H, shift=float(nrm.item()))     # descending
+        Zr_t = ops.gemm(Qt[:k], Z, transb=True)               # k x D : Ritz vectors as rows
+        E = ops.gemm(Qt[:k], KZ, transb=True)                 # rows: (K z_j)^T
+        E -= ops.scale(Zr_t, rows=theta[:k])
+        stats = torch.stack([ops.frobenius_norm(E)[0], theta[0].abs() + abs(shift),
+                             torch.stack(flags).max().to(K.dtype).reshape(())])
+        resid, scale, bad = (float(x) for x in stats.cpu())
+        if bad != 0.0 or not (scale > 0.0):
+            return None
+        if resid <= tol * scale * (k ** 0.5):
+            return theta[:k], Zr_t
+        flags = []
+        Z = ops.gemm(Z, Qt, transb=True)
+    return None
+
+
+def _cholesky_whiteners(C, dims, c, scales, eps_floor):
+    """Per view: R_i = (1-c_i) C_ii + c_i I = L_i L_i^T and Linv_i = sqrt(scale_i) L_i^-1.
+    Returns the list of Linv_i, or None when a block is not numerically positive definite or when
+    lambda_min(R_i) cannot be certified >= eps_floor (then the reference's eps floor, _mcca.py:170-172 /
+    _gcca.py:102-104, might be active and the eigen route must decide).  The certificate is
+    lambda_min(R) = 1 / ||R^-1||_2 >= 1 / ||L^-1||_F^2."""
+    sl = _slices(dims)
+    out, flags, norms = [], [], []
+    for i, s in enumerate(sl):
+        R = (1.0 - c[i]) * C[s, s]
+        R.diagonal().add_(c[i])
+        dmax = R.diagonal().max()
+        flags.append(ops.potrf_(R, pivot_tol=0.0))
+        Linv = torch.eye(dims[i], dtype=C.dtype, device=C.device)
+        ops.trsm_(R, Linv, side="left")
+        norms.append(torch.stack([ops.frobenius_norm(Linv)[0], dmax]))
+        out.append((R, Linv))
+    stats = torch.cat([torch.stack(flags).max().to(C.dtype).reshape(1), torch.stack(norms).reshape(-1)]).cpu()
+    if float(stats[0]) != 0.0:
+        return None
+    for i in range(len(dims)):
+        fro, dmax = float(stats[1 + 2 * i]), float(stats[2 + 2 * i])
+        if not (fro > 0.0) or not np.isfinite(fro):
+            return None
+        lam_min_lb = 1.0 / (fro * fro)
+        if lam_min_lb < eps_floor or lam_min_lb < _rank_tol(dims[i], C.dtype) * dmax:
+            return None
+    return [Linv if scales[i] == 1.0 else Linv.mul_(scales[i] ** 0.5) for i, (_, Linv) in enumerate(out)]
+
+
+def mcca_weights_cholesky(C, dims, latent_dimensions, c, eps):
+    """MCCA through the Cholesky reduction of the generalised problem (what scipy.linalg.eigh(A, B) does,
+    cca_zoo/_utils/_linalg.py:67-71): B_i = R_i/m = L_B L_B^T, K_ij = Linv_i C_ij Linv_j^T (i != j, zero
+    diagonal blocks), largest eigenpairs of K by subspace iteration, v_i = sqrt(m) Linv_i^T y_i (v^T B v = 1)."""
+    m = len(dims)
+    sl = _slices(dims)
+    D = C.shape[0]
+    k = min(latent_dimensions, D)
+    if 4 * k > D:
+        return None
+    Linv = _cholesky_whiteners(C, dims, c, [1.0] * m, eps)
+    if Linv is None:
+        return None
+    K = torch.zeros((D, D), dtype=C.dtype, device=C.device)
+    for i in range(m):
+        for j in range(i + 1, m):
+            tmp = ops.gemm(Linv[i], C[sl[i], sl[j]])
+            ops.gemm(tmp, Linv[j], transb=True, out=K[sl[i], sl[j]])
+            K[sl[j], sl[i]] = K[sl[i], sl[j]].T
+    cmax = max(c)
+    shift = 1.0 / (1.0 - cmax) if cmax <= 0.9 else float(ops.frobenius_norm(K).item())
+    res = topk_eigsh(K, k, shift)
+    if res is None:
+        return None
+    _, Yt = res
+    return [ops.gemm(Linv[i], Yt[:, sl[i]], transa=True, transb=True, alpha=m ** 0.5) for i in range(m)]
+
+
+def gcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c, mu, eps):
+    """GCCA primal form with Cholesky whiteners: Wt_i = sqrt(mu_i) L_i^-1, G = (n-1) Wt C Wt^T (PSD), top-k of
+    G by subspace iteration, W_i = C_ii^-1 [C Wt^T U]_i sig^-1/2 (C_ii^-1 from its own Cholesky factor)."""
+    m = len(dims)
+    sl = _slices(dims)
+    D = C.shape[0]
+    k = min(latent_dimensions, D, n_samples)
+    if 4 * k > D:
+        return None
+    Wt = _cholesky_whiteners(C, dims, c, mu, eps)
+    if Wt is None:
+        return None
+    # factors of the UNregularised blocks for pinv(X_i) = C_ii^-1 X_i^T/(n-1) (full column rank certified)
+    Lc = _cholesky_whiteners(C, dims, [0.0] * m, [1.0] * m, 0.0) if any(ci != 0.0 for ci in c) else \
+        [w / (mu[i] ** 0.5) for i, w in enumerate(Wt)]
+    if Lc is None:
+        return None
+    G = torch.empty((D, D), dtype=C.dtype, device=C.device)
+    for i in range(m):
+        for j in range(i, m):
+            tmp = ops.gemm(Wt[i], C[sl[i], sl[j]])
+            ops.gemm(tmp, Wt[j], transb=True, alpha=float(n_samples - 1), out=G[sl[i], sl[j]])
+            if j > i:
+                G[sl[j], sl[i]] = G[sl[i], sl[j]].T
+    res = topk_eigsh(G, k, 0.0)
+    if res is None:
+        return None
+    sig, Ut = res
+    P = torch.empty((D, k), dtype=C.dtype, device=C.device)
+    for i in range(m):
+        ops.gemm(Wt[i], Ut[:, sl[i]], transa=True, transb=True, out=P[sl[i]])
+    CP = ops.gemm(C, P)
+    out = []
+    for i in range(m):
+        t1 = ops.gemm(Lc[i], CP[sl[i]])                 # Linv CP_i
+        wi = ops.gemm(Lc[i], t1, transa=True)           # Linv^T Linv CP_i = C_ii^-1 CP_i
+        out.append(ops.scale(wi, cols=sig, cols_pow=-0.5))
+    return out
+
+
 def rcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c):
     """rCCA through the Cholesky form of the whitening (same weights as ``rcca_weights`` up to sign):
     R_i = (1-c_i) C_ii + c_i I = L_i L_i^T ; T = L_1^-1 C_12 L_2^-T ; weights = L_i^-T U_k / V_k.
@@ -158,7 +295,7 @@ def rcca_weights(C, dims, n_samples, latent_dimensions, c, solver="auto"):
     return [w1, w2]
 
 
-def mcca_weights(C, dims, latent_dimensions, c, eps):
+def mcca_weights(C, dims, latent_dimensions, c, eps, solver="auto"):
     """MCCA (cca_zoo/linear/_mcca.py:113-135,141-173): top-k of A v = lam B v, v^T B v = 1 with
     A = (C - blkdiag C_ii)/m, B = blkdiag((1-c_i) C_ii + c_i I)/m (+ eps floor).
 
@@ -166,6 +303,10 @@ def mcca_weights(C, dims, latent_dimensions, c, eps):
     symmetric one K y = lam y, K_ij = Wt_i A_ij Wt_j^T, v_i = Wt_i^T y_i.  K is indefinite (for two
     views its spectrum is +-sigma), so it is solved shifted by ||K||_F to keep +-pairs apart.
     """
+    if solver == "cholesky" or (solver == "auto" and C.shape[0] >= 512):
+        w = mcca_weights_cholesky(C, dims, latent_dimensions, c, eps)
+        if w is not None:
+            return w
     m = len(dims)
     sl = _slices(dims)
     D = C.shape[0]
@@ -189,13 +330,17 @@ def mcca_weights(C, dims, latent_dimensions, c, eps):
     return [ops.gemm(wts[i], evt[:k, sl[i]], transa=True, transb=True) for i in range(m)]
 
 
-def gcca_weights(C, dims, n_samples, latent_dimensions, c, mu, eps):
+def gcca_weights(C, dims, n_samples, latent_dimensions, c, mu, eps, solver="auto"):
     """GCCA in primal (D x D) form (cca_zoo/linear/_gcca.py:94-109).
 
     reg_i = (1-c_i) L_i + c_i (+ per-view eps floor, :102-104) ; Wt_i = diag(sqrt(mu_i) reg_i^-1/2) V_i^T ;
     G = (n-1) Wt C Wt^T (block-wise) ; top-k G u = sig u ;
     W_i = pinv(C_ii) [C Wt^T u]_i sig^-1/2   (pinv from the same eigendecomposition).
     """
+    if solver == "cholesky" or (solver == "auto" and C.shape[0] >= 512):
+        w = gcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c, mu, eps)
+        if w is not None:
+            return w
     m = len(dims)
     sl = _slices(dims)
     D = C.shape[0]

@@ -3,6 +3,8 @@ from __future__ import annotations
 
 from typing import Any, ClassVar
 
+from sklearn.utils._param_validation import StrOptions
+
 from .._base import BaseModel
 from .._solvers import gcca_weights
 from .._validation import perview_parameter
@@ -25,14 +27,16 @@ class GCCA(BaseModel):
         "c": RIDGE_PARAMETER,
         "view_weights": [None, "array-like"],
         "eps": POSITIVE_EPS,
+        "solver": [StrOptions({"auto", "eigen", "cholesky"})],
     }
 
     def __init__(self, latent_dimensions: int = 1, center: bool = True, c=0.0, view_weights=None,
-                 eps: float = 1e-6, precision: str = "tf32x3", device=None) -> None:
+                 eps: float = 1e-6, precision: str = "tf32x3", device=None, solver: str = "auto") -> None:
         super().__init__(latent_dimensions=latent_dimensions, center=center, precision=precision, device=device)
         self.c = c
         self.view_weights = view_weights
         self.eps = eps
+        self.solver = solver
 
     def fit(self, views, y=None):
         C, dims, n_total = self._fit_device(views)
@@ -42,4 +46,4 @@ class GCCA(BaseModel):
         c_ = perview_parameter("c", self.c, 0.0, self.n_views_)
         mu = perview_parameter("view_weights", self.view_weights, 1.0, self.n_views_)
         return gcca_weights(C, dims, n_total, self.latent_dimensions, [float(x) for x in c_],
-                            [float(x) for x in mu], float(self.eps))
+                            [float(x) for x in mu], float(self.eps), solver=self.solver)

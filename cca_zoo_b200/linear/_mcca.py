@@ -4,7 +4,7 @@ from __future__ import annotations
 from numbers import Real
 from typing import Any, ClassVar
 
-from sklearn.utils._param_validation import Interval
+from sklearn.utils._param_validation import Interval, StrOptions
 
 from .._base import BaseModel
 from .._solvers import mcca_weights
@@ -34,14 +34,16 @@ class MCCA(BaseModel):
         "c": RIDGE_PARAMETER,
         "pca": ["boolean"],
         "eps": POSITIVE_EPS,
+        "solver": [StrOptions({"auto", "eigen", "cholesky"})],
     }
 
     def __init__(self, latent_dimensions: int = 1, center: bool = True, c=0.0, pca: bool = True,
-                 eps: float = 1e-6, precision: str = "tf32x3", device=None) -> None:
+                 eps: float = 1e-6, precision: str = "tf32x3", device=None, solver: str = "auto") -> None:
         super().__init__(latent_dimensions=latent_dimensions, center=center, precision=precision, device=device)
         self.c = c
         self.pca = pca
         self.eps = eps
+        self.solver = solver
 
     def fit(self, views, y=None):
         C, dims, n_total = self._fit_device(views)
@@ -49,4 +51,5 @@ class MCCA(BaseModel):
 
     def _solve(self, C, dims, n_total):
         c_ = perview_parameter("c", self.c, 0.0, self.n_views_)
-        return mcca_weights(C, dims, self.latent_dimensions, [float(x) for x in c_], float(self.eps))
+        return mcca_weights(C, dims, self.latent_dimensions, [float(x) for x in c_], float(self.eps),
+                            solver=self.solver)

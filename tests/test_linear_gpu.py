@@ -167,3 +167,37 @@ def test_rcca_cholesky_route_falls_back_when_rank_deficient():
     a = rCCA(latent_dimensions=3, c=0.0, solver="eigen").fit([x1, x2])
     b = rCCA(latent_dimensions=3, c=0.0, solver="cholesky").fit([x1, x2])
     np.testing.assert_allclose(b.score([x1, x2]), a.score([x1, x2]), rtol=1e-6)
+
+
+def test_mcca_gcca_cholesky_route_equals_eigen_route_and_oracle():
+    """solver="cholesky" (Cholesky reduction + top-k subspace iteration) vs solver="eigen" vs the oracle, float64."""
+    from cca_zoo_b200.datasets import joint_data
+    from cca_zoo_b200.linear import GCCA, MCCA
+
+    dims = [220, 200, 180]
+    views = joint_data(n_views=3, n_samples=5000, n_features=dims, latent_dimensions=6,
+                       signal_to_noise=0.05, random_state=21)
+    M, s, n = R.moments(views)
+    C = R.covariance_from_moments(M, s, n)
+    w_or, _ = R.cov_mcca_fit(C, dims, 6, [0.1, 0.0, 0.2])
+    for solver in ("eigen", "cholesky", "auto"):
+        est = MCCA(latent_dimensions=6, c=[0.1, 0.0, 0.2], solver=solver).fit(views)
+        assert R.max_rel_err_per_vector(est.weights_, w_or) < 1e-5, solver
+    w_or, _ = R.cov_gcca_fit(C, dims, n, 6, [0.1, 0.0, 0.2], [1.0, 2.0, 0.5])
+    for solver in ("eigen", "cholesky", "auto"):
+        est = GCCA(latent_dimensions=6, c=[0.1, 0.0, 0.2], view_weights=[1.0, 2.0, 0.5], solver=solver).fit(views)
+        assert R.max_rel_err_per_vector(est.weights_, w_or) < 1e-5, solver
+
+
+def test_mcca_cholesky_route_declines_when_eps_floor_may_be_active():
+    """A nearly singular view: lambda_min(B) < eps, the reference adds the floor (_mcca.py:170-172); the
+    Cholesky route cannot certify lambda_min and must hand over to the eigen route (same answer as eigen)."""
+    from cca_zoo_b200.linear import MCCA
+
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal((3000, 200))
+    x1 = np.hstack([base, base[:, :100] + 1e-5 * rng.standard_normal((3000, 100))])   # 300 cols, 100 nearly dependent
+    x2 = rng.standard_normal((3000, 280)) + np.hstack([base, base[:, :80]])
+    a = MCCA(latent_dimensions=4, solver="eigen").fit([x1, x2])
+    b = MCCA(latent_dimensions=4, solver="cholesky").fit([x1, x2])
+    np.testing.assert_allclose(b.score([x1, x2]), a.score([x1, x2]), rtol=1e-8)
