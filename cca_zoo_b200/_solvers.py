@@ -60,7 +60,7 @@ def _cholqr_(Y, flags, passes=1):
 def topk_svd(T, k, max_rounds=4, iters_per_round=5, oversample=None, seed=1234):
     """Leading k singular triplets of T (d1 x d2) by blocked subspace iteration + Rayleigh-Ritz.
 
-    Z <- orth(T^T orth(T Z)) repeated (one CholQR pass per product: enough to keep the block
+    Z <- orth(T^T T Z) repeated (one CholQR pass per iteration: enough to keep the block
     well-conditioned; the last one is done twice); then the Jacobi SVD of the thin block Y = T Z (d1 x p)
     gives U, sigma and V = Z V_y.  Converged when ||T^T U_k - V_k diag(sigma)||_F <= tol sigma_1 sqrt(k) (the
     other residual T v_j - sigma_j u_j vanishes by construction).  Returns (sigma[k], Ut[k,d1], Vt[k,d2]) or
@@ -76,7 +76,9 @@ def topk_svd(T, k, max_rounds=4, iters_per_round=5, oversample=None, seed=1234):
     tol = 200.0 * _eps(T.dtype)
     for _ in range(max_rounds):
         for it in range(iters_per_round):
-            Y = _cholqr_(ops.gemm(T, Z), flags)                   # d1 x p
+            # one application of T^T T between orthonormalisations: the block's condition number grows by
+            # (sigma_1/sigma_p)^2 per step, far below what a single CholQR pass tolerates
+            Y = ops.gemm(T, Z)                                    # d1 x p
             Z = _cholqr_(ops.gemm(T, Y, transa=True), flags,      # d2 x p
                          passes=2 if it == iters_per_round - 1 else 1)
         Yt = ops.gemm(Z, T, transa=True, transb=True)       # (T Z)^T : p x d1, rows = columns of Y
