@@ -236,11 +236,19 @@ def run_ours(args):
     flops = N_ROWS * D * (D + 1)  # algorithmic: symmetric product, SURVEY.md §8d
     k1 = float(np.mean([m for m in k1_ms if m and m > 0])) if any(m and m > 0 for m in k1_ms) else None
     passes = 3 if args.precision == "tf32x3" else 1
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_k1_traffic.json")) as f:
+            tr = json.load(f)[args.precision]
+        traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]   # one ncu --set full capture, per launch
+    except Exception:
+        pass
     roof = None
     if k1:
         ach = flops / (k1 * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "moments_tf32_kernel", "achieved": ach, "peak": bf16 / 2, "unit": "TFLOP/s",
-                "frac": ach / (bf16 / 2), "traffic": None, "kernel_ms": k1, "mma_passes": passes,
+        roof = {"bound": "tensor", "kernel": "moments_tf32_2cta_kernel", "achieved": ach, "peak": bf16 / 2,
+                "unit": "TFLOP/s", "frac": ach / (bf16 / 2), "traffic": traffic, "kernel_ms": k1, "mma_passes": passes,
+                "algorithmic_flops": flops, "algorithmic_bytes": N_ROWS * D * 4,
                 "frac_of_issued": passes * ach / (bf16 / 2), "peak_source": peak_src,
                 "share_of_step": k1 / ms_per_step}
 
