@@ -201,3 +201,36 @@ def test_mcca_cholesky_route_declines_when_eps_floor_may_be_active():
     a = MCCA(latent_dimensions=4, solver="eigen").fit([x1, x2])
     b = MCCA(latent_dimensions=4, solver="cholesky").fit([x1, x2])
     np.testing.assert_allclose(b.score([x1, x2]), a.score([x1, x2]), rtol=1e-8)
+
+
+def test_edge_shapes():
+    """Smallest legal inputs, single-column views, more columns than samples, too many views."""
+    from cca_zoo_b200.linear import CCA, MCCA, rCCA
+
+    rng = np.random.default_rng(0)
+    # one column per view: the single canonical correlation is |Pearson r|
+    x, y = rng.standard_normal((40, 1)), rng.standard_normal((40, 1))
+    y = y + 0.8 * x
+    est = CCA(latent_dimensions=1).fit([x, y])
+    r = np.corrcoef(x[:, 0], y[:, 0])[0, 1]
+    np.testing.assert_allclose(np.abs(est.score([x, y])), [abs(r)], atol=1e-10)
+    # n < d with ridge: the covariance blocks are singular, the whitening must still be finite
+    a, b = rng.standard_normal((20, 50)), rng.standard_normal((20, 30))
+    est = rCCA(latent_dimensions=3, c=0.5).fit([a, b])
+    assert all(np.isfinite(w).all() for w in est.weights_)
+    from oracle import restatement as R
+    w_ref, _ = R.ref_rcca_fit([a, b], 3, 0.5)
+    assert R.max_rel_err_per_vector(est.weights_, w_ref) < 1e-6
+    # minimum sample count for a covariance
+    with pytest.raises(ValueError):
+        CCA().fit([rng.standard_normal((1, 3)), rng.standard_normal((1, 2))])
+    # more views than the moment kernel's tile table supports -> a clear error, not a wrong answer
+    many = [rng.standard_normal((30, 2)) for _ in range(9)]
+    with pytest.raises(ValueError, match="views"):
+        MCCA().fit(many)
+    # non-finite input in a CUDA tensor is rejected like check_array does for numpy
+    import torch
+    bad = torch.randn(30, 4, device="cuda")
+    bad[3, 2] = float("nan")
+    with pytest.raises(ValueError, match="NaN|infinity"):
+        CCA().fit([bad, torch.randn(30, 3, device="cuda")])
