@@ -22,6 +22,35 @@ def _eps(dtype):
     return float(torch.finfo(dtype).eps)
 
 
+class _two_streams:
+    """Fork the current stream into two side streams and join them back on exit: independent per-view
+    chains of small latency-bound kernels (Cholesky factorisations, back-substitutions) overlap."""
+
+    _pool = {}
+
+    def __init__(self, device):
+        self.device = device
+
+    def __enter__(self):
+        key = (self.device.index, torch.cuda.current_stream(self.device).cuda_stream)
+        if key not in self._pool:
+            self._pool[key] = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
+        self.streams = self._pool[key]
+        self.main = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(self.main)
+        for st in self.streams:
+            st.wait_event(ev)
+        return self.streams
+
+    def __exit__(self, *exc):
+        for st in self.streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            self.main.wait_event(ev)
+        return False
+
+
 def _rank_tol(d, dtype):
     """Relative eigenvalue threshold below which a direction of a d x d covariance block is treated as
     numerically null: the covariance-space image of the reference's ``s > 0`` filter
@@ -81,17 +110,22 @@ def topk_svd(T, k, max_rounds=4, iters_per_round=5, oversample=None, seed=1234):
             Y = ops.gemm(T, Z)                                    # d1 x p
             Z = _cholqr_(ops.gemm(T, Y, transa=True), flags,      # d2 x p
                          passes=2 if it == iters_per_round - 1 else 1)
-        Yt = ops.gemm(Z, T, transa=True, transb=True)       # (T Z)^T : p x d1, rows = columns of Y
-        sig, Vy_t, Ut = ops.gesvj(Yt)                       # Y = U diag(sig) Vy^T
+        # Rayleigh-Ritz on Y = T Z (d1 x p): Y^T Y = Vy diag(sig^2) Vy^T (p x p Jacobi eigensolve; the block is
+        # well conditioned -- sigma_1/sigma_p is a few units -- so squaring costs nothing at the top), then
+        # U = Y Vy diag(1/sig), V = Z Vy
+        Y = ops.gemm(T, Z)                                  # d1 x p
+        sig2, Vy_t = ops.syevj(ops.gemm(Y, Y, transa=True))
+        sig = sig2.clamp_min(0).sqrt()
+        Ut = ops.scale(ops.gemm(Vy_t[:k], Y, transb=True), rows=sig[:k], rows_pow=-1)   # k x d1
         Vt = ops.gemm(Vy_t[:k], Z, transb=True)             # k x d2 : rows of (Z Vy)^T
-        E = ops.gemm(Ut[:k], T)                             # rows: u_j^T T
+        E = ops.gemm(Ut, T)                                 # rows: u_j^T T
         E -= ops.scale(Vt, rows=sig[:k])
         stats = torch.stack([ops.frobenius_norm(E)[0], sig[0], torch.stack(flags).max().to(T.dtype).reshape(())])
         resid, s1, bad = (float(x) for x in stats.cpu())    # the round's single host read-back
         if bad != 0.0 or not (s1 > 0.0):
             return None
         if resid <= tol * s1 * (k ** 0.5):
-            return sig[:k], Ut[:k], Vt
+            return sig[:k], Ut, Vt
         flags = []
         Z = ops.gemm(Z, Vy_t, transb=True)                  # continue from the Ritz basis (all p vectors)
     return None
@@ -240,15 +274,18 @@ def rcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c):
     Returns None when a regularised block is not numerically positive definite (the eigen route, which
     reproduces the reference's rank handling, is used instead)."""
     s1, s2 = _slices(dims)
-    Ls = []
-    for i, s in enumerate((s1, s2)):
-        R = (1.0 - c[i]) * C[s, s]
-        R.diagonal().add_(c[i])
-        dmax = float(R.diagonal().max().item())
-        info = ops.potrf_(R, pivot_tol=_rank_tol(dims[i], C.dtype) * dmax)
-        if int(info.item()) != 0:
-            return None
-        Ls.append(R)
+    Ls, infos = [], []
+    dmax = torch.stack([C[s, s].diagonal().max() for s in (s1, s2)]).cpu()      # one read-back for both views
+    with _two_streams(C.device) as streams:
+        for i, s in enumerate((s1, s2)):
+            with torch.cuda.stream(streams[i]):       # the two factorisations are independent: run them abreast
+                R = (1.0 - c[i]) * C[s, s]
+                R.diagonal().add_(c[i])
+                tol = _rank_tol(dims[i], C.dtype) * ((1.0 - c[i]) * float(dmax[i]) + c[i])
+                infos.append(ops.potrf_(R, pivot_tol=tol))
+                Ls.append(R)
+    if int(torch.stack(infos).max().item()) != 0:
+        return None
     T = C[s1, s2].contiguous()
     ops.trsm_(Ls[0], T, side="left")                 # L1^-1 C12
     ops.trsm_(Ls[1], T, side="right", trans=True)    # ... L2^-T
@@ -261,8 +298,11 @@ def rcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c):
         _, Ut, Vt = res
     w1 = Ut.T.contiguous()
     w2 = Vt.T.contiguous()
-    ops.trsm_(Ls[0], w1, side="left", trans=True)    # L1^-T U_k
-    ops.trsm_(Ls[1], w2, side="left", trans=True)
+    with _two_streams(C.device) as streams:
+        with torch.cuda.stream(streams[0]):
+            ops.trsm_(Ls[0], w1, side="left", trans=True)    # L1^-T U_k
+        with torch.cuda.stream(streams[1]):
+            ops.trsm_(Ls[1], w2, side="left", trans=True)
     return [w1, w2]
 
 
