@@ -118,6 +118,32 @@ def cpu_baseline(budget_s: float = 20.0):
                       f"{t:.2f} s measured, x{N_ROWS / n_s:.1f} linear-in-n extrapolation"}
 
 
+def parity_vs_oracle(est, views):
+    """Outside the timed region: the fitted weights / canonical correlations against the float64 oracle
+    (covariance form of cca_zoo/linear/_rcca.py:83-101, numpy LAPACK) on the very same float32 inputs."""
+    from oracle import restatement as R
+
+    X = np.hstack(views).astype(np.float64)
+    n = X.shape[0]
+    mu = X.mean(axis=0)
+    X -= mu
+    C = X.T @ X / (n - 1)
+    del X
+    w_ref, sv = R.cov_rcca_fit(C, DIMS, K, C_RIDGE, n)
+    w = [x.astype(np.float64) for x in est.weights_]
+    ws = R.align_signs(w, w_ref)
+    per_vec = np.concatenate([np.linalg.norm(a - b, axis=0) / np.linalg.norm(b, axis=0) for a, b in zip(ws, w_ref)])
+    sub = np.random.default_rng(0).choice(n, 20_000, replace=False)
+    vs = [v[sub] for v in views]
+    sc = est.score(vs)
+    sc_ref = R.score(vs, [mu[:DIMS[0]], mu[DIMS[0]:]], w_ref)
+    return {"oracle": "oracle.restatement.cov_rcca_fit, float64, same inputs",
+            "max_weight_rel_err": float(per_vec.max()), "median_weight_rel_err": float(np.median(per_vec)),
+            "canonical_corr_max_rel_err": float(np.max(np.abs(sc - sc_ref) / np.abs(sc_ref))),
+            "subspace_distance": float(max(R.subspace_distance(w[i], w_ref[i]) for i in range(2))),
+            "min_gap_of_reference_spectrum": float(np.min(-np.diff(sv))), "tolerance_float32": 1e-3}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -268,6 +294,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline()
+        line["parity"] = parity_vs_oracle(est, [h.numpy() for h in host])
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
