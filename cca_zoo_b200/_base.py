@@ -142,8 +142,46 @@ class BaseModel(BaseEstimator, ABC):
         """Average pairwise canonical correlations per dimension (cca_zoo/_base.py:140-151)."""
         return self.average_pairwise_correlations(views)
 
+    #: element count above which host inputs are scored on the device as well (one K1 pass instead of
+    #: m tall numpy products); CUDA tensors always are
+    _device_score_threshold: ClassVar[int] = 1 << 24
+
+    def _pairwise_correlations_device(self, validated):
+        """Correlations of the variates from the block covariance of ``views``:
+        corr(X_i w_i, X_j w_j) = w_i^T C_ij w_j / sqrt(w_i^T C_ii w_i * w_j^T C_jj w_j)  per latent dimension,
+        exactly what cca_zoo/_base.py:153-174 computes from the transformed samples (its centring makes the
+        stored ``means_`` irrelevant) -- at the cost of one moment pass (K1) instead of m tall products."""
+        device = self._device()
+        dev_views = [self._to_device(v, device) for v in validated]
+        if len({v.dtype for v in dev_views}) > 1:
+            dev_views = [v.to(torch.float64) for v in dev_views]
+        dims = [int(v.shape[1]) for v in dev_views]
+        if dims != list(self.n_features_in_):
+            raise ValueError(f"views have {dims} features, the model was fitted on {self.n_features_in_}")
+        mom = ops.moments(dev_views, precision=self.precision)
+        mom, n_total = parallel.allreduce_moments(mom, int(dev_views[0].shape[0]))
+        C, _ = ops.covariance(mom, dims, n_total, center=True, dtype=torch.float64)
+        off = np.concatenate([[0], np.cumsum(dims)]).astype(int)
+        sl = [slice(int(off[i]), int(off[i + 1])) for i in range(len(dims))]
+        W = [torch.from_numpy(np.ascontiguousarray(w, dtype=np.float64)).to(device) for w in self.weights_]
+        m, k = len(dims), W[0].shape[1]
+        S = torch.empty((m, m, k), dtype=torch.float64, device=device)
+        for i in range(m):
+            Ti = ops.gemm(C[:, sl[i]], W[i])                      # D x k : C[:, i] w_i
+            for j in range(m):
+                S[j, i] = ops.gemm(W[j], Ti[sl[j]], transa=True).diagonal()
+        S = S.cpu().numpy()
+        norms = np.sqrt(np.stack([S[i, i] for i in range(m)]) * (n_total - 1))     # ||centred variate||
+        denom = np.where(norms > 1e-12, norms, 1.0) / np.sqrt(n_total - 1)
+        return S / (denom[:, None, :] * denom[None, :, :])
+
     def pairwise_correlations(self, views):
         """(n_views, n_views, k) Pearson correlations of the variates (cca_zoo/_base.py:153-174)."""
+        check_is_fitted(self)
+        on_gpu = any(isinstance(v, torch.Tensor) and v.is_cuda for v in views)
+        big = sum(int(np.prod(getattr(v, "shape", (0,)))) for v in views) >= self._device_score_threshold
+        if on_gpu or (big and torch.cuda.is_available()):
+            return self._pairwise_correlations_device(validate_views(views))
         transformed = self.transform(views)
         T = np.stack(transformed, axis=0)
         T = T - T.mean(axis=1, keepdims=True)

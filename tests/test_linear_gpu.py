@@ -234,3 +234,20 @@ def test_edge_shapes():
     bad[3, 2] = float("nan")
     with pytest.raises(ValueError, match="NaN|infinity"):
         CCA().fit([bad, torch.randn(30, 3, device="cuda")])
+
+
+def test_device_score_path_equals_reference_definition():
+    """score() of CUDA inputs is computed from one moment pass; it must equal the
+    sample-wise definition of cca_zoo/_base.py:153-194 (numpy path) for every estimator family."""
+    import torch
+    from cca_zoo_b200.linear import GCCA, MCCA, rCCA
+
+    views = G.dataset("joint3_med")
+    test = [v[:700] + 0.3 for v in views]                     # different rows, shifted means
+    for est in (rCCA(latent_dimensions=4, c=0.1).fit(views[:2]), MCCA(latent_dimensions=3, c=0.05).fit(views),
+                GCCA(latent_dimensions=3).fit(views)):
+        vs = test[:2] if isinstance(est, rCCA) else test
+        host = est.pairwise_correlations(vs)
+        dev = est.pairwise_correlations([torch.from_numpy(v).cuda() for v in vs])
+        np.testing.assert_allclose(dev, host, atol=1e-9)
+        np.testing.assert_allclose(est.score([torch.from_numpy(v).cuda() for v in vs]), est.score(vs), atol=1e-9)
