@@ -40,6 +40,8 @@ SIGNATURES = {
                             C.c_int64, C.c_double, _vp, C.c_int64, _vp]),
     "ccab_whiten_rows": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_double, C.c_double, _vp, C.c_double,
                                    C.c_double, C.c_int, C.c_double, _vp, C.c_int64, _vp, _vp, _vp]),
+    "ccab_ccaloss_small": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, C.c_double, _vp, _vp, _vp, _vp, _vp,
+                                     _vp]),
     "ccab_potrf": (C.c_int, [C.c_int, C.c_int, _vp, C.c_int64, C.c_double, _vp, _vp]),
     "ccab_trsm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp]),
     "ccab_scale": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int64,

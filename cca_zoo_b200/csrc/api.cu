@@ -7,6 +7,7 @@
 #include <atomic>
 #include <exception>
 
+#include "ccaloss.cuh"
 #include "chol.cuh"
 #include "common.cuh"
 #include "dense.cuh"
@@ -264,6 +265,24 @@ int ccab_whiten_rows(int dtype, int d, const void* lam, const void* Vt, int64_t 
   return whiten_rows<double>(d, static_cast<const double*>(lam), static_cast<const double*>(Vt), ldv, c, floor_add,
                              static_cast<const double*>(floor_dev), scale, rank_tol, max_rank, lam_floor,
                              static_cast<double*>(Wt), ldw, static_cast<double*>(g_out), rank_out, s);
+  CCAB_CATCH
+}
+
+int ccab_ccaloss_small(int dtype, int d1, int d2, const void* C, int64_t ldc, double eps, void* loss, void* G11,
+                       void* P, void* G22, void* min_pivot, void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(C && loss && G11 && P && G22 && min_pivot, "null pointer argument");
+  int rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CCAB_F32)
+    return ccaloss_small<float>(static_cast<const float*>(C), ldc, d1, d2, eps, static_cast<float*>(loss),
+                                static_cast<float*>(G11), static_cast<float*>(P), static_cast<float*>(G22),
+                                static_cast<float*>(min_pivot), s);
+  return ccaloss_small<double>(static_cast<const double*>(C), ldc, d1, d2, eps, static_cast<double*>(loss),
+                               static_cast<double*>(G11), static_cast<double*>(P), static_cast<double*>(G22),
+                               static_cast<double*>(min_pivot), s);
   CCAB_CATCH
 }
 

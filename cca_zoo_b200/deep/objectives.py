@@ -54,6 +54,15 @@ class _CCALossFn(torch.autograd.Function):
         z1d, z2d = z1.detach(), z2.detach()
         mom = ops.moments([z1d, z2d], precision=precision)
         C, _ = ops.covariance(mom, [d1, d2], n, center=True, dtype=z1.dtype)
+        ctx.n = n
+        if max(d1, d2) <= 64:
+            # fused small-matrix stage (K6): loss and the three gradient matrices in one single-CTA launch
+            loss1, G11, P, G22, minp = ops.ccaloss_small(C, d1, d2, eps)
+            if float(minp.item()) > 4.0 * eps:          # clamp provably inactive (one host read-back)
+                ctx.fused = True
+                ctx.save_for_backward(z1d, z2d, G11, P, G22)
+                return loss1.reshape(()).clone()
+        ctx.fused = False
         S12 = C[:d1, d1:].contiguous()
         Ls = _whiteners_cholesky(C, d1, eps)
         if Ls is not None:
@@ -78,18 +87,20 @@ class _CCALossFn(torch.autograd.Function):
         fro = ops.frobenius_norm(T)
         loss = -(fro * fro).reshape(())
         ctx.save_for_backward(z1d, z2d, W1t, W2t, S12)
-        ctx.n = n
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        z1, z2, W1t, W2t, S12 = ctx.saved_tensors
         n = ctx.n
-        S1inv = ops.gemm(W1t, W1t, transa=True)          # S11^-1 = W1 W1^T  (W_i^T = L_i^-1 or Lam^-1/2 V^T)
-        S2inv = ops.gemm(W2t, W2t, transa=True)
-        P = ops.gemm(ops.gemm(S1inv, S12), S2inv)        # d1 x d2
-        g11 = ops.gemm(ops.gemm(P, S12, transb=True), S1inv)   # P S21 S11^-1
-        g22 = ops.gemm(ops.gemm(S2inv, S12, transa=False, transb=True), P)  # S22^-1 S21 P
+        if ctx.fused:
+            z1, z2, g11, P, g22 = ctx.saved_tensors
+        else:
+            z1, z2, W1t, W2t, S12 = ctx.saved_tensors
+            S1inv = ops.gemm(W1t, W1t, transa=True)          # S11^-1 = W1 W1^T  (W_i^T = L_i^-1 or Lam^-1/2 V^T)
+            S2inv = ops.gemm(W2t, W2t, transa=True)
+            P = ops.gemm(ops.gemm(S1inv, S12), S2inv)        # d1 x d2
+            g11 = ops.gemm(ops.gemm(P, S12, transb=True), S1inv)   # P S21 S11^-1
+            g22 = ops.gemm(ops.gemm(S2inv, S12, transa=False, transb=True), P)  # S22^-1 S21 P
         a = 2.0 / (n - 1)
         g1 = ops.gemm(z1, g11, alpha=a)
         ops.gemm(z2, P, transb=True, alpha=-a, beta=1.0, out=g1)

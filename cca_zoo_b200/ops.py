@@ -203,6 +203,23 @@ def whiten_rows(lam, Vt, c, floor_add=0.0, floor_dev=None, scale=1.0, rank_tol=0
     return Wt, g, rank
 
 
+def ccaloss_small(Cm, d1, d2, eps):
+    """Fused loss stage for widths <= 64: returns (loss[1], G11, P, G22, min_pivot[1]) device tensors."""
+    lib = _lib.load()
+    _require_cuda(Cm, "C")
+    dev, dt = Cm.device, Cm.dtype
+    loss = torch.empty(1, dtype=dt, device=dev)
+    minp = torch.empty(1, dtype=dt, device=dev)
+    G11 = torch.empty((d1, d1), dtype=dt, device=dev)
+    P = torch.empty((d1, d2), dtype=dt, device=dev)
+    G22 = torch.empty((d2, d2), dtype=dt, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.ccab_ccaloss_small(_DT[dt], d1, d2, _ptr(Cm), Cm.stride(0), float(eps), _ptr(loss), _ptr(G11), _ptr(P),
+                                    _ptr(G22), _ptr(minp), _stream(Cm))
+    _lib.check(rc, "ccab_ccaloss_small")
+    return loss, G11, P, G22, minp
+
+
 def potrf_(A, pivot_tol=0.0):
     """In place lower Cholesky of a square row-major CUDA matrix.  Returns the device info flag (int32[1])."""
     lib = _lib.load()

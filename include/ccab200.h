@@ -114,6 +114,17 @@ int ccab_whiten_rows(int dtype, int d, const void* lam, const void* Vt, int64_t 
                      const void* floor_dev, double scale, double rank_tol, int max_rank, double lam_floor, void* Wt,
                      int64_t ldw, void* g_out, int* rank_out, void* stream);
 
+/* ---- K6: fused small-matrix stage of the deep-CCA objective (widths d1, d2 <= 64) -------------------
+ * From the (d1+d2)^2 block covariance C of [z1 z2] (device, row-major): S_ii = C_ii + eps I,
+ * P = S11^-1 S12 S22^-1, loss[0] = -<P, S12> = -||S11^-1/2 S12 S22^-1/2||_F^2, G11 = P S21 S11^-1 (d1 x d1),
+ * G22 = S22^-1 S21 P (d2 x d2), P (d1 x d2), and min_pivot[0] = the smallest elimination pivot of S11/S22:
+ * min_pivot > 4 eps certifies that the eigenvalue clamp of the reference is inactive (otherwise callers take
+ * the eigen route).  One single-CTA launch.
+ * Replaces: _inv_sqrtm x2, the T / T^T T products and eigvalsh of cca_zoo/deep/objectives.py:94-102 (forward)
+ * and supplies the matrices of the analytic backward. */
+int ccab_ccaloss_small(int dtype, int d1, int d2, const void* C, int64_t ldc, double eps, void* loss, void* G11,
+                       void* P, void* G22, void* min_pivot, void* stream);
+
 /* ---- Cholesky route of the generalised problem ----------------------------------------------------
  * ccab_potrf: lower triangle of A (n x n, row-major, device) <- L with A = L L^T, in place (the strict
  * upper triangle is not referenced).  *info_dev (device int): 0, or the 1-based index of the first pivot
