@@ -3,7 +3,8 @@
 //   * moments_tf32_kernel : tcgen05.mma kind::tf32, both operands MN-major straight out of row-major X
 //     (TMA boxes of 32 columns x KC rows, 128B rows swizzled in 32B chunks), fp32 accumulators in TMEM, warp-specialised
 //     (TMA producer / single-thread MMA issuer / 4 epilogue warps), split over the sample axis.
-//     Optional 3xTF32 (hi/lo split operands, 3 MMAs per k-step) for fp32-grade accuracy.
+//     Optional 3xTF32 (raw operand = hi by hardware truncation, materialised residual lo, 3 MMAs per k-step)
+//     for fp32-grade accuracy.
 //     Column sums ride on the same pipeline as one extra N=16 MMA against a block of ones.
 //   * moments_simt_kernel : exact FMA (fp32 or fp64) tile kernel for fp64 inputs and as the
 //     non-tensor reference path.
@@ -65,7 +66,7 @@ float moments_profile_last_ms() {
 }
 
 TcDebug& tc_debug() {
-  static TcDebug d = {-1, -1, -1, 0, 0, 0, 0};
+  static TcDebug d = {-1, -1, -1, 0, 0, 0, 0, 0};
   return d;
 }
 
@@ -486,9 +487,21 @@ moments_tf32_2cta_kernel(const __grid_constant__ TcParams2 p) {
   }
 }
 
-// hi = rna_tf32(x), lo = rna_tf32(x - hi): the 3xTF32 operand split (one HBM-bound pre-pass)
-__global__ void split_tf32_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx,
-                                  float* __restrict__ hi, float* __restrict__ lo, int64_t ldo) {
+// 3xTF32 operand split.  The tensor core TRUNCATES its fp32 operands to TF32 (measured: tools/probe_trunc.py),
+// so the raw array itself serves as the "hi" operand (hi = x with the low 13 mantissa bits cleared) and only
+// the residual lo = rna_tf32(x - hi) is materialised (exact subtraction, then 11 significant bits: the
+// hardware's own truncation of lo is a no-op).  x = hi + lo + O(2^-21 |x|).  One HBM-bound pre-pass:
+// reads n*d*4 bytes, writes n*d*4 bytes.
+__device__ __forceinline__ float tf32_residual(float v) {
+  const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  uint32_t l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+  return __uint_as_float(l);
+}
+
+// round-to-nearest variant: hi = rna_tf32(x), lo = rna_tf32(x - hi); both operands materialised
+__global__ void tf32_split_rn_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx,
+                                     float* __restrict__ hi, float* __restrict__ lo, int64_t ldo) {
   const int64_t total = n * (int64_t)d;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -502,6 +515,34 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, int64_t n, int d,
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hf));
     hi[r * ldo + c] = hf;
     lo[r * ldo + c] = __uint_as_float(l);
+  }
+}
+
+__global__ void tf32_residual_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx,
+                                     float* __restrict__ lo, int64_t ldo, int vec4) {
+  if (vec4) {
+    const int d4 = d >> 2;
+    const int64_t total = n * (int64_t)d4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = i / d4;
+      const int c = (int)(i - r * d4) << 2;
+      const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+      float4 o;
+      o.x = tf32_residual(v.x);
+      o.y = tf32_residual(v.y);
+      o.z = tf32_residual(v.z);
+      o.w = tf32_residual(v.w);
+      *reinterpret_cast<float4*>(lo + r * ldo + c) = o;
+    }
+  } else {
+    const int64_t total = n * (int64_t)d;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = i / d;
+      const int c = (int)(i - r * d);
+      lo[r * ldo + c] = tf32_residual(x[r * ldx + c]);
+    }
   }
 }
 
@@ -733,17 +774,24 @@ TcPlan plan_tc(const ColumnLayout& L, int64_t n_rows, bool x3) {
   P.ntiles = nt;
   const int slots = P.two_cta ? sm_count() / 2 : sm_count();  // CTA pairs occupy two SMs
   int S = 1;
+  int max_splits = 64;
   if (nt < slots) S = slots / nt;
   if (x3) {
     // tcgen05 accumulates in fp32 with round-toward-zero: a monotone sum (every diagonal entry of M) drifts
-    // low by ~0.5 ulp per accumulation step.  The 3xTF32 mode exists for fp32-grade results, so bound one
-    // accumulator run to 8192 samples (1024 steps, < 6e-5 relative) and let the fixed-order double reduction
-    // of the partials do the long sum.
-    S = std::max<int64_t>(S, ceil_div(n_rows, 8192));
+    // low by ~0.5 ulp per accumulation step -- measured -1.4e-4 relative on the diagonal for 8192-sample runs,
+    // uniform to 1e-6 (tools/probe_x3.py), which acts like a negative ridge and costs ~1e-3 in the weights.
+    // The 3xTF32 mode exists for fp32-grade results, so bound one accumulator run to 2048 samples (256 k-steps,
+    // drift < 4e-5) and let the fixed-order double reduction of the partials do the long sum.  Measured cost
+    // of 49 instead of 2 splits at n=1e5: none (tools/probe_x3b.py).
+    S = std::max<int64_t>(S, ceil_div(n_rows, 2048));
+    max_splits = 256;
   }
   const int min_chunks = 8;  // keep the pipeline prologue/epilogue amortised
   S = (int)std::min<int64_t>(S, std::max<int64_t>(1, P.total_chunks / min_chunks));
-  S = std::min(S, 64);
+  // keep the split partials below 2 GiB
+  const int64_t slab = (int64_t)P.ldp * P.ldp * (int64_t)sizeof(float);
+  max_splits = (int)std::max<int64_t>(1, std::min<int64_t>(max_splits, ((int64_t)2 << 30) / slab));
+  S = std::min(S, max_splits);
   if (tc_debug().force_splits > 0) S = tc_debug().force_splits;
   S = std::max(1, std::min(S, P.total_chunks));
   P.chunks_per_split = (int)ceil_div(P.total_chunks, S);
@@ -754,7 +802,7 @@ TcPlan plan_tc(const ColumnLayout& L, int64_t n_rows, bool x3) {
   if (x3) {
     for (int v = 0; v < L.n_views; ++v) {
       int64_t ldo = ceil_div(L.dims[v], 4) * 4;
-      P.split_bytes += 2 * (size_t)n_rows * ldo * sizeof(float);
+      P.split_bytes += 2 * (size_t)n_rows * ldo * sizeof(float);   // lo (and hi for the round-to-nearest split)
     }
   }
   return P;
@@ -808,16 +856,29 @@ int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t*
   CUtensorMap maps[2 * kMaxViews];
   for (int v = 0; v < L.n_views; ++v) {
     const float* x = static_cast<const float*>(views[v]);
-    if (x3) {
+    if (x3 && tc_debug().x3_split == 1) {
       const int64_t ldo = ceil_div(L.dims[v], 4) * 4;
       float* hi = reinterpret_cast<float*>(splitbuf);
       float* lo = hi + (size_t)n_rows * ldo;
       splitbuf += 2 * (size_t)n_rows * ldo * sizeof(float);
       const int64_t total = n_rows * (int64_t)L.dims[v];
       int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
-      split_tf32_kernel<<<blocks, 256, 0, stream>>>(x, n_rows, L.dims[v], lds[v], hi, lo, ldo); count_launches(1);
+      tf32_split_rn_kernel<<<blocks, 256, 0, stream>>>(x, n_rows, L.dims[v], lds[v], hi, lo, ldo); count_launches(1);
       CCAB_CUDA(cudaGetLastError());
       int rc = encode_view_map(&maps[v], hi, n_rows, L.dims[v], ldo, P.kc);
+      if (rc) return rc;
+      rc = encode_view_map(&maps[kMaxViews + v], lo, n_rows, L.dims[v], ldo, P.kc);
+      if (rc) return rc;
+    } else if (x3) {
+      const int64_t ldo = ceil_div(L.dims[v], 4) * 4;
+      float* lo = reinterpret_cast<float*>(splitbuf);
+      splitbuf += (size_t)n_rows * ldo * sizeof(float);
+      const int vec4 = (L.dims[v] % 4 == 0) && (lds[v] % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+      const int64_t total = n_rows * (int64_t)L.dims[v] / (vec4 ? 4 : 1);
+      int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
+      tf32_residual_kernel<<<blocks, 256, 0, stream>>>(x, n_rows, L.dims[v], lds[v], lo, ldo, vec4); count_launches(1);
+      CCAB_CUDA(cudaGetLastError());
+      int rc = encode_view_map(&maps[v], x, n_rows, L.dims[v], lds[v], P.kc);   // "hi" = the raw view (HW truncates)
       if (rc) return rc;
       rc = encode_view_map(&maps[kMaxViews + v], lo, n_rows, L.dims[v], ldo, P.kc);
       if (rc) return rc;

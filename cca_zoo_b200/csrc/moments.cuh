@@ -48,6 +48,7 @@ struct TcDebug {
   int variant;      // 0: CTA-pair kernel (cta_group::2, default), 1: single-CTA kernel
   int kc;           // CTA-pair kernel, 1-pass: rows per stage 16 / 32 (default) / 64
   int dry_run;      // CTA-pair kernel: skip TMA after the first ring fill (MMA-rate experiment; wrong results)
+  int x3_split;     // 3xTF32 operand split: 0 = residual only (raw array is hi by truncation), 1 = round-to-nearest hi/lo
 };
 TcDebug& tc_debug();
 
