@@ -85,26 +85,74 @@ class BaseModel(BaseEstimator, ABC):
             t = t.to(torch.float64)
         return t.to(device, non_blocking=True)
 
-    def _fit_device(self, views, min_views: int = 2):
-        """_setup_fit (cca_zoo/_base.py:78-102) + the covariance stage.  Returns (C, dims, n_total)."""
-        self._validate_params()
-        validated = validate_views(views, min_views)
-        device = self._device()
-        dev_views = [self._to_device(v, device) for v in validated]
-        if len({v.dtype for v in dev_views}) > 1:
-            dev_views = [v.to(torch.float64) for v in dev_views]
-        in_dtype = dev_views[0].dtype
-        dims = [int(v.shape[1]) for v in dev_views]
-        n_local = int(dev_views[0].shape[0])
-        mom = ops.moments(dev_views, precision=self.precision)
+    #: host inputs larger than this many bytes are streamed to the device in row chunks (copy of chunk i+1
+    #: overlaps the moment kernel of chunk i; device memory holds a few chunks instead of the whole data set)
+    _stream_threshold_bytes: ClassVar[int] = 64 << 20
+    _stream_chunk_rows: ClassVar[int] = 16384
+
+    def _local_moments(self, validated, device):
+        """Moment buffer of the rows this process holds.  Returns (moments, n_rows, dims, input dtype)."""
+        host = all(not (isinstance(v, torch.Tensor) and v.is_cuda) for v in validated)
+        n_rows = int(validated[0].shape[0])
+        nbytes = sum(int(np.prod(v.shape)) * (v.element_size() if isinstance(v, torch.Tensor) else v.dtype.itemsize)
+                     for v in validated)
+        if not (host and nbytes >= self._stream_threshold_bytes and n_rows >= 4 * self._stream_chunk_rows):
+            dev_views = [self._to_device(v, device) for v in validated]
+            if len({v.dtype for v in dev_views}) > 1:
+                dev_views = [v.to(torch.float64) for v in dev_views]
+            dims = [int(v.shape[1]) for v in dev_views]
+            return ops.moments(dev_views, precision=self.precision), n_rows, dims, dev_views[0].dtype
+        # ---- streamed: the moments are additive over row chunks (the same identity the multi-GPU path uses) ----
+        cpu_views = []
+        for v in validated:
+            t = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v))
+            if t.dtype not in (torch.float32, torch.float64):
+                t = t.to(torch.float64)
+            cpu_views.append(t)
+        if len({t.dtype for t in cpu_views}) > 1:
+            cpu_views = [t.to(torch.float64) for t in cpu_views]
+        dims = [int(t.shape[1]) for t in cpu_views]
+        main = torch.cuda.current_stream(device)
+        copy = getattr(self, "_copy_stream", None)
+        if copy is None or copy.device != device:
+            copy = torch.cuda.Stream(device)
+            object.__setattr__(self, "_copy_stream", copy)
+        mom = None
+        step = self._stream_chunk_rows
+        pending = None
+        for lo in range(0, n_rows, step):
+            hi = min(lo + step, n_rows)
+            with torch.cuda.stream(copy):
+                chunk = [t[lo:hi].to(device, non_blocking=True) for t in cpu_views]
+                ready = torch.cuda.Event()
+                ready.record(copy)
+            if pending is not None:
+                mom = self._accumulate(mom, pending, main)
+            pending = (chunk, ready)
+        mom = self._accumulate(mom, pending, main)
+        return mom, n_rows, dims, cpu_views[0].dtype
+
+    def _accumulate(self, mom, pending, main):
+        chunk, ready = pending
+        main.wait_event(ready)
+        for c in chunk:
+            c.record_stream(main)
+        part = ops.moments(chunk, precision=self.precision)
+        if mom is None:
+            return part
+        mom.add_(part)
+        return mom
+
+    def _covariance_stage(self, mom, n_local, dims, in_dtype, check_finite):
+        """All-reduce (if sharded), finalise the covariance, record the fitted metadata (_base.py:94-101)."""
         mom, n_total = parallel.allreduce_moments(mom, n_local)
         # NaN / inf anywhere in the inputs poisons the moments: one tiny device-side check replaces the
         # reference's host scan (check_array) for tensors that never visit the host
-        if any(isinstance(v, torch.Tensor) for v in validated) and not bool(torch.isfinite(mom).all()):
+        if check_finite and not bool(torch.isfinite(mom).all()):
             raise ValueError("Input contains NaN or infinity.")
         solve_dtype = torch.float64 if (self._solve_in_float64 or in_dtype == torch.float64) else torch.float32
         C, mean = ops.covariance(mom, dims, n_total, center=bool(self.center), dtype=solve_dtype)
-        self.n_views_ = len(dev_views)
+        self.n_views_ = len(dims)
         self.n_features_in_ = dims
         self.n_samples_ = n_total
         off = np.concatenate([[0], np.cumsum(dims)]).astype(int)
@@ -115,6 +163,42 @@ class BaseModel(BaseEstimator, ABC):
         else:
             self.means_ = [np.zeros(p) for p in dims]
         return C, dims, n_total
+
+    def _fit_device(self, views, min_views: int = 2):
+        """_setup_fit (cca_zoo/_base.py:78-102) + the covariance stage.  Returns (C, dims, n_total)."""
+        self._validate_params()
+        validated = validate_views(views, min_views)
+        device = self._device()
+        mom, n_local, dims, in_dtype = self._local_moments(validated, device)
+        self._partial = None
+        return self._covariance_stage(mom, n_local, dims, in_dtype,
+                                      any(isinstance(v, torch.Tensor) for v in validated))
+
+    def partial_fit(self, views, y=None, solve: bool = True):
+        """Incremental fit on a batch of rows (a capability the reference lacks: its streaming answer is the
+        stochastic EY family).  The block moments are additive over rows, so batches can arrive from disk or a
+        loader in any split; the result after the last batch is the same as one ``fit`` on all rows (up to
+        floating-point summation order).  ``solve=False`` only accumulates (use it for all but the last batch
+        when the intermediate models are not needed)."""
+        self._validate_params()
+        validated = validate_views(views)
+        device = self._device()
+        mom, n_local, dims, in_dtype = self._local_moments(validated, device)
+        state = getattr(self, "_partial", None)
+        if state is not None:
+            if state["dims"] != dims or state["dtype"] != in_dtype:
+                raise ValueError(f"partial_fit batches must keep the view widths/dtype: {state['dims']} vs {dims}")
+            mom = state["mom"].add_(mom)
+            n_local += state["n"]
+        self._partial = {"mom": mom, "n": n_local, "dims": dims, "dtype": in_dtype}
+        if solve:
+            C, dims, n_total = self._covariance_stage(mom.clone(), n_local, dims, in_dtype, True)
+            if type(self)._requires_two_views and len(dims) != 2:
+                raise ValueError(f"rCCA requires exactly 2 views, got {len(dims)}. Use MCCA for more than 2 views.")
+            self._finish(self._solve(C, dims, n_total))
+        return self
+
+    _requires_two_views: ClassVar[bool] = False
 
     def _finish(self, weights: list[torch.Tensor]):
         self.weights_ = [w.cpu().numpy() for w in weights]

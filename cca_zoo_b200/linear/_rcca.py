@@ -37,6 +37,7 @@ class rCCA(BaseModel):
             the latter for large full-rank problems and falls back to ``"eigen"`` otherwise.
     """
 
+    _requires_two_views = True
     _parameter_constraints: ClassVar[dict[str, list[Any]]] = {
         **BaseModel._parameter_constraints,
         "c": RIDGE_PARAMETER,

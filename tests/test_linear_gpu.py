@@ -251,3 +251,34 @@ def test_device_score_path_equals_reference_definition():
         dev = est.pairwise_correlations([torch.from_numpy(v).cuda() for v in vs])
         np.testing.assert_allclose(dev, host, atol=1e-9)
         np.testing.assert_allclose(est.score([torch.from_numpy(v).cuda() for v in vs]), est.score(vs), atol=1e-9)
+
+
+def test_partial_fit_and_streamed_fit_equal_one_shot_fit():
+    """Row batches through partial_fit, and a host data set large enough to take the streamed (chunked H2D)
+    path, give the weights of a single fit on device-resident data."""
+    import torch
+    from cca_zoo_b200.datasets import joint_data
+    from cca_zoo_b200.linear import MCCA, rCCA
+
+    views = joint_data(n_views=2, n_samples=9000, n_features=[64, 48], latent_dimensions=5,
+                       signal_to_noise=0.1, random_state=4)
+    ref = rCCA(latent_dimensions=5, c=0.1).fit([torch.from_numpy(v).cuda() for v in views])
+    inc = rCCA(latent_dimensions=5, c=0.1)
+    for lo, hi, last in [(0, 2500, False), (2500, 2501, False), (2501, 9000, True)]:
+        inc.partial_fit([v[lo:hi] for v in views], solve=last)
+    assert inc.n_samples_ == 9000
+    assert R.max_rel_err_per_vector(inc.weights_, ref.weights_) < 1e-9
+    np.testing.assert_allclose(inc.means_[0], ref.means_[0], rtol=1e-12, atol=1e-13)
+    # another fit() forgets the partial state
+    inc.fit([v[:100] for v in views])
+    assert inc.n_samples_ == 100
+    # streamed host path (threshold lowered so that the test stays small)
+    st = rCCA(latent_dimensions=5, c=0.1)
+    st._stream_threshold_bytes = 1 << 20
+    st._stream_chunk_rows = 1000
+    st.fit(views)
+    assert R.max_rel_err_per_vector(st.weights_, ref.weights_) < 1e-9
+    with pytest.raises(ValueError, match="exactly 2 views"):
+        rCCA().partial_fit([views[0], views[1], views[0]])
+    m = MCCA(latent_dimensions=3).partial_fit([v[:4000] for v in views]).partial_fit([v[4000:] for v in views])
+    np.testing.assert_allclose(m.score(views), MCCA(latent_dimensions=3).fit(views).score(views), rtol=1e-9)
