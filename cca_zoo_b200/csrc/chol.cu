@@ -21,44 +21,50 @@ constexpr int kNB = 64;
 // ---------------------------------------------------------------------------------------------
 // (a) factor one diagonal block (<= 64 x 64) in shared memory; info: first non-positive pivot (1-based)
 // ---------------------------------------------------------------------------------------------
+// Thread i owns row i of the lower triangle in registers (statically indexed: the k and j loops are fully
+// unrolled); per column k: the pivot owner publishes 1/sqrt(piv), every thread scales its entry of column k and
+// publishes it, then updates its own row with broadcast shared-memory reads.  Two 64-thread barriers per column.
 template <typename T>
-__global__ void __launch_bounds__(256) potrf_diag_kernel(T* __restrict__ A, int64_t lda, int nb, int j0,
+__global__ void __launch_bounds__(kNB) potrf_diag_kernel(T* __restrict__ A, int64_t lda, int nb, int j0,
                                                          double piv_tol, int* __restrict__ info) {
-  __shared__ T S[kNB][kNB + 1];
+  __shared__ T col[kNB];
+  __shared__ T dinv_s;
   __shared__ int bad;
-  if (threadIdx.x == 0) bad = 0;
-  for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
-    const int i = e / nb, j = e % nb;
-    S[i][j] = (j <= i) ? A[(size_t)i * lda + j] : T(0);
-  }
+  const int i = threadIdx.x;
+  if (i == 0) bad = 0;
+  T a[kNB];
+#pragma unroll
+  for (int j = 0; j < kNB; ++j) a[j] = (i < nb && j <= i && j < nb) ? A[(size_t)i * lda + j] : T(0);
   __syncthreads();
-  for (int k = 0; k < nb; ++k) {
-    if (threadIdx.x == 0) {
-      const T piv = S[k][k];
-      if (!(piv > (T)piv_tol)) {
-        if (!bad) bad = j0 + k + 1;
-        S[k][k] = T(1);  // keep going with a harmless value; the caller checks info
-      } else {
-        S[k][k] = sqrt(piv);
+#pragma unroll
+  for (int k = 0; k < kNB; ++k) {
+    if (k < nb) {
+      if (i == k) {
+        const T piv = a[k];
+        if (!(piv > (T)piv_tol)) {
+          if (!bad) bad = j0 + k + 1;
+          dinv_s = T(1);       // keep going with a harmless value; the caller checks info
+          a[k] = T(1);
+        } else {
+          const T d = sqrt(piv);
+          dinv_s = T(1) / d;
+          a[k] = d;
+        }
       }
+      __syncthreads();
+      if (i > k) a[k] *= dinv_s;
+      col[i] = (i > k) ? a[k] : T(0);
+      __syncthreads();
+      const T lik = (i > k) ? a[k] : T(0);
+#pragma unroll
+      for (int j = k + 1; j < kNB; ++j) a[j] = fma(-lik, col[j], a[j]);   // entries with j > i stay unused
     }
-    __syncthreads();
-    const T d = S[k][k];
-    for (int i = k + 1 + threadIdx.x; i < nb; i += blockDim.x) S[i][k] /= d;
-    __syncthreads();
-    // trailing update of the lower triangle: (i, j) with k < j <= i
-    const int rem = nb - k - 1;
-    for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
-      const int i = k + 1 + e / rem, j = k + 1 + e % rem;
-      if (j <= i) S[i][j] -= S[i][k] * S[j][k];
-    }
-    __syncthreads();
   }
-  for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
-    const int i = e / nb, j = e % nb;
-    if (j <= i) A[(size_t)i * lda + j] = S[i][j];
-  }
-  if (threadIdx.x == 0 && bad) atomicCAS(info, 0, bad);
+#pragma unroll
+  for (int j = 0; j < kNB; ++j)
+    if (i < nb && j <= i && j < nb) A[(size_t)i * lda + j] = a[j];
+  __syncthreads();
+  if (i == 0 && bad) atomicCAS(info, 0, bad);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -148,7 +154,7 @@ int potrf(int n, T* A, int64_t lda, double piv_tol, int* info_dev, cudaStream_t 
   for (int j0 = 0; j0 < n; j0 += kNB) {
     const int nb = std::min(kNB, n - j0);
     T* Ajj = A + (size_t)j0 * lda + j0;
-    potrf_diag_kernel<T><<<1, 256, 0, stream>>>(Ajj, lda, nb, j0, piv_tol, info_dev);
+    potrf_diag_kernel<T><<<1, kNB, 0, stream>>>(Ajj, lda, nb, j0, piv_tol, info_dev);
     count_launches(1);
     const int rows = n - j0 - nb;
     if (rows > 0) {
