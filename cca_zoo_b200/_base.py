@@ -32,6 +32,17 @@ from . import ops, parallel
 from ._validation import validate_views
 
 
+_COPY_STREAMS: dict = {}
+
+
+def _copy_stream(device):
+    """One side stream per device for host->device staging (kept off the estimator so that it stays picklable)."""
+    key = (device.type, device.index)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device)
+    return _COPY_STREAMS[key]
+
+
 class BaseModel(BaseEstimator, ABC):
     """Abstract base of all estimators (mirrors cca_zoo._base.BaseModel)."""
 
@@ -113,10 +124,7 @@ class BaseModel(BaseEstimator, ABC):
             cpu_views = [t.to(torch.float64) for t in cpu_views]
         dims = [int(t.shape[1]) for t in cpu_views]
         main = torch.cuda.current_stream(device)
-        copy = getattr(self, "_copy_stream", None)
-        if copy is None or copy.device != device:
-            copy = torch.cuda.Stream(device)
-            object.__setattr__(self, "_copy_stream", copy)
+        copy = _copy_stream(device)
         mom = None
         step = self._stream_chunk_rows
         pending = None
@@ -171,8 +179,7 @@ class BaseModel(BaseEstimator, ABC):
         device = self._device()
         mom, n_local, dims, in_dtype = self._local_moments(validated, device)
         self._partial = None
-        return self._covariance_stage(mom, n_local, dims, in_dtype,
-                                      any(isinstance(v, torch.Tensor) for v in validated))
+        return self._covariance_stage(mom, n_local, dims, in_dtype, True)
 
     def partial_fit(self, views, y=None, solve: bool = True):
         """Incremental fit on a batch of rows (a capability the reference lacks: its streaming answer is the
@@ -188,7 +195,7 @@ class BaseModel(BaseEstimator, ABC):
         if state is not None:
             if state["dims"] != dims or state["dtype"] != in_dtype:
                 raise ValueError(f"partial_fit batches must keep the view widths/dtype: {state['dims']} vs {dims}")
-            mom = state["mom"].add_(mom)
+            mom = state["mom"].to(device).add_(mom)
             n_local += state["n"]
         self._partial = {"mom": mom, "n": n_local, "dims": dims, "dtype": in_dtype}
         if solve:
@@ -199,6 +206,16 @@ class BaseModel(BaseEstimator, ABC):
         return self
 
     _requires_two_views: ClassVar[bool] = False
+
+    def __getstate__(self):
+        """Estimators stay picklable like the reference's: fitted state is numpy; an open
+        partial_fit accumulator travels as a host tensor."""
+        state = super().__getstate__()
+        part = state.get("_partial")
+        if part is not None:
+            state = dict(state)
+            state["_partial"] = {**part, "mom": part["mom"].detach().cpu()}
+        return state
 
     def _finish(self, weights: list[torch.Tensor]):
         self.weights_ = [w.cpu().numpy() for w in weights]

@@ -11,6 +11,21 @@ from sklearn.utils.validation import check_array
 _T = TypeVar("_T")
 
 
+#: host arrays above this many elements skip sklearn's finiteness scan (a full extra pass over the data on one
+#: core); BaseModel checks the moment buffer on the device instead -- NaN/inf anywhere poisons it
+_HOST_SCAN_LIMIT = 1 << 22
+
+
+def _check_host_array(v):
+    size = int(np.prod(np.shape(v))) if hasattr(v, "shape") else 0
+    if size <= _HOST_SCAN_LIMIT:
+        return check_array(v, ensure_2d=True, allow_nd=False, dtype="numeric")
+    try:
+        return check_array(v, ensure_2d=True, allow_nd=False, dtype="numeric", ensure_all_finite=False)
+    except TypeError:  # scikit-learn < 1.6 spells it force_all_finite
+        return check_array(v, ensure_2d=True, allow_nd=False, dtype="numeric", force_all_finite=False)
+
+
 def validate_views(views, min_views: int = 2):
     """Return a list of 2-D float arrays / tensors with equal row counts.
 
@@ -33,7 +48,7 @@ def validate_views(views, min_views: int = 2):
             # BaseModel._fit_device): a host-side scan of a large pinned tensor would dominate fit()
             processed.append(v)
         else:
-            processed.append(check_array(v, ensure_2d=True, allow_nd=False, dtype="numeric"))
+            processed.append(_check_host_array(v))
     n = processed[0].shape[0]
     if not all(v.shape[0] == n for v in processed):
         raise ValueError(

@@ -100,3 +100,21 @@ def test_estimator_surface_matches_reference_contract():
     assert perview_parameter("c", None, 0.0, 2) == [0.0, 0.0]
     with pytest.raises(ValueError, match="list of length"):
         perview_parameter("c", [0.1], 0.0, 2)
+
+
+def test_estimators_pickle_roundtrip():
+    """Fitted state is plain numpy (picklable like the reference's sklearn estimators)."""
+    import pickle
+
+    import numpy as np
+
+    from cca_zoo_b200.linear import rCCA
+
+    est = rCCA(latent_dimensions=2, c=0.1)
+    est.weights_ = [np.ones((4, 2)), np.ones((3, 2))]
+    est.means_ = [np.zeros(4), np.zeros(3)]
+    est.n_views_, est.n_features_in_, est.n_samples_ = 2, [4, 3], 10
+    back = pickle.loads(pickle.dumps(est))
+    assert back.get_params() == est.get_params()
+    two = [np.random.default_rng(0).standard_normal((5, 4)), np.random.default_rng(1).standard_normal((5, 3))]
+    np.testing.assert_allclose(back.transform(two)[0], est.transform(two)[0])

@@ -282,3 +282,18 @@ def test_partial_fit_and_streamed_fit_equal_one_shot_fit():
         rCCA().partial_fit([views[0], views[1], views[0]])
     m = MCCA(latent_dimensions=3).partial_fit([v[:4000] for v in views]).partial_fit([v[4000:] for v in views])
     np.testing.assert_allclose(m.score(views), MCCA(latent_dimensions=3).fit(views).score(views), rtol=1e-9)
+
+
+def test_fitted_and_partially_fitted_estimators_pickle():
+    import pickle
+
+    from cca_zoo_b200.linear import rCCA
+
+    views = G.dataset("joint2_med")
+    est = rCCA(latent_dimensions=3, c=0.1).fit(views)
+    back = pickle.loads(pickle.dumps(est))
+    np.testing.assert_array_equal(back.weights_[0], est.weights_[0])
+    np.testing.assert_allclose(back.score(views), est.score(views))
+    half = rCCA(latent_dimensions=3, c=0.1).partial_fit([v[:1500] for v in views], solve=False)
+    resumed = pickle.loads(pickle.dumps(half)).partial_fit([v[1500:] for v in views])
+    assert R.max_rel_err_per_vector(resumed.weights_, est.weights_) < 1e-9
