@@ -28,6 +28,15 @@ sys.path.insert(0, ROOT)
 N_ROWS, DIMS, K, C_RIDGE = 100_000, [1024, 1024], 64, 0.1
 SNR = 2.0 / 1024
 WORKLOAD = "rCCA.fit 2 views n=100000 rows/GPU d=[1024,1024] k=64 c=0.1 float32 (JointData snr=2/1024)"
+MODEL = "rcca"
+
+
+def select_workload(name: str) -> None:
+    """configs[1] (default) or configs[3]: MCCA 4 views d=512 k=32, 125000 rows per GPU (n=1e6 on 8 GPUs)."""
+    global N_ROWS, DIMS, K, C_RIDGE, SNR, WORKLOAD, MODEL
+    if name == "mcca4":
+        N_ROWS, DIMS, K, C_RIDGE, SNR, MODEL = 125_000, [512] * 4, 32, 0.0, 2.0 / 512, "mcca"
+        WORKLOAD = "MCCA.fit 4 views n=125000 rows/GPU d=[512]*4 k=32 c=0 float32 (JointData snr=2/512)"
 
 
 def make_views(seed: int, n_rows: int = N_ROWS):
@@ -227,7 +236,12 @@ def run_ours(args):
 
     host = [torch.from_numpy(v).pin_memory() for v in make_views(1000 + rank)]
     views = [h.to(dev) for h in host]
-    est = rCCA(latent_dimensions=K, c=C_RIDGE, precision=args.precision)
+    if MODEL == "mcca":
+        from cca_zoo_b200.linear import MCCA
+
+        est = MCCA(latent_dimensions=K, c=C_RIDGE, precision=args.precision)
+    else:
+        est = rCCA(latent_dimensions=K, c=C_RIDGE, precision=args.precision)
 
     def barrier():
         if world > 1:
@@ -292,7 +306,7 @@ def run_ours(args):
     peak_src = "MEASURED_PEAKS.json bf16_tflops/2 (TF32 runs at half the dense bf16 rate)" if peaks else \
         "fallback 1590/2 TFLOP/s (B200_PROFILING.md)"
     D = sum(DIMS)
-    flops = N_ROWS * D * (D + 1)  # algorithmic: symmetric product, SURVEY.md §8d
+    flops = N_ROWS * D * (D + 1)  # algorithmic: symmetric product, SURVEY.md §8d (per rank)
     k1 = float(np.mean([m for m in k1_ms if m and m > 0])) if any(m and m > 0 for m in k1_ms) else None
     passes = 3 if args.precision == "tf32x3" else 1
     traffic = None
@@ -312,7 +326,7 @@ def run_ours(args):
                 "share_of_step": k1 / ms_per_step}
 
     line = {
-        "metric": "rcca_fit_per_s", "value": value, "unit": "fit/s", "n_gpus": world, "steps": args.steps,
+        "metric": f"{MODEL}_fit_per_s", "value": value, "unit": "fit/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "tf32x3+f32" if args.precision == "tf32x3" else args.precision + "+f32",
         "data": "synthetic",
@@ -325,7 +339,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "roofline": roof,
     }
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and MODEL == "rcca":
         line["cpu_baseline"] = cpu_baseline()
         line["parity"] = parity_vs_oracle(est, [h.numpy() for h in host])
     print(json.dumps(line), flush=True)
@@ -341,7 +355,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="tf32x3", choices=["tf32", "tf32x3", "exact"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="rcca", choices=["rcca", "mcca4"],
+                    help="rcca = BASELINE configs[1] (the headline); mcca4 = configs[3] shard (scaling study)")
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.impl == "reference":
         run_reference(args)
     else:
