@@ -274,7 +274,7 @@ def rcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c):
     Returns None when a regularised block is not numerically positive definite (the eigen route, which
     reproduces the reference's rank handling, is used instead)."""
     s1, s2 = _slices(dims)
-    Ls, infos = [], []
+    Linv, infos = [], []
     dmax = torch.stack([C[s, s].diagonal().max() for s in (s1, s2)]).cpu()      # one read-back for both views
     with _two_streams(C.device) as streams:
         for i, s in enumerate((s1, s2)):
@@ -283,12 +283,14 @@ def rcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c):
                 R.diagonal().add_(c[i])
                 tol = _rank_tol(dims[i], C.dtype) * ((1.0 - c[i]) * float(dmax[i]) + c[i])
                 infos.append(ops.potrf_(R, pivot_tol=tol))
-                Ls.append(R)
+                # explicit L^-1 (one triangular solve against I): everything downstream -- T and the
+                # back-substitution of the k weight vectors -- becomes plain GEMMs.  R is ridge-regularised
+                # and certified positive definite, so cond(L) = sqrt(cond(R)) is benign.
+                E = torch.eye(dims[i], dtype=C.dtype, device=C.device)
+                Linv.append(ops.trsm_(R, E, side="left"))
     if int(torch.stack(infos).max().item()) != 0:
         return None
-    T = C[s1, s2].contiguous()
-    ops.trsm_(Ls[0], T, side="left")                 # L1^-1 C12
-    ops.trsm_(Ls[1], T, side="right", trans=True)    # ... L2^-T
+    T = ops.gemm(ops.gemm(Linv[0], C[s1, s2]), Linv[1], transb=True)      # L1^-1 C12 L2^-T
     k = min(latent_dimensions, dims[0], dims[1])
     res = topk_svd(T, k) if 4 * k <= min(dims) else None
     if res is None:
@@ -296,13 +298,8 @@ def rcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c):
         Ut, Vt = Ut[:k], Vt[:k]
     else:
         _, Ut, Vt = res
-    w1 = Ut.T.contiguous()
-    w2 = Vt.T.contiguous()
-    with _two_streams(C.device) as streams:
-        with torch.cuda.stream(streams[0]):
-            ops.trsm_(Ls[0], w1, side="left", trans=True)    # L1^-T U_k
-        with torch.cuda.stream(streams[1]):
-            ops.trsm_(Ls[1], w2, side="left", trans=True)
+    w1 = ops.gemm(Linv[0], Ut, transa=True, transb=True)                   # L1^-T U_k   (d1 x k)
+    w2 = ops.gemm(Linv[1], Vt, transa=True, transb=True)
     return [w1, w2]
 
 
