@@ -7,6 +7,8 @@ Algebra: SURVEY.md §3.1-3.3, checked against the reference by oracle/restatemen
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -97,12 +99,16 @@ def topk_svd(T, k, max_rounds=4, iters_per_round=5, oversample=None, seed=1234):
     runs the full Jacobi SVD.  One host read-back per round.
     """
     d1, d2 = T.shape
-    p = min(min(d1, d2), max(2 * k, k + 32) if oversample is None else k + oversample)
+    if oversample is None:
+        oversample = int(os.environ.get("CCAB_TOPK_OVERSAMPLE", "0")) or max(32, k // 2)
+    p = min(min(d1, d2), k + oversample)
     gen = torch.Generator(device=T.device).manual_seed(seed)
+    # a Gaussian start block is well conditioned by itself (cond ~ (sqrt(d)+sqrt(p))/(sqrt(d)-sqrt(p))):
+    # no orthonormalisation needed before the first product
     Z = torch.randn((d2, p), generator=gen, device=T.device, dtype=T.dtype)
     flags = []
-    _cholqr_(Z, flags, passes=2)
     tol = 200.0 * _eps(T.dtype)
+    iters_per_round = int(os.environ.get("CCAB_TOPK_ITERS", "0")) or iters_per_round
     for _ in range(max_rounds):
         for it in range(iters_per_round):
             # one application of T^T T between orthonormalisations: the block's condition number grows by
@@ -122,6 +128,8 @@ def topk_svd(T, k, max_rounds=4, iters_per_round=5, oversample=None, seed=1234):
         E -= ops.scale(Vt, rows=sig[:k])
         stats = torch.stack([ops.frobenius_norm(E)[0], sig[0], torch.stack(flags).max().to(T.dtype).reshape(())])
         resid, s1, bad = (float(x) for x in stats.cpu())    # the round's single host read-back
+        if os.environ.get("CCAB_DEBUG_TOPK"):
+            print(f"[topk_svd] p={p} iters={iters_per_round} resid={resid:.3e} limit={tol * s1 * (k ** 0.5):.3e}")
         if bad != 0.0 or not (s1 > 0.0):
             return None
         if resid <= tol * s1 * (k ** 0.5):
