@@ -119,6 +119,10 @@ class ClockSampler:
         return self
 
     def stop(self):
+        try:  # one sample taken by the caller's thread at the end of the timed region (the Python-side loop
+            self._sample_nvml() if self._nvml else self._sample_smi()   # can starve the sampler thread)
+        except Exception:
+            pass
         self._stop.set()
         self._t.join(timeout=6)
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
