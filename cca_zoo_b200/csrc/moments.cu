@@ -6,8 +6,8 @@
 //     Optional 3xTF32 (raw operand = hi by hardware truncation, materialised residual lo, 3 MMAs per k-step)
 //     for fp32-grade accuracy.
 //     Column sums ride on the same pipeline as one extra N=16 MMA against a block of ones.
-//   * moments_simt_kernel : exact FMA (fp32 or fp64) tile kernel for fp64 inputs and as the
-//     non-tensor reference path.
+//   * moments_simt_kernel : exact FMA (fp32) tile kernel, the non-tensor reference path;
+//     moments_dmma_kernel : float64 inputs on the fp64 tensor pipe (mma.sync m8n8k4.f64).
 //   * reduce / covariance kernels (K2): fixed-order sum of the split partials into a double
 //     moment buffer (the all-reduce payload), then C = (M - s s^T / n) / (n - 1).
 //
@@ -17,6 +17,7 @@
 #include "moments.cuh"
 
 #include <mutex>
+#include <type_traits>
 
 namespace ccab {
 
@@ -66,7 +67,7 @@ float moments_profile_last_ms() {
 }
 
 TcDebug& tc_debug() {
-  static TcDebug d = {-1, -1, -1, 0, 0, 0, 0, 0};
+  static TcDebug d = {-1, -1, -1, 0, 0, 0, 0, 0, 0};
   return d;
 }
 
@@ -637,6 +638,96 @@ __global__ void __launch_bounds__(256) moments_simt_kernel(const SimtParams p) {
 }
 
 // =============================================================================================
+// fp64 tensor-core variant of the exact kernel: mma.sync.aligned.m8n8k4.row.col.f64 (DMMA; tcgen05 has no
+// f64 kind).  Same 64x64 tiles, same partial layout and split planning as moments_simt_kernel<double>.
+// 8 warps; warp w owns the 32 x 16 sub-tile (rows 32*(w&1), cols 16*(w>>1)) = 4 x 2 m8n8 fragments.
+// Shared tiles are [k][64 + 8] doubles: the 16-bank skew between consecutive k rows makes the 64-bit
+// fragment loads conflict-free (two wavefronts, the minimum for 32 lanes x 8 bytes).
+// =============================================================================================
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256) moments_dmma_kernel(const SimtParams p) {
+  constexpr int KC = 16;
+  constexpr int LDS = 64 + 8;
+  __shared__ double As[KC][LDS];
+  __shared__ double Bs[KC][LDS];
+  int t = blockIdx.x, bi = 0, rowlen = p.nb64;
+  while (t >= rowlen) { t -= rowlen; ++bi; --rowlen; }
+  const int bj = bi + t;
+  const int split = blockIdx.y;
+  const int64_t r0 = split * p.rows_per_split;
+  const int64_t r1 = min(r0 + p.rows_per_split, p.n_rows);
+
+  auto locate = [&](int pcol0, int& v, int& c0) {
+    v = 0;
+    while (v + 1 < p.n_views && p.view_poff[v + 1] <= pcol0) ++v;
+    c0 = pcol0 - p.view_poff[v];
+  };
+  int vA, cA, vB, cB;
+  locate(bi * 64, vA, cA);
+  locate(bj * 64, vB, cB);
+  const double* XA = static_cast<const double*>(p.view_ptr[vA]);
+  const double* XB = static_cast<const double*>(p.view_ptr[vB]);
+  const int64_t ldA = p.view_ld[vA], ldB = p.view_ld[vB];
+  const int dA = p.view_dim[vA], dB = p.view_dim[vB];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
+  const int gq = lane >> 2, tq = lane & 3;     // fragment coordinates: row/col group and k index
+  double acc[4][2][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  double csum = 0.0;                            // column sums: thread c < 64 of a diagonal tile sums column c
+
+  const int lc = threadIdx.x & 63, lr = threadIdx.x >> 6;
+  for (int64_t r = r0; r < r1; r += KC) {
+#pragma unroll
+    for (int i = 0; i < KC / 4; ++i) {
+      const int kr = lr + 4 * i;
+      const int64_t row = r + kr;
+      const bool rv = row < r1;
+      As[kr][lc] = (rv && cA + lc < dA) ? XA[row * ldA + cA + lc] : 0.0;
+      Bs[kr][lc] = (rv && cB + lc < dB) ? XB[row * ldB + cB + lc] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k0 = 0; k0 < KC; k0 += 4) {
+      double a[4], b[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k0 + tq][wm + 8 * i + gq];   // A[m][k] = X[k][m]
+#pragma unroll
+      for (int j = 0; j < 2; ++j) b[j] = Bs[k0 + tq][wn + 8 * j + gq];   // B[k][n] = X[k][n]
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    if (bi == bj && threadIdx.x < 64) {
+#pragma unroll
+      for (int k = 0; k < KC; ++k) csum += Bs[k][threadIdx.x];
+    }
+    __syncthreads();
+  }
+  double* P = static_cast<double*>(p.partial) + (size_t)split * p.Dp * p.Dp;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int row = bi * 64 + wm + 8 * i + gq;       // C fragment: row = lane/4, cols = (lane%4)*2 + {0,1}
+      const int col = bj * 64 + wn + 8 * j + 2 * tq;
+      *reinterpret_cast<double2*>(P + (size_t)row * p.Dp + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+  if (bi == bj && threadIdx.x < 64)
+    static_cast<double*>(p.partial_sum)[(size_t)split * p.Dp + bi * 64 + threadIdx.x] = csum;
+}
+
+// =============================================================================================
 // K2: reduce split partials (fixed order => deterministic) and finalise the covariance
 // =============================================================================================
 // valid_blk: partial tiles exist for block-row <= block-col where blocks are `blk` wide.
@@ -1029,7 +1120,11 @@ int moments_simt(const ColumnLayout& L, const void* const* views, const int64_t*
   // partial sums of non-diagonal 64-blocks inside a 128-block are never written by the kernel: the
   // reducer only reads what a tile wrote (block-triangle test at 64 granularity).
   dim3 grid(P.ntiles, P.num_splits);
-  moments_simt_kernel<T><<<grid, 256, 0, stream>>>(prm); count_launches(1);
+  if (std::is_same<T, double>::value && !tc_debug().f64_simt)
+    moments_dmma_kernel<<<grid, 256, 0, stream>>>(prm);
+  else
+    moments_simt_kernel<T><<<grid, 256, 0, stream>>>(prm);
+  count_launches(1);
   CCAB_CUDA(cudaGetLastError());
   const size_t total = (size_t)L.Dp * L.Dp + L.Dp;
   int rblocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);

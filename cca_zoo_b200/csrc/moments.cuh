@@ -49,6 +49,7 @@ struct TcDebug {
   int kc;           // CTA-pair kernel, 1-pass: rows per stage 16 / 32 (default) / 64
   int dry_run;      // CTA-pair kernel: skip TMA after the first ring fill (MMA-rate experiment; wrong results)
   int x3_split;     // 3xTF32 operand split: 0 = residual only (raw array is hi by truncation), 1 = round-to-nearest hi/lo
+  int f64_simt;     // float64 inputs: 0 = DMMA kernel (default), 1 = CUDA-core FMA kernel
 };
 TcDebug& tc_debug();
 
