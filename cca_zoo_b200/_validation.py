@@ -59,14 +59,13 @@ def validate_views(views, min_views: int = 2):
 
 
 def perview_parameter(name: str, value, default, n_views: int):
-    """Broadcast a scalar / per-view list (cca_zoo/_utils/_validation.py:45-75)."""
-    if value is None:
-        return [default] * n_views
+    """One value per view from a scalar, a per-view list or ``None`` (same contract and error text as
+    cca_zoo/_utils/_validation.py:45-75): ``None`` -> the default everywhere, a list must have exactly
+    ``n_views`` entries and is returned as is, anything else is repeated."""
     if isinstance(value, list):
-        if len(value) != n_views:
-            raise ValueError(
-                f"Parameter '{name}' must be a scalar or a list of length "
-                f"{n_views}, got length {len(value)}."
-            )
-        return value
-    return [value] * n_views
+        if len(value) == n_views:
+            return value
+        raise ValueError(
+            f"Parameter '{name}' must be a scalar or a list of length {n_views}, got length {len(value)}."
+        )
+    return [default if value is None else value for _ in range(n_views)]
