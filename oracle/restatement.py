@@ -164,6 +164,107 @@ def ref_gcca_fit(views, latent_dimensions=1, c=0.0, view_weights=None, eps=1e-6,
     return [np.linalg.pinv(v) @ T for v in vs], means
 
 
+def _mcca_core(vs, latent_dimensions, c_, eps):
+    """A, B of cca_zoo/linear/_mcca.py:141-173 (pca=False) from already processed views + gevp."""
+    m = len(vs)
+    A = np.cov(np.hstack(vs), rowvar=False)
+    A = A - scipy.linalg.block_diag(*[np.atleast_2d(np.cov(v, rowvar=False)) for v in vs])
+    A = A / m
+    blocks = [(1.0 - c_[i]) * np.atleast_2d(np.cov(v, rowvar=False)) + c_[i] * np.eye(v.shape[1])
+              for i, v in enumerate(vs)]
+    B = scipy.linalg.block_diag(*blocks)
+    min_eig = np.linalg.eigvalsh(B).min()
+    if min_eig < eps:
+        B = B + (eps - min_eig) * np.eye(B.shape[0])
+    B = B / m
+    _, vecs = ref_gevp(A, B, latent_dimensions)
+    splits = np.cumsum([v.shape[1] for v in vs])
+    return np.split(vecs, splits[:-1], axis=0)
+
+
+def ref_partialcca_fit(views, partials, latent_dimensions=1, c=0.0, eps=1e-6, center=True):
+    """cca_zoo/linear/_partialcca.py:67-103.  Returns (weights, means, confound_betas)."""
+    vs, means = setup_fit(views, center)
+    P = np.asarray(partials, dtype=float)
+    betas = [np.linalg.pinv(P) @ v for v in vs]
+    dec = [v - P @ b for v, b in zip(vs, betas)]
+    c_ = perview(c, 0.0, len(vs))
+    return _mcca_core(dec, latent_dimensions, c_, eps), means, betas
+
+
+def grcca_maps(dims, groups, c_, mu_):
+    """The linear maps T_i (d_i x d_i') behind GRCCA's feature augmentation and weight collapse
+    (cca_zoo/linear/_grcca.py:126-160): processed_i = X_i T_i, weights_i = T_i block_i.
+    T_i = [ (I - P_g)/c | E diag(1/sqrt(mu_eff * counts)) ] with E the feature->group indicator and
+    P_g = E diag(1/counts) E^T; T_i = I when c_i <= 0."""
+    maps = []
+    for d, g, ci, mi in zip(dims, groups, c_, mu_):
+        if ci <= 0:
+            maps.append(np.eye(d))
+            continue
+        ids, inv, counts = np.unique(np.asarray(g), return_inverse=True, return_counts=True)
+        E = np.zeros((d, len(ids)))
+        E[np.arange(d), inv] = 1.0
+        mu_eff = 1.0 if mi == 0 else mi
+        T1 = (np.eye(d) - E @ np.diag(1.0 / counts) @ E.T) / ci
+        T2 = E @ np.diag(1.0 / np.sqrt(mu_eff * counts))
+        maps.append(np.hstack([T1, T2]))
+    return maps
+
+
+def ref_grcca_fit(views, feature_groups, latent_dimensions=1, c=0.0, mu=0.0, eps=1e-6, center=True):
+    """cca_zoo/linear/_grcca.py:76-160 restated through the linear maps of ``grcca_maps`` (the reference
+    builds the same augmented views with per-group means; equality is asserted against the live reference in
+    tests/test_oracle_vs_reference.py)."""
+    vs, means = setup_fit(views, center)
+    m = len(vs)
+    c_ = perview(c, 0.0, m)
+    mu_ = perview(mu, 0.0, m)
+    if feature_groups is None:
+        feature_groups = [np.ones(v.shape[1], dtype=int) for v in vs]
+    maps = grcca_maps([v.shape[1] for v in vs], feature_groups, c_, mu_)
+    processed = [v @ T for v, T in zip(vs, maps)]
+    blocks = _mcca_core(processed, latent_dimensions, c_, eps)
+    return [T @ b for T, b in zip(maps, blocks)], means
+
+
+def cov_partialcca(M, s, n, dims, q, latent_dimensions=1, c=0.0, eps=1e-6, center=True):
+    """Covariance form of PartialCCA from the moments of [X_1 .. X_m, P] (P: the q confound columns, LAST):
+    beta = (P^T P)^+ P^T Xc ; cov(deconfounded) = (Xc^T Xc - G^T beta - t t^T / n)/(n-1) with
+    G = P^T Xc, t = 1^T (Xc - P beta); then the MCCA solve (pca=False)."""
+    D = int(sum(dims))
+    Mxx, Mxp, Mpp = M[:D, :D], M[:D, D:], M[D:, D:]
+    sx, sp = s[:D], s[D:]
+    if center:
+        mu = sx / n
+        XcXc = Mxx - n * np.outer(mu, mu)
+        G = Mxp.T - np.outer(sp, mu)
+        colsum_xc = np.zeros(D)
+    else:
+        XcXc, G, colsum_xc = Mxx, Mxp.T, sx
+    beta = np.linalg.pinv(Mpp) @ G
+    t = colsum_xc - sp @ beta
+    Cd = (XcXc - G.T @ beta - np.outer(t, t) / n) / (n - 1)
+    w, _ = cov_mcca_fit(Cd, dims, latent_dimensions, c, eps)
+    sl = block_slices(dims)
+    return w, [beta[:, sl_i] for sl_i in sl]
+
+
+def cov_grcca(C, dims, feature_groups, latent_dimensions=1, c=0.0, mu=0.0, eps=1e-6):
+    """Covariance form of GRCCA: C' = T^T C T with T = blkdiag(T_i) (no extra pass over the data), MCCA solve
+    on the augmented widths, weights_i = T_i block_i."""
+    m = len(dims)
+    c_ = perview(c, 0.0, m)
+    mu_ = perview(mu, 0.0, m)
+    if feature_groups is None:
+        feature_groups = [np.ones(d, dtype=int) for d in dims]
+    maps = grcca_maps(dims, feature_groups, c_, mu_)
+    T = scipy.linalg.block_diag(*maps)
+    Cp = T.T @ C @ T
+    blocks, _ = cov_mcca_fit(Cp, [Tm.shape[1] for Tm in maps], latent_dimensions, c_, eps)
+    return [Tm @ b for Tm, b in zip(maps, blocks)]
+
+
 def ref_inv_sqrtm(A, eps=1e-5):
     """cca_zoo/deep/objectives.py:9-21."""
     L, V = np.linalg.eigh(A)

@@ -65,3 +65,38 @@ def loss_outputs(name):
         grads.append(_NPZ[f"{name}/grad{i}"])
         i += 1
     return float(_NPZ[f"{name}/loss"]), grads
+
+
+# ---- extension fixtures: estimators that call the MCCA core with extra fit arguments (make_golden_ext.py) ----
+with open(os.path.join(_DIR, "reference_outputs_ext.json")) as _f:
+    META_EXT = json.load(_f)
+_NPZ_EXT = np.load(os.path.join(_DIR, "reference_outputs_ext.npz"))
+PARTIAL_CASES = {c["name"]: c for c in META_EXT["partial_cases"]}
+GROUP_CASES = {c["name"]: c for c in META_EXT["group_cases"]}
+
+
+def ext_inputs(name):
+    """(views, extra): extra = confound matrix (PartialCCA cases) or per-view group labels (GRCCA cases); the same
+    seeded recipes as oracle/make_golden_ext.py."""
+    c = PARTIAL_CASES.get(name) or GROUP_CASES[name]
+    views = dataset(c["dataset"], c["dtype"])
+    rng = np.random.default_rng(c["seed"])
+    if name in PARTIAL_CASES:
+        extra = rng.standard_normal((views[0].shape[0], c["q"])) + np.linspace(0.3, 1.2, c["q"])
+    else:
+        extra = [rng.integers(0, g, size=v.shape[1]) for v, g in zip(views, c["n_groups"])]
+    return views, extra
+
+
+def ext_outputs(name):
+    out, i = {"w": [], "mean": [], "beta": []}, 0
+    while f"{name}/w{i}" in _NPZ_EXT:
+        out["w"].append(_NPZ_EXT[f"{name}/w{i}"])
+        out["mean"].append(_NPZ_EXT[f"{name}/mean{i}"])
+        if f"{name}/beta{i}" in _NPZ_EXT:
+            out["beta"].append(_NPZ_EXT[f"{name}/beta{i}"])
+        i += 1
+    out["score"] = _NPZ_EXT[f"{name}/score"]
+    if f"{name}/partial_corr" in _NPZ_EXT:
+        out["partial_corr"] = _NPZ_EXT[f"{name}/partial_corr"]
+    return out

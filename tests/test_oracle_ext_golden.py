@@ -1,0 +1,75 @@
+"""Oracle restatements of PartialCCA / GRCCA (callers of the MCCA core) against the golden
+vectors made from the reference by oracle/make_golden_ext.py.  Runs everywhere (no GPU, no /root/reference)."""
+import numpy as np
+import pytest
+
+from oracle import restatement as R
+from tests import golden_io as G
+
+
+def _tol(case):
+    # float32 inputs: the reference itself works in float64 after np.cov / pinv, the inputs are exact in both
+    return 1e-6 if case["dtype"] == "f32" else 1e-8
+
+
+@pytest.mark.parametrize("form", ["ref", "cov"])
+@pytest.mark.parametrize("name", sorted(G.PARTIAL_CASES))
+def test_partialcca_oracle_matches_golden(name, form):
+    case = G.PARTIAL_CASES[name]
+    views, Z = G.ext_inputs(name)
+    ref = G.ext_outputs(name)
+    kw = dict(case["kwargs"])
+    k, center, c = kw.pop("latent_dimensions"), kw.pop("center", True), kw.pop("c", 0.0)
+    v64 = [v.astype(np.float64) for v in views]
+    if form == "ref":
+        w, _, betas = R.ref_partialcca_fit(v64, Z, k, c, center=center)
+    else:
+        M, s, n = R.moments(v64 + [Z])
+        w, betas = R.cov_partialcca(M, s, n, [v.shape[1] for v in views], Z.shape[1], k, c, center=center)
+    assert R.max_rel_err_per_vector(w, ref["w"]) < _tol(case)
+    for a, b in zip(betas, ref["beta"]):
+        np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6 if case["dtype"] == "f32" else 1e-10)
+
+
+@pytest.mark.parametrize("form", ["ref", "cov"])
+@pytest.mark.parametrize("name", sorted(G.GROUP_CASES))
+def test_grcca_oracle_matches_golden(name, form):
+    case = G.GROUP_CASES[name]
+    views, groups = G.ext_inputs(name)
+    ref = G.ext_outputs(name)
+    kw = dict(case["kwargs"])
+    k, c, mu = kw.pop("latent_dimensions"), kw.pop("c", 0.0), kw.pop("mu", 0.0)
+    v64 = [v.astype(np.float64) for v in views]
+    if form == "ref":
+        w, means = R.ref_grcca_fit(v64, groups, k, c, mu)
+    else:
+        M, s, n = R.moments(v64)
+        C = R.covariance_from_moments(M, s, n, True)
+        w = R.cov_grcca(C, [v.shape[1] for v in views], groups, k, c, mu)
+        means = [v.mean(axis=0) for v in v64]
+    assert R.max_rel_err_per_vector(w, ref["w"]) < _tol(case)
+    np.testing.assert_allclose(R.score(v64, means, w), ref["score"], rtol=1e-6)
+
+
+def test_grcca_zero_c_is_plain_mcca():
+    """tests/linear/test_eigendecomposition.py:553-558 of the reference, on the oracle."""
+    views, groups = G.ext_inputs("grcca_c0")
+    w, _ = R.ref_grcca_fit(views, groups, 2, 0.0)
+    w_mcca, _ = R.ref_mcca_fit(views, 2, 0.0)
+    assert R.max_rel_err_per_vector(w, w_mcca) < 1e-12
+
+
+def test_partialcca_removes_a_dominant_confound():
+    """tests/linear/test_eigendecomposition.py:493-516 of the reference, on the oracle (same seeded data)."""
+    rng = np.random.default_rng(0)
+    n = 200
+    z = rng.standard_normal((n, 2))
+    confound = rng.standard_normal((n, 1))
+    x1 = z @ rng.standard_normal((2, 6)) + confound @ rng.standard_normal((1, 6)) * 5.0 + 0.1 * rng.standard_normal((n, 6))
+    x2 = z @ rng.standard_normal((2, 6)) + confound @ rng.standard_normal((1, 6)) * 5.0 + 0.1 * rng.standard_normal((n, 6))
+    M, s, nn = R.moments([x1, x2, confound])
+    w, betas = R.cov_partialcca(M, s, nn, [6, 6], 1, 2)
+    mu = [x1.mean(0), x2.mean(0)]
+    z1, z2 = [((x - m) - confound @ b) @ ww for x, m, b, ww in zip([x1, x2], mu, betas, w)]
+    corrs = np.array([abs(np.corrcoef(z1[:, d], z2[:, d])[0, 1]) for d in range(2)])
+    assert np.all(corrs > 0.5)

@@ -78,3 +78,38 @@ def test_conftest_fixture_recipe_matches_reference_file():
         ref = getattr(mod, name).__wrapped__()
         for a, b in zip(conftest_views(name), ref):
             assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("c,center,nv", [(0.0, True, 2), (0.2, True, 3), ([0.1, 0.3], False, 2)])
+def test_partialcca(c, center, nv):
+    from cca_zoo.linear import PartialCCA
+
+    v = conftest_views("three_views")[:nv]
+    Z = np.random.default_rng(7).standard_normal((v[0].shape[0], 3)) + 0.7
+    ref = PartialCCA(latent_dimensions=2, c=c, center=center).fit(v, partials=Z)
+    w, _, betas = R.ref_partialcca_fit(v, Z, 2, c, center=center)
+    assert R.max_rel_err_per_vector(w, ref.weights_) < 1e-12
+    M, s, n = R.moments(v + [Z])
+    w, betas = R.cov_partialcca(M, s, n, [x.shape[1] for x in v], 3, 2, c, center=center)
+    assert R.max_rel_err_per_vector(w, ref.weights_) < 1e-9
+    for a, b in zip(betas, ref.confound_betas_):
+        np.testing.assert_allclose(a, b, atol=1e-12)
+
+
+@pytest.mark.parametrize("c,mu,nv", [(0.0, 0.0, 2), (0.5, 0.0, 2), ([0.3, 0.6, 0.0], [0.5, 2.0, 1.0], 3)])
+def test_grcca(c, mu, nv):
+    import warnings
+
+    from cca_zoo.linear import GRCCA
+
+    v = conftest_views("three_views")[:nv]
+    rng = np.random.default_rng(5)
+    gs = [rng.integers(0, 3, size=x.shape[1]) for x in v]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = GRCCA(latent_dimensions=2, c=c, mu=mu).fit(v, feature_groups=gs)
+    w, _ = R.ref_grcca_fit(v, gs, 2, c, mu)
+    assert R.max_rel_err_per_vector(w, ref.weights_) < 1e-10
+    C, n = _C(v)
+    w = R.cov_grcca(C, [x.shape[1] for x in v], gs, 2, c, mu)
+    assert R.max_rel_err_per_vector(w, ref.weights_) < 1e-9
