@@ -1,4 +1,4 @@
-"""Differentiable CCA objectives on the GPU (mirrors cca_zoo/deep/objectives.py:24-153).
+"""Differentiable CCA objectives on the GPU (mirrors cca_zoo/deep/objectives.py:24-220).
 
 ``CCALoss.forward([z1, z2])`` returns ``-|| S11^-1/2 S12 S22^-1/2 ||_F^2`` with
 ``Sii = cov(zi) + eps I`` and eigenvalues clamped at ``eps`` exactly as the reference
@@ -151,3 +151,85 @@ class MCCALoss(nn.Module):
             for j in range(i + 1, n_views):
                 total = total + self._cca_loss([representations[i], representations[j]])
         return total
+
+
+class _GCCALossFn(torch.autograd.Function):
+    """MAX-VAR GCCA objective in its primal form.
+
+    The reference (objectives.py:196-220) builds the n x n matrix M = sum_i H_i H_i^T, H_i = Zc_i S_i^-1/2, and
+    sums its top-k eigenvalues: O(n^2) memory, O(n^3) work per step.  With H = [H_1 .. H_m] (n x D) the non-zero
+    spectrum of M = H H^T equals that of K = H^T H = (n-1) Wt C Wt^T (D x D), Wt = blkdiag(Wt_i) with
+    Wt_i = diag(clamp(lam_i + eps, min=eps)^-1/2) V_i^T -- all of it a function of the block covariance C that
+    one K1 pass provides.  Backward is analytic (Hellmann-Feynman on the eigenvalue sum, no eigh-backward):
+        Q = Wt^T U_k Lam_k^-1/2,  A = (n-1) C Q,  B = blkdiag(S_i^-1) A,
+        dL/dz_i = center( -2 (Z Q) B_i^T + 2/(n-1) z_i B_i B_i^T ).
+    """
+
+    @staticmethod
+    def forward(ctx, eps, precision, *zs):
+        if not all(z.is_cuda for z in zs):
+            raise RuntimeError("cca_zoo_b200.GCCALoss needs CUDA tensors (sm_100a); there is no CPU fallback.")
+        dt = zs[0].dtype
+        if dt not in (torch.float32, torch.float64) or any(z.dtype != dt for z in zs):
+            raise ValueError("representations must share a float32/float64 dtype")
+        n = zs[0].shape[0]
+        dims = [int(z.shape[1]) for z in zs]
+        D, k = sum(dims), dims[0]
+        zd = [z.detach() for z in zs]
+        mom = ops.moments(zd, precision=precision)
+        C, _ = ops.covariance(mom, dims, n, center=True, dtype=dt)
+        Wt = torch.zeros((D, D), dtype=dt, device=C.device)
+        off = 0
+        for d in dims:
+            lam, Vt = ops.syevj(C[off:off + d, off:off + d].contiguous())
+            Wi, _, _ = ops.whiten_rows(lam, Vt, 0.0, floor_add=eps, rank_tol=-1.0, lam_floor=0.0)
+            Wt[off:off + d, off:off + d] = Wi
+            off += d
+        K = ops.gemm(ops.gemm(Wt, C), Wt, transb=True, alpha=float(n - 1))
+        K = 0.5 * (K + K.T)
+        evals, Ut = ops.syevj(K)                              # descending; rows of Ut are eigenvectors
+        lam_k = evals[:k].contiguous()
+        ctx.n, ctx.dims = n, dims
+        ctx.save_for_backward(C, Wt, lam_k, Ut[:k].contiguous(), *zd)
+        return -lam_k.sum()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        C, Wt, lam_k, Ut_k, *zs = ctx.saved_tensors
+        n, dims = ctx.n, ctx.dims
+        k = lam_k.shape[0]
+        safe = lam_k.clamp_min(torch.finfo(lam_k.dtype).tiny * 1e8)
+        Qt = ops.scale(Ut_k, rows=safe, rows_pow=-0.5)                    # k x D : Lam^-1/2 U_k^T
+        Q = ops.gemm(Wt, Qt, transa=True, transb=True)                    # D x k
+        A = ops.gemm(C, Q, alpha=float(n - 1))                            # D x k
+        B = ops.gemm(Wt, ops.gemm(Wt, A), transa=True)                    # blkdiag(S_i^-1) A
+        Y = torch.zeros((n, k), dtype=C.dtype, device=C.device)
+        off = 0
+        for z, d in zip(zs, dims):
+            ops.gemm(z, Q[off:off + d], beta=1.0, out=Y)
+            off += d
+        go = grad_out.to(C.dtype)
+        grads, off = [], 0
+        for z, d in zip(zs, dims):
+            Bi = B[off:off + d]
+            g = ops.gemm(Y, Bi, transb=True, alpha=-2.0)
+            ops.gemm(z, ops.gemm(Bi, Bi, transb=True), alpha=2.0 / (n - 1), beta=1.0, out=g)
+            ops.center_columns_(g)
+            grads.append(g * go)
+            off += d
+        return (None, None, *grads)
+
+
+class GCCALoss(nn.Module):
+    r"""Generalised (MAX-VAR) CCA loss for two or more views (cca_zoo/deep/objectives.py:156-220):
+    :math:`-\sum_{d \le k} \lambda_d(\sum_i H_i H_i^\top)` with ``k`` the width of the first representation.
+    Same constructor and ``forward(list[Tensor]) -> 0-dim Tensor`` as the reference, so it plugs into
+    ``DCCA(objective=...)`` and is what ``DGCCA`` uses (cca_zoo/deep/_dgcca.py:70).  At most 8 views."""
+
+    def __init__(self, eps: float = 1e-5, precision: str = "exact") -> None:
+        super().__init__()
+        self.eps = eps
+        self.precision = precision
+
+    def forward(self, representations: list[torch.Tensor]) -> torch.Tensor:
+        return _GCCALossFn.apply(float(self.eps), self.precision, *representations)

@@ -24,7 +24,10 @@ refshim.install()
 
 from cca_zoo.linear import GRCCA, PartialCCA  # noqa: E402
 
-from oracle.make_golden import DATASETS, build_dataset  # noqa: E402
+import torch  # noqa: E402
+from cca_zoo.deep.objectives import GCCALoss  # noqa: E402
+
+from oracle.make_golden import DATASETS, build_dataset, loss_inputs  # noqa: E402
 
 
 def confounds(n, q, seed):
@@ -60,8 +63,26 @@ GROUP_CASES = [
 ]
 
 
+GLOSS_CASES = [
+    # (name, batch, widths, eps, seed) -- inputs: make_golden.loss_inputs (shared latent + noise)
+    ("gloss_32x4x3", 32, [4, 4, 4], 1e-4, 10),
+    ("gloss_256x3", 256, [8, 6, 10], 1e-5, 11),
+    ("gloss_12x5x3", 12, [5, 5, 5], 1e-4, 12),          # fewer samples than total width
+    ("gloss_1024x32x4", 1024, [32, 32, 24, 16], 1e-5, 13),
+]
+
+
 def main():
-    out, meta = {}, {"datasets": DATASETS, "partial_cases": [], "group_cases": []}
+    out, meta = {}, {"datasets": DATASETS, "partial_cases": [], "group_cases": [], "gloss_cases": []}
+    for name, batch, widths, eps, seed in GLOSS_CASES:
+        zs = [z.clone().requires_grad_(True) for z in loss_inputs(batch, widths, seed)]
+        loss = GCCALoss(eps=eps)(zs)
+        loss.backward()
+        out[f"{name}/loss"] = np.array(loss.item())
+        for i, z in enumerate(zs):
+            out[f"{name}/grad{i}"] = z.grad.numpy()
+        meta["gloss_cases"].append(dict(name=name, batch=batch, widths=widths, eps=eps, seed=seed))
+        print(name, loss.item())
     for name, kwargs, ds, dt, q, seed in PARTIAL_CASES:
         views = build_dataset(ds)
         if dt == "f32":

@@ -286,6 +286,55 @@ def ref_ccaloss(z1, z2, eps=1e-5):
     return -np.maximum(ev, 0.0).sum()
 
 
+def ref_gccaloss(zs, eps=1e-5):
+    """cca_zoo/deep/objectives.py:196-220 (forward only; forms the n x n matrix like the reference)."""
+    n = zs[0].shape[0]
+    M = np.zeros((n, n))
+    for z in zs:
+        zc = z - z.mean(axis=0)
+        cov = zc.T @ zc / (n - 1) + eps * np.eye(z.shape[1])
+        h = zc @ ref_inv_sqrtm(cov, eps)
+        M += h @ h.T
+    ev = np.linalg.eigvalsh(M)
+    return -ev[-zs[0].shape[1]:].sum()
+
+
+def cov_gccaloss(zs, eps=1e-5):
+    """Primal form the CUDA path implements: with H = [H_1 .. H_m] the n x n matrix is H H^T and its non-zero
+    eigenvalues are those of K = H^T H = (n-1) Wt C Wt^T (D x D, D = sum of widths; Wt_i any matrix with
+    Wt_i^T Wt_i = (C_ii + eps I)^-1).  Returns (loss, grads) with the analytic gradient
+        Q = Wt^T U_k Lam_k^-1/2,  A_i = (n-1) C[i,:] Q,  B_i = S_i^-1 A_i,
+        dL/dz_i = center( -2 (Zc Q) B_i^T + 2/(n-1) Zc_i B_i B_i^T )
+    (Hellmann-Feynman on the top-k eigenvalue sum; valid when lambda_k > lambda_k+1 and the clamp is inactive)."""
+    n = zs[0].shape[0]
+    dims = [z.shape[1] for z in zs]
+    k = dims[0]
+    sl = block_slices(dims)
+    Zc = np.hstack([z - z.mean(axis=0) for z in zs])
+    C = Zc.T @ Zc / (n - 1)
+    D = C.shape[0]
+    Wt = np.zeros((D, D))
+    Sinv = []
+    for s_ in sl:
+        lam, V = np.linalg.eigh(C[s_, s_] + eps * np.eye(s_.stop - s_.start))
+        lam = np.maximum(lam, eps)
+        Wt[s_, s_] = (V / np.sqrt(lam)).T
+        Sinv.append((V / lam) @ V.T)
+    K = (n - 1) * Wt @ C @ Wt.T
+    ev, U = np.linalg.eigh(K)
+    ev, U = ev[::-1][:k], U[:, ::-1][:, :k]
+    loss = -ev.sum()
+    Q = Wt.T @ (U / np.sqrt(ev))
+    Y = Zc @ Q
+    grads = []
+    for i, s_ in enumerate(sl):
+        A = (n - 1) * C[s_, :] @ Q
+        B = Sinv[i] @ A
+        g = -2.0 * Y @ B.T + (2.0 / (n - 1)) * Zc[:, s_] @ (B @ B.T)
+        grads.append(g - g.mean(axis=0))
+    return loss, grads
+
+
 def ref_mccaloss(zs, eps=1e-5):
     """cca_zoo/deep/objectives.py:138-153."""
     tot = 0.0

@@ -49,7 +49,7 @@ def loss_inputs(name):
     """Same recipe as oracle/make_golden.py:loss_inputs (torch CPU generator)."""
     import torch
 
-    c = LOSS_CASES[name]
+    c = LOSS_CASES.get(name) or GLOSS_CASES[name]
     g = torch.Generator().manual_seed(c["seed"])
     zl = torch.randn(c["batch"], 4, generator=g, dtype=torch.float64)
     out = []
@@ -60,11 +60,12 @@ def loss_inputs(name):
 
 
 def loss_outputs(name):
+    npz = _NPZ if name in LOSS_CASES else _NPZ_EXT
     grads, i = [], 0
-    while f"{name}/grad{i}" in _NPZ:
-        grads.append(_NPZ[f"{name}/grad{i}"])
+    while f"{name}/grad{i}" in npz:
+        grads.append(npz[f"{name}/grad{i}"])
         i += 1
-    return float(_NPZ[f"{name}/loss"]), grads
+    return float(npz[f"{name}/loss"]), grads
 
 
 # ---- extension fixtures: estimators that call the MCCA core with extra fit arguments (make_golden_ext.py) ----
@@ -73,6 +74,7 @@ with open(os.path.join(_DIR, "reference_outputs_ext.json")) as _f:
 _NPZ_EXT = np.load(os.path.join(_DIR, "reference_outputs_ext.npz"))
 PARTIAL_CASES = {c["name"]: c for c in META_EXT["partial_cases"]}
 GROUP_CASES = {c["name"]: c for c in META_EXT["group_cases"]}
+GLOSS_CASES = {c["name"]: c for c in META_EXT["gloss_cases"]}
 
 
 def ext_inputs(name):

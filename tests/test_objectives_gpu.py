@@ -83,3 +83,47 @@ def test_loss_rank_deficient_batch_uses_eigen_route_and_matches_reference_forwar
     loss = CCALoss(eps=1e-3)([z1.cuda(), z2.cuda()])
     ref = R.ref_ccaloss(z1.numpy(), z2.numpy(), 1e-3)
     assert abs(loss.item() - ref) < 1e-6 * abs(ref)
+
+
+@pytest.mark.parametrize("name", sorted(G.GLOSS_CASES))
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-5), (torch.float32, 1e-3)])
+def test_gccaloss_and_gradients(name, dtype, tol):
+    """GCCALoss (primal D x D form, analytic backward) against the reference's n x n forward and autograd."""
+    from cca_zoo_b200.deep import GCCALoss
+
+    c = G.GLOSS_CASES[name]
+    loss_ref, grads_ref = G.loss_outputs(name)
+    zs = [z.to(dtype).cuda().requires_grad_(True) for z in G.loss_inputs(name)]
+    loss = GCCALoss(eps=c["eps"])(zs)
+    assert loss.dim() == 0 and loss.dtype == dtype
+    assert abs(loss.item() - loss_ref) < tol * abs(loss_ref)
+    loss.backward()
+    for z, gr in zip(zs, grads_ref):
+        g = z.grad.double().cpu().numpy()
+        denom = np.abs(gr).max()
+        assert np.abs(g - gr).max() < tol * denom, f"grad err {np.abs(g - gr).max() / denom:.2e}"
+
+
+def test_gccaloss_reference_behaviour_and_large_batch():
+    """tests/deep/test_deep.py:252-258 of the reference (scalar for 3 views) + a batch size whose n x n form
+    (the reference's) would need 134 MB and an O(n^3) eigensolve per step; checked against the oracle's primal
+    form in float64."""
+    from cca_zoo_b200.deep import GCCALoss
+    from oracle import restatement as R
+
+    views = [torch.randn(32, 4, device="cuda") for _ in range(3)]
+    loss = GCCALoss(eps=1e-4)(views)
+    assert loss.dim() == 0 and loss.item() < 0
+    g = torch.Generator().manual_seed(5)
+    lat = torch.randn(4096, 6, generator=g, dtype=torch.float64)
+    zs = [lat @ torch.randn(6, w, generator=g, dtype=torch.float64)
+          + 0.7 * torch.randn(4096, w, generator=g, dtype=torch.float64) for w in (48, 64, 40)]
+    L, grads = R.cov_gccaloss([z.numpy() for z in zs], 1e-5)
+    zc = [z.cuda().requires_grad_(True) for z in zs]
+    loss = GCCALoss()(zc)
+    loss.backward()
+    assert abs(loss.item() - L) < 1e-8 * abs(L)
+    for z, gr in zip(zc, grads):
+        assert np.abs(z.grad.cpu().numpy() - gr).max() < 1e-7 * np.abs(gr).max()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GCCALoss()([z.cpu() for z in views])

@@ -73,3 +73,17 @@ def test_partialcca_removes_a_dominant_confound():
     z1, z2 = [((x - m) - confound @ b) @ ww for x, m, b, ww in zip([x1, x2], mu, betas, w)]
     corrs = np.array([abs(np.corrcoef(z1[:, d], z2[:, d])[0, 1]) for d in range(2)])
     assert np.all(corrs > 0.5)
+
+
+@pytest.mark.parametrize("name", sorted(G.GLOSS_CASES))
+def test_gccaloss_oracle_matches_golden(name):
+    """Literal n x n restatement and the primal form (with its analytic gradient) against the reference's
+    forward value and autograd gradients."""
+    c = G.GLOSS_CASES[name]
+    zs = [z.numpy() for z in G.loss_inputs(name)]
+    loss_ref, grads_ref = G.loss_outputs(name)
+    assert abs(R.ref_gccaloss(zs, c["eps"]) - loss_ref) < 1e-10 * abs(loss_ref)
+    L, grads = R.cov_gccaloss(zs, c["eps"])
+    assert abs(L - loss_ref) < 1e-10 * abs(loss_ref)
+    for g, gr in zip(grads, grads_ref):
+        np.testing.assert_allclose(g, gr, rtol=1e-6, atol=1e-9 * np.abs(gr).max())
