@@ -342,6 +342,20 @@ def rcca_weights(C, dims, n_samples, latent_dimensions, c, solver="auto"):
     return [w1, w2]
 
 
+#: above this total width the dense Jacobi route (O(D^3) per sweep on a D x D matrix) is refused instead of being
+#: entered silently when the top-k route declines: at D = 16384 it would run for hours
+_MAX_DENSE_JACOBI = 8192
+
+
+def _refuse_dense(D, what):
+    if D > _MAX_DENSE_JACOBI:
+        raise RuntimeError(
+            f"{what}: the top-k (Cholesky + subspace iteration) route declined on a {D} x {D} problem (a block is "
+            f"not positive definite, an eps floor may be active, 4k > D, or no spectral gap after the block) and "
+            f"the dense Jacobi route is limited to D <= {_MAX_DENSE_JACOBI}.  Regularise (c > 0) or reduce "
+            f"latent_dimensions.")
+
+
 def mcca_weights(C, dims, latent_dimensions, c, eps, solver="auto"):
     """MCCA (cca_zoo/linear/_mcca.py:113-135,141-173): top-k of A v = lam B v, v^T B v = 1 with
     A = (C - blkdiag C_ii)/m, B = blkdiag((1-c_i) C_ii + c_i I)/m (+ eps floor).
@@ -354,6 +368,7 @@ def mcca_weights(C, dims, latent_dimensions, c, eps, solver="auto"):
         w = mcca_weights_cholesky(C, dims, latent_dimensions, c, eps)
         if w is not None:
             return w
+    _refuse_dense(C.shape[0], "MCCA")
     m = len(dims)
     sl = _slices(dims)
     D = C.shape[0]
@@ -388,6 +403,7 @@ def gcca_weights(C, dims, n_samples, latent_dimensions, c, mu, eps, solver="auto
         w = gcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c, mu, eps)
         if w is not None:
             return w
+    _refuse_dense(C.shape[0], "GCCA")
     m = len(dims)
     sl = _slices(dims)
     D = C.shape[0]

@@ -1,5 +1,10 @@
 """Timing of GCCALoss forward+backward (CUDA events) at DGCCA-like sizes."""
+import os
+import sys
+
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cca_zoo_b200.deep import GCCALoss
 
 for n, widths, dt in [(4096, [64, 64, 64], torch.float32), (4096, [64, 64, 64], torch.float64),
