@@ -622,6 +622,26 @@ __global__ void jacobi_gather_kernel(JacobiCtx<T> c, int n, const T* __restrict_
 // ---------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------
+// Pinned landing buffer of the per-sweep convergence flags.  Grow-only and kept for the life of the calling
+// thread: cudaMallocHost / cudaFreeHost cost 0.5-10 ms per call (the free synchronises the device), which used to
+// dominate every small eigensolve.  Portable so that one process driving several devices can share it.
+static unsigned* pinned_stat_buffer(size_t count) {
+  static thread_local unsigned* buf = nullptr;
+  static thread_local size_t cap = 0;
+  if (count > cap) {
+    if (buf) cudaFreeHost(buf);
+    buf = nullptr;
+    cap = 0;
+    const size_t want = std::max<size_t>(count, 1024);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&buf), want * sizeof(unsigned), cudaHostAllocPortable) != cudaSuccess) {
+      buf = nullptr;
+      return nullptr;
+    }
+    cap = want;
+  }
+  return buf;
+}
+
 int& jacobi_inner_sweeps() {
   static int v = 0;
   return v;
@@ -734,8 +754,8 @@ int jacobi_solve(const JacobiArgs<T>& a, void* ws, size_t ws_bytes, cudaStream_t
   const int apply_chunks = (int)(ceil_div(m, 128) + ceil_div(P.n_pad, 128));
   int sweeps_done = 0;
   float last_ratio = -1.f;
-  unsigned* h_stat = nullptr;
-  CCAB_CUDA(cudaMallocHost(&h_stat, sizeof(unsigned) * batch));
+  unsigned* h_stat = pinned_stat_buffer((size_t)batch);
+  CCAB_CHECK_ARG(h_stat != nullptr, "could not allocate the pinned convergence-flag buffer");
   int rc = 0;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     for (int r = 0; r < rounds; ++r) {
@@ -781,7 +801,6 @@ int jacobi_solve(const JacobiArgs<T>& a, void* ws, size_t ws_bytes, cudaStream_t
     if (worst <= (float)tol) break;
     jacobi_reset_stat_kernel<<<1, 1024, 0, stream>>>(c.stat, batch); count_launches(1);
   }
-  cudaFreeHost(h_stat);
   if (rc) return rc;
   if (a.info) { a.info[0] = sweeps_done; }
   if (a.final_offdiag) *a.final_offdiag = last_ratio;
