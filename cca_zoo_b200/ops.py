@@ -70,6 +70,8 @@ def moments(views, precision: str = "tf32x3") -> torch.Tensor:
             raise ValueError("views must share one dtype (float32 or float64)")
         if v.shape[0] != views[0].shape[0]:
             raise ValueError("All views must have the same number of samples.")
+        if v.device != views[0].device:
+            raise ValueError(f"views live on different devices: {v.device} vs {views[0].device}")
     prec = {"tf32": _lib.PREC_TF32, "tf32x3": _lib.PREC_TF32X3, "exact": _lib.PREC_EXACT}[precision]
     if dt == torch.float64:
         prec = _lib.PREC_EXACT
@@ -96,6 +98,14 @@ def covariance(mom: torch.Tensor, dims, n_total: float, center: bool = True, dty
     lib = _lib.load()
     _require_cuda(mom, "moments")
     D = int(sum(dims))
+    expect = lib.ccab_moments_size(len(dims), _lib.i64_array(dims))
+    if expect < 0:
+        raise ValueError(_lib.last_error())
+    if mom.dtype != torch.float64 or mom.numel() != expect or not mom.is_contiguous():
+        raise ValueError(f"moments buffer must be a contiguous float64 tensor of {expect} elements for widths "
+                         f"{list(dims)}, got {mom.dtype} x {mom.numel()}")
+    if not n_total >= 2:
+        raise ValueError(f"at least 2 samples are needed for a covariance, got n = {n_total}")
     Cm = torch.empty((D, D), dtype=dtype, device=mom.device)
     mean = torch.empty(D, dtype=dtype, device=mom.device)
     with torch.cuda.device(mom.device):
@@ -174,9 +184,15 @@ def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, out=None):
     k2, n = (B.shape[1], B.shape[0]) if transb else B.shape
     if k != k2:
         raise ValueError(f"gemm inner dimensions differ: {k} vs {k2}")
+    if A.dtype != B.dtype or A.device != B.device:
+        raise ValueError(f"gemm operands differ in dtype/device: {A.dtype}@{A.device} vs {B.dtype}@{B.device}")
     if out is None:
         out = torch.empty((m, n), dtype=A.dtype, device=A.device)
         beta = 0.0
+    elif (out.dim() != 2 or tuple(out.shape) != (m, n) or out.stride(1) != 1 or out.stride(0) < n
+          or out.dtype != A.dtype or out.device != A.device):
+        raise ValueError(f"gemm `out` must be a row-major ({m}, {n}) {A.dtype} tensor on {A.device}, got "
+                         f"{tuple(out.shape)} strides {out.stride()} {out.dtype} on {out.device}")
     with torch.cuda.device(A.device):
         rc = lib.ccab_gemm(_DT[A.dtype], int(transa), int(transb), m, n, k, float(alpha), _ptr(A), A.stride(0),
                            _ptr(B), B.stride(0), float(beta), _ptr(out), out.stride(0), _stream(A))
