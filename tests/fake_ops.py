@@ -1,0 +1,193 @@
+"""TEST INFRASTRUCTURE ONLY: a torch-CPU stand-in for ``cca_zoo_b200.ops`` (same functions, same contracts, LAPACK /
+torch arithmetic instead of the CUDA kernels) so that the HOST-SIDE logic -- solver routes and their fall-backs,
+the covariance-space algebra of PartialCCA / GRCCA, the sharded fit with its all-reduce -- can be exercised by the
+``-m "not gpu"`` suite.  Nothing in the package imports this module; ``install(monkeypatch)`` swaps it in for one
+test.  The product keeps failing loudly without a CUDA device (tests/test_abi_cpu.py checks that).
+
+Contracts mirrored (see cca_zoo_b200/ops.py and include/ccab200.h): the padded moment buffer ``[Dp*Dp + Dp]`` with
+every view padded to 128-column blocks, eigenvalues descending with eigenvectors as ROWS, ``gesvj`` taking the
+transposed matrix, in-place ``potrf_`` / ``trsm_`` / ``center_columns_`` and their device-side status flags.
+"""
+from __future__ import annotations
+
+import contextlib
+
+import numpy as np
+import torch
+
+BLK = 128
+
+
+def _layout(dims):
+    pads = [(int(d) + BLK - 1) // BLK * BLK for d in dims]
+    poff = np.concatenate([[0], np.cumsum(pads)]).astype(int)
+    return poff, int(poff[-1])
+
+
+def moments(views, precision="tf32x3"):
+    if not (1 <= len(views) <= 8):
+        raise ValueError(f"between 1 and 8 views are supported, got {len(views)}")
+    dims = [int(v.shape[1]) for v in views]
+    poff, Dp = _layout(dims)
+    X = torch.zeros((views[0].shape[0], Dp), dtype=torch.float64)
+    for v, o in zip(views, poff):
+        X[:, o:o + v.shape[1]] = v.to(torch.float64)
+    return torch.cat([(X.T @ X).reshape(-1), X.sum(dim=0)])
+
+
+def covariance(mom, dims, n_total, center=True, dtype=torch.float64):
+    poff, Dp = _layout(dims)
+    if mom.numel() != Dp * Dp + Dp:
+        raise ValueError("moments buffer has the wrong size")
+    if not n_total >= 2:
+        raise ValueError("at least 2 samples are needed for a covariance")
+    M = mom[:Dp * Dp].reshape(Dp, Dp)
+    s = mom[Dp * Dp:]
+    keep = np.concatenate([np.arange(o, o + d) for o, d in zip(poff, dims)])
+    M, s = M[keep][:, keep], s[keep]
+    if center:
+        M = M - torch.outer(s, s) / n_total
+    mean = s / n_total if center else torch.zeros_like(s)
+    return (M / (n_total - 1)).to(dtype).contiguous(), mean.to(dtype)
+
+
+def syevj(A, shift=0.0, return_info=False):
+    squeeze = A.dim() == 2
+    Ab = A.unsqueeze(0) if squeeze else A
+    w, V = torch.linalg.eigh(0.5 * (Ab + Ab.transpose(-1, -2)).to(torch.float64))
+    w, V = w.flip(-1), V.flip(-1)
+    evals, evt = w.to(A.dtype), V.transpose(-1, -2).contiguous().to(A.dtype)
+    if squeeze:
+        evals, evt = evals[0], evt[0]
+    if return_info:
+        return evals, evt, {"sweeps": 0, "offdiag": 0.0}
+    return evals, evt
+
+
+def gesvj(Gt, return_info=False):
+    G = Gt.T.to(torch.float64)                      # m x n
+    m, n = G.shape
+    U, S, Vh = torch.linalg.svd(G, full_matrices=False)
+    r = S.shape[0]
+    sigma = torch.zeros(n, dtype=torch.float64)
+    right = torch.zeros((n, n), dtype=torch.float64)
+    left = torch.zeros((n, m), dtype=torch.float64)
+    sigma[:r], right[:r], left[:r] = S, Vh, U.T
+    out = (sigma.to(Gt.dtype), right.to(Gt.dtype), left.to(Gt.dtype))
+    return out + ({"sweeps": 0, "offdiag": 0.0},) if return_info else out
+
+
+def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, out=None):
+    a = A.T if transa else A
+    b = B.T if transb else B
+    if a.shape[1] != b.shape[0]:
+        raise ValueError(f"gemm inner dimensions differ: {a.shape[1]} vs {b.shape[0]}")
+    res = alpha * (a @ b)
+    if out is None:
+        return res.contiguous()
+    if tuple(out.shape) != tuple(res.shape) or out.stride(1) != 1:
+        raise ValueError("gemm `out` has the wrong layout")
+    out.copy_(res + beta * out if beta != 0.0 else res)
+    return out
+
+
+def whiten_rows(lam, Vt, c, floor_add=0.0, floor_dev=None, scale=1.0, rank_tol=0.0, max_rank=None, lam_floor=-1e300):
+    d = Vt.shape[0]
+    lam64 = lam.to(torch.float64)
+    l0 = max(float(lam64[0]), 0.0)
+    fl = floor_add + (float(floor_dev[0]) if floor_dev is not None else 0.0)
+    keep = (lam64 > rank_tol * l0) & (torch.arange(d) < (d if max_rank is None else max_rank))
+    g = torch.where(keep, 1.0 / torch.sqrt(((1.0 - c) * lam64.clamp_min(lam_floor) + c + fl) * scale),
+                    torch.zeros_like(lam64))
+    Wt = (g[:, None] * Vt.to(torch.float64)).to(Vt.dtype)
+    return Wt, g.to(Vt.dtype), keep.sum().to(torch.int32).reshape(1)
+
+
+def potrf_(A, pivot_tol=0.0):
+    n = A.shape[0]
+    sym = torch.tril(A) + torch.tril(A, -1).T
+    L, info = torch.linalg.cholesky_ex(sym.to(torch.float64))
+    flag = int(info.item())
+    if flag == 0 and pivot_tol > 0.0:
+        small = (L.diagonal() ** 2 <= pivot_tol).nonzero()
+        flag = int(small[0].item()) + 1 if small.numel() else 0
+    if flag == 0:
+        idx = torch.tril_indices(n, n)
+        A[idx[0], idx[1]] = L[idx[0], idx[1]].to(A.dtype)
+    return torch.tensor([flag], dtype=torch.int32)
+
+
+def trsm_(L, B, side="left", trans=False):
+    Lt = torch.tril(L).to(torch.float64)
+    b64 = B.to(torch.float64)
+    if side == "left":
+        if B.shape[0] != L.shape[0]:
+            raise ValueError("shape mismatch")
+        sol = torch.linalg.solve_triangular(Lt.T if trans else Lt, b64, upper=bool(trans))
+    else:
+        if B.shape[1] != L.shape[0] or not trans:
+            raise ValueError("right side supports B <- B L^-T only")
+        sol = torch.linalg.solve_triangular(Lt, b64.T, upper=False).T      # B L^-T = (L^-1 B^T)^T
+    B.copy_(sol.to(B.dtype))
+    return B
+
+
+def scale(A, rows=None, rows_pow=1, cols=None, cols_pow=1, out=None):
+    res = A.clone()
+    if rows is not None:
+        res = res * (rows.to(A.dtype) ** rows_pow)[:, None]
+    if cols is not None:
+        res = res * (cols.to(A.dtype) ** cols_pow)[None, :]
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def center_columns_(A):
+    A.sub_(A.mean(dim=0, keepdim=True))
+    return A
+
+
+def frobenius_norm(A):
+    return torch.linalg.norm(A.to(torch.float64)).to(A.dtype).reshape(1)
+
+
+def ccaloss_small(Cm, d1, d2, eps):
+    C64 = Cm.to(torch.float64)
+    S11 = C64[:d1, :d1] + eps * torch.eye(d1, dtype=torch.float64)
+    S22 = C64[d1:, d1:] + eps * torch.eye(d2, dtype=torch.float64)
+    S12 = C64[:d1, d1:]
+    i11, i22 = torch.linalg.inv(S11), torch.linalg.inv(S22)
+    P = i11 @ S12 @ i22
+    loss = -(S12 * P).sum()                       # -tr(S11^-1 S12 S22^-1 S21)
+    G11 = P @ S12.T @ i11
+    G22 = i22 @ S12.T @ P
+    minp = torch.minimum(torch.linalg.eigvalsh(S11)[0], torch.linalg.eigvalsh(S22)[0])
+    dt = Cm.dtype
+    return loss.reshape(1).to(dt), G11.to(dt), P.to(dt), G22.to(dt), minp.reshape(1).to(dt)
+
+
+def debug_set(key, value):
+    return None
+
+
+@contextlib.contextmanager
+def _no_streams(device):
+    yield [None, None]
+
+
+def install(monkeypatch):
+    """Route the host logic of the package through this module for the duration of one test."""
+    import sys
+
+    import cca_zoo_b200
+    from cca_zoo_b200 import _base, _solvers
+    from cca_zoo_b200.linear import _grcca, _partialcca
+
+    me = sys.modules[__name__]
+    for mod in (_base, _solvers, _partialcca, _grcca):
+        monkeypatch.setattr(mod, "ops", me)
+    monkeypatch.setattr(cca_zoo_b200, "ops", me, raising=False)
+    monkeypatch.setattr(_solvers, "_two_streams", _no_streams)
+    monkeypatch.setattr(_base.BaseModel, "_device", lambda self: torch.device("cpu"))

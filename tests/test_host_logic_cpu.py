@@ -1,0 +1,233 @@
+"""Host-side logic of the estimators on CPU: the whole ``fit`` -- validation, moment pass, all-reduce, covariance
+stage, solver routes and their fall-backs, PartialCCA / GRCCA algebra -- with tests/fake_ops.py (torch CPU, LAPACK)
+standing in for the CUDA kernels.  What this checks is the PYTHON between the kernels, against the same reference
+goldens the GPU tests use; the kernels themselves are checked by the ``-m gpu`` tests.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import restatement as R
+from tests import fake_ops
+from tests import golden_io as G
+
+
+@pytest.fixture
+def host(monkeypatch):
+    fake_ops.install(monkeypatch)
+
+
+def _tol(case):
+    return 2e-3 if case["dtype"] == "f32" and case["model"] in ("CCA", "rCCA", "PLS") else \
+        (1e-5 if case["dtype"] == "f32" else 1e-8)
+
+
+@pytest.mark.parametrize("solver", ["auto", "eigen", "cholesky"])
+@pytest.mark.parametrize("name", sorted(G.CASES))
+def test_estimators_through_host_logic(host, name, solver):
+    from cca_zoo_b200 import linear
+
+    case = G.CASES[name]
+    views = G.case_inputs(name)
+    w_ref, mu_ref, score_ref = G.case_outputs(name)
+    kwargs = dict(case["kwargs"])
+    if case["model"] not in ("CCA", "PLS"):
+        kwargs["solver"] = solver
+    elif solver != "auto":
+        pytest.skip("CCA / PLS take no solver argument")
+    est = getattr(linear, case["model"])(**kwargs).fit(views)
+    err = R.max_rel_err_per_vector([w.astype(np.float64) for w in est.weights_], w_ref)
+    assert err < _tol(case), f"{name}/{solver}: {err:.2e}"
+    np.testing.assert_allclose(est.score(views), score_ref, rtol=max(_tol(case), 1e-7))
+    assert est.n_samples_ == views[0].shape[0] and est.n_features_in_ == [v.shape[1] for v in views]
+
+
+@pytest.mark.parametrize("name", sorted(G.PARTIAL_CASES))
+def test_partialcca_through_host_logic(host, name):
+    from cca_zoo_b200.linear import PartialCCA
+
+    case = G.PARTIAL_CASES[name]
+    views, Z = G.ext_inputs(name)
+    ref = G.ext_outputs(name)
+    est = PartialCCA(**case["kwargs"]).fit(views, partials=Z)
+    tol = 1e-5 if case["dtype"] == "f32" else 1e-8
+    assert R.max_rel_err_per_vector([w.astype(np.float64) for w in est.weights_], ref["w"]) < tol
+    for b, br in zip(est.confound_betas_, ref["beta"]):
+        np.testing.assert_allclose(b, br, rtol=1e-5, atol=1e-6 if case["dtype"] == "f32" else 1e-10)
+    # row batches accumulate to the same model
+    inc = PartialCCA(**case["kwargs"])
+    n = views[0].shape[0]
+    cut = n // 3
+    inc.partial_fit([v[:cut] for v in views], partials=Z[:cut], solve=False)
+    inc.partial_fit([v[cut:] for v in views], partials=Z[cut:])
+    assert R.max_rel_err_per_vector(inc.weights_, est.weights_) < 1e-7
+
+
+@pytest.mark.parametrize("name", sorted(G.GROUP_CASES))
+def test_grcca_through_host_logic(host, name):
+    from cca_zoo_b200.linear import GRCCA
+
+    case = G.GROUP_CASES[name]
+    views, groups = G.ext_inputs(name)
+    ref = G.ext_outputs(name)
+    est = GRCCA(**case["kwargs"]).fit(views, feature_groups=groups)
+    tol = 1e-5 if case["dtype"] == "f32" else 1e-8
+    assert R.max_rel_err_per_vector([w.astype(np.float64) for w in est.weights_], ref["w"]) < tol
+    np.testing.assert_allclose(est.score(views), ref["score"], rtol=1e-6)
+
+
+def _wide_views(n=3000, dims=(300, 280), k=6, seed=3, dtype=np.float64):
+    rng = np.random.default_rng(seed)
+    z = rng.standard_normal((n, k))
+    return [(z @ rng.standard_normal((k, d)) * 0.4 + rng.standard_normal((n, d))).astype(dtype) for d in dims]
+
+
+def test_cholesky_and_eigen_routes_agree_on_wide_views(host):
+    """min(dims) >= 256 and n > max(dims): ``auto`` takes the Cholesky + subspace-iteration route."""
+    from cca_zoo_b200 import _solvers
+    from cca_zoo_b200.linear import MCCA, GCCA, rCCA
+
+    views = _wide_views()
+    w_ref, _ = R.ref_rcca_fit(views, 4, 0.2)
+    calls = {"n": 0}
+    real = _solvers.topk_svd
+
+    def spy(*a, **kw):
+        calls["n"] += 1
+        return real(*a, **kw)
+
+    _solvers.topk_svd, keep = spy, real
+    try:
+        auto = rCCA(latent_dimensions=4, c=0.2).fit(views)
+    finally:
+        _solvers.topk_svd = keep
+    assert calls["n"] == 1, "auto must take the top-k route here"
+    eig = rCCA(latent_dimensions=4, c=0.2, solver="eigen").fit(views)
+    assert R.max_rel_err_per_vector(auto.weights_, w_ref) < 1e-8
+    assert R.max_rel_err_per_vector(eig.weights_, w_ref) < 1e-8
+    three = views + [_wide_views(seed=4)[0][:, :260]]
+    for cls, ref in ((MCCA, R.ref_mcca_fit(three, 3, 0.1)[0]), (GCCA, None)):
+        a = cls(latent_dimensions=3, c=0.1, solver="cholesky").fit(three)
+        e = cls(latent_dimensions=3, c=0.1, solver="eigen").fit(three)
+        assert R.max_rel_err_per_vector(a.weights_, e.weights_) < 1e-7
+        if ref is not None:
+            assert R.max_rel_err_per_vector(a.weights_, ref) < 1e-7
+
+
+def test_cholesky_route_declines_on_a_singular_block_and_the_eigen_route_drops_the_null_directions(host):
+    """Three duplicated columns make a block exactly singular: potrf reports it, the eigen route takes over and
+    drops the numerically null directions (lambda <= d eps lambda_max, the covariance-space image of the
+    reference's ``s > 0`` filter).  The canonical correlations then equal those of the views WITHOUT the
+    duplicates (same column space).  The reference itself keeps singular values of 1e-14 in this corner
+    (``s > 0`` is true for them), which yields weights of 1e13 and correlations that are off by 8e-4 -- the
+    oracle's literal restatement reproduces that artefact, its covariance form does not."""
+    from cca_zoo_b200.linear import rCCA
+
+    views = _wide_views()
+    w_true, mu_true = R.ref_rcca_fit(views, 3, 0.0)
+    truth = R.score(views, mu_true, w_true)
+    dup = [np.hstack([views[0], views[0][:, :3]]), views[1]]
+    for solver in ("cholesky", "eigen"):
+        est = rCCA(latent_dimensions=3, c=0.0, solver=solver).fit(dup)
+        np.testing.assert_allclose(est.score(dup), truth, rtol=1e-7)
+        assert np.abs(est.weights_[0]).max() < 1e3
+    M, s, n = R.moments(dup)
+    w_cov, _ = R.cov_rcca_fit(R.covariance_from_moments(M, s, n), [303, 280], 3, 0.0, n)
+    np.testing.assert_allclose(R.score(dup, [v.mean(axis=0) for v in dup], w_cov), truth, rtol=1e-7)
+
+
+def test_dense_route_is_refused_beyond_its_size_limit(host, monkeypatch):
+    from cca_zoo_b200 import _solvers
+    from cca_zoo_b200.linear import MCCA
+
+    monkeypatch.setattr(_solvers, "_MAX_DENSE_JACOBI", 256)
+    views = _wide_views(n=900, dims=(200, 180))
+    MCCA(latent_dimensions=2, c=0.1, solver="eigen").fit([v[:, :100] for v in views])   # D = 200: allowed
+    with pytest.raises(RuntimeError, match="dense Jacobi route is limited"):
+        MCCA(latent_dimensions=120, c=0.1).fit(views)                                    # 4k > D: top-k declines
+
+
+def test_validation_errors_match_the_reference_messages(host):
+    from sklearn.exceptions import NotFittedError
+    from sklearn.utils._param_validation import InvalidParameterError
+
+    from cca_zoo_b200.linear import MCCA, rCCA
+
+    v = _wide_views(n=50, dims=(6, 5))
+    with pytest.raises(ValueError, match="exactly 2 views"):
+        rCCA().fit(v + [v[0]])
+    with pytest.raises(ValueError, match="same number of samples"):
+        MCCA().fit([v[0], v[1][:-1]])
+    with pytest.raises(ValueError, match="At least 2 views"):
+        MCCA().fit(v[:1])
+    with pytest.raises(InvalidParameterError):
+        rCCA(c=1.5).fit(v)
+    with pytest.raises(InvalidParameterError):
+        MCCA(latent_dimensions=0).fit(v)
+    with pytest.raises(NotFittedError):
+        rCCA().transform(v)
+    bad = [v[0].copy(), v[1]]
+    bad[0][3, 2] = np.nan
+    with pytest.raises(ValueError, match="NaN"):
+        rCCA().fit(bad)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# N > 1: the whole sharded fit (row shards -> moments -> ONE all-reduce -> replicated solve), gloo, world 2
+# ------------------------------------------------------------------------------------------------------------
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _sharded_fit_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mpatch = pytest.MonkeyPatch()
+        fake_ops.install(mpatch)
+        from cca_zoo_b200 import parallel
+        from cca_zoo_b200.linear import MCCA, PartialCCA, rCCA
+
+        views = G.dataset("joint3_med")
+        Z = np.random.default_rng(9).standard_normal((views[0].shape[0], 3)) + 0.4
+        lo, hi = parallel.shard_rows(views[0].shape[0], rank, world)
+        shard = [v[lo:hi] for v in views]
+        out = {}
+        out["rcca"] = rCCA(latent_dimensions=4, c=0.1).fit(shard[:2]).weights_
+        m = MCCA(latent_dimensions=3, c=0.05).fit(shard)
+        out["mcca"], out["mcca_n"] = m.weights_, np.array([m.n_samples_])
+        p = PartialCCA(latent_dimensions=3, c=0.05).fit(shard, partials=Z[lo:hi])
+        out["pcca"], out["pcca_beta"] = p.weights_, p.confound_betas_
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"),
+                 **{f"{k}{i}": a for k, v in out.items() for i, a in enumerate(v)})
+        mpatch.undo()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_fit_world2_equals_single_process_fit(tmp_path, host):
+    world = 2
+    mp.spawn(_sharded_fit_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    for key in r0.files:
+        assert np.array_equal(r0[key], r1[key]), f"{key}: replicated solve must be bit-identical on every rank"
+    views = G.dataset("joint3_med")
+    Z = np.random.default_rng(9).standard_normal((views[0].shape[0], 3)) + 0.4
+    assert int(r0["mcca_n0"]) == views[0].shape[0]
+    w, _ = R.ref_rcca_fit(views[:2], 4, 0.1)
+    assert R.max_rel_err_per_vector([r0["rcca0"], r0["rcca1"]], w) < 1e-8
+    w, _ = R.ref_mcca_fit(views, 3, 0.05)
+    assert R.max_rel_err_per_vector([r0[f"mcca{i}"] for i in range(3)], w) < 1e-8
+    w, _, betas = R.ref_partialcca_fit(views, Z, 3, 0.05)
+    assert R.max_rel_err_per_vector([r0[f"pcca{i}"] for i in range(3)], w) < 1e-8
+    for i, b in enumerate(betas):
+        np.testing.assert_allclose(r0[f"pcca_beta{i}"], b, atol=1e-10)
