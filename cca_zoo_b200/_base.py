@@ -56,6 +56,13 @@ class BaseModel(BaseEstimator, ABC):
     #: dtype of the eigen-stage for float32 inputs: the reference keeps float32 in rCCA
     #: (numpy SVD) but upcasts to float64 in MCCA/GCCA (np.cov), see SURVEY.md §7.3-7.
     _solve_in_float64: ClassVar[bool] = False
+    #: ``center=False`` only skips the mean subtraction of ``_setup_fit`` (cca_zoo/_base.py:96-99).  rCCA then works
+    #: on the raw views (uncentred second moments); MCCA and its subclasses build A and B with ``np.cov``, which
+    #: centres regardless (cca_zoo/linear/_mcca.py:150,166), so their covariance is always the centred one and
+    #: ``center`` only decides ``means_``.
+    _covariance_always_centred: ClassVar[bool] = False
+    #: GCCA with ``center=False`` needs both: np.cov for the regularised blocks, raw products for the rest
+    _wants_second_moment: ClassVar[bool] = False
 
     def __init__(self, latent_dimensions: int = 1, center: bool = True, precision: str = "tf32x3",
                  device=None) -> None:
@@ -159,7 +166,12 @@ class BaseModel(BaseEstimator, ABC):
         if check_finite and not bool(torch.isfinite(mom).all()):
             raise ValueError("Input contains NaN or infinity.")
         solve_dtype = torch.float64 if (self._solve_in_float64 or in_dtype == torch.float64) else torch.float32
-        C, mean = ops.covariance(mom, dims, n_total, center=bool(self.center), dtype=solve_dtype)
+        centred = bool(self.center) or self._covariance_always_centred
+        C, mean = ops.covariance(mom, dims, n_total, center=centred, dtype=solve_dtype)
+        # estimators whose reference mixes np.cov (always centred) with products of the raw views (GCCA, center=False)
+        self._second_moment = None
+        if self._wants_second_moment and not self.center:
+            self._second_moment, _ = ops.covariance(mom, dims, n_total, center=False, dtype=solve_dtype)
         self.n_views_ = len(dims)
         self.n_features_in_ = dims
         self.n_samples_ = n_total

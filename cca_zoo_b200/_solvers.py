@@ -62,6 +62,27 @@ def _rank_tol(d, dtype):
     return d * _eps(dtype)
 
 
+def _regularised_rank_tol(lam, c, d):
+    """Threshold (relative to lambda_max) below which a direction of C_ii is dropped by the eigen route.
+
+    The reference filters on ``s > 0`` (cca_zoo/_utils/_linalg.py:30), which in floating point only removes exact
+    zeros; what makes a direction unusable is a numerically null REGULARISED eigenvalue (1-c) lam + c.  So the test
+    is (1-c) lam + c > tol ((1-c) lam_max + c): for c = 0 the plain relative filter lam > tol lam_max (there the
+    reference itself returns 1e13-sized weights for the null directions), for any practical ridge c > tol lam_max
+    nothing is dropped -- exactly what the reference and the Cholesky route (pivot test on the regularised block) do.
+    Returned in the form the kernel wants: keep iff lam > value * lam_max (-1 keeps everything)."""
+    tol = _rank_tol(d, lam.dtype)
+    if c == 0.0:
+        return tol
+    if c >= 1.0:
+        return -1.0
+    lam_max = max(float(lam[0].item()), 0.0)            # one host read-back; the eigen route is the slow path anyway
+    thr = (tol * ((1.0 - c) * lam_max + c) - c) / (1.0 - c)
+    if thr < 0.0 or lam_max == 0.0:
+        return -1.0
+    return thr / lam_max
+
+
 def _block_eigh(C, dims):
     """Eigendecomposition of every diagonal block C_ii; equal-sized blocks go in one batched call."""
     sl = _slices(dims)
@@ -236,9 +257,11 @@ def mcca_weights_cholesky(C, dims, latent_dimensions, c, eps):
     return [ops.gemm(Linv[i], Yt[:, sl[i]], transa=True, transb=True, alpha=m ** 0.5) for i in range(m)]
 
 
-def gcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c, mu, eps):
+def gcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c, mu, eps, second_moment=None):
     """GCCA primal form with Cholesky whiteners: Wt_i = sqrt(mu_i) L_i^-1, G = (n-1) Wt C Wt^T (PSD), top-k of
-    G by subspace iteration, W_i = C_ii^-1 [C Wt^T U]_i sig^-1/2 (C_ii^-1 from its own Cholesky factor)."""
+    G by subspace iteration, W_i = C_ii^-1 [C Wt^T U]_i sig^-1/2 (C_ii^-1 from its own Cholesky factor).
+    ``second_moment`` (center=False): see ``gcca_weights``."""
+    Cd = C if second_moment is None else second_moment
     m = len(dims)
     sl = _slices(dims)
     D = C.shape[0]
@@ -249,14 +272,14 @@ def gcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c, mu, eps):
     if Wt is None:
         return None
     # factors of the UNregularised blocks for pinv(X_i) = C_ii^-1 X_i^T/(n-1) (full column rank certified)
-    Lc = _cholesky_whiteners(C, dims, [0.0] * m, [1.0] * m, 0.0) if any(ci != 0.0 for ci in c) else \
-        [w / (mu[i] ** 0.5) for i, w in enumerate(Wt)]
+    Lc = _cholesky_whiteners(Cd, dims, [0.0] * m, [1.0] * m, 0.0) if (Cd is not C or any(ci != 0.0 for ci in c)) \
+        else [w / (mu[i] ** 0.5) for i, w in enumerate(Wt)]
     if Lc is None:
         return None
     G = torch.empty((D, D), dtype=C.dtype, device=C.device)
     for i in range(m):
         for j in range(i, m):
-            tmp = ops.gemm(Wt[i], C[sl[i], sl[j]])
+            tmp = ops.gemm(Wt[i], Cd[sl[i], sl[j]])
             ops.gemm(tmp, Wt[j], transb=True, alpha=float(n_samples - 1), out=G[sl[i], sl[j]])
             if j > i:
                 G[sl[j], sl[i]] = G[sl[i], sl[j]].T
@@ -267,7 +290,7 @@ def gcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c, mu, eps):
     P = torch.empty((D, k), dtype=C.dtype, device=C.device)
     for i in range(m):
         ops.gemm(Wt[i], Ut[:, sl[i]], transa=True, transb=True, out=P[sl[i]])
-    CP = ops.gemm(C, P)
+    CP = ops.gemm(Cd, P)
     out = []
     for i in range(m):
         t1 = ops.gemm(Lc[i], CP[sl[i]])                 # Linv CP_i
@@ -326,7 +349,7 @@ def rcca_weights(C, dims, n_samples, latent_dimensions, c, solver="auto"):
     lams, vts = _block_eigh(C, dims)
     wts, ranks = [], []
     for i in range(2):
-        Wt, _, rank = ops.whiten_rows(lams[i], vts[i], c[i], rank_tol=_rank_tol(dims[i], C.dtype),
+        Wt, _, rank = ops.whiten_rows(lams[i], vts[i], c[i], rank_tol=_regularised_rank_tol(lams[i], c[i], dims[i]),
                                       max_rank=min(n_samples, dims[i]))
         wts.append(Wt)
         ranks.append(rank)
@@ -392,22 +415,29 @@ def mcca_weights(C, dims, latent_dimensions, c, eps, solver="auto"):
     return [ops.gemm(wts[i], evt[:k, sl[i]], transa=True, transb=True) for i in range(m)]
 
 
-def gcca_weights(C, dims, n_samples, latent_dimensions, c, mu, eps, solver="auto"):
+def gcca_weights(C, dims, n_samples, latent_dimensions, c, mu, eps, solver="auto", second_moment=None):
     """GCCA in primal (D x D) form (cca_zoo/linear/_gcca.py:94-109).
 
     reg_i = (1-c_i) L_i + c_i (+ per-view eps floor, :102-104) ; Wt_i = diag(sqrt(mu_i) reg_i^-1/2) V_i^T ;
     G = (n-1) Wt C Wt^T (block-wise) ; top-k G u = sig u ;
     W_i = pinv(C_ii) [C Wt^T u]_i sig^-1/2   (pinv from the same eigendecomposition).
+
+    ``second_moment`` = X^T X / (n-1) WITHOUT mean subtraction, given when the estimator was built with
+    ``center=False``: the reference then still regularises with ``np.cov`` (centred, :98-100) but forms
+    ``v R^-1 v^T`` and ``pinv(v)`` from the raw views (:105,109), so G, the projection and the pseudo-inverse use
+    the second moment while the whiteners use the covariance.
     """
     if solver == "cholesky" or (solver == "auto" and C.shape[0] >= 512):
-        w = gcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c, mu, eps)
+        w = gcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c, mu, eps, second_moment)
         if w is not None:
             return w
     _refuse_dense(C.shape[0], "GCCA")
+    Cd = C if second_moment is None else second_moment
     m = len(dims)
     sl = _slices(dims)
     D = C.shape[0]
     lams, vts = _block_eigh(C, dims)
+    lams_d, vts_d = (lams, vts) if Cd is C else _block_eigh(Cd, dims)
     wts = []
     for i in range(m):
         reg_min = float(((1.0 - c[i]) * lams[i][-1] + c[i]).item())
@@ -417,7 +447,7 @@ def gcca_weights(C, dims, n_samples, latent_dimensions, c, mu, eps, solver="auto
     G = torch.empty((D, D), dtype=C.dtype, device=C.device)
     for i in range(m):
         for j in range(i, m):
-            tmp = ops.gemm(wts[i], C[sl[i], sl[j]])
+            tmp = ops.gemm(wts[i], Cd[sl[i], sl[j]])
             ops.gemm(tmp, wts[j], transb=True, alpha=float(n_samples - 1), out=G[sl[i], sl[j]])
             if j > i:
                 G[sl[j], sl[i]] = G[sl[i], sl[j]].T
@@ -427,12 +457,12 @@ def gcca_weights(C, dims, n_samples, latent_dimensions, c, mu, eps, solver="auto
     P = torch.empty((D, k), dtype=C.dtype, device=C.device)
     for i in range(m):
         ops.gemm(wts[i], evt[:k, sl[i]], transa=True, transb=True, out=P[sl[i]])
-    CP = ops.gemm(C, P)                                                   # (D x k)
+    CP = ops.gemm(Cd, P)                                                  # (D x k)
     out = []
     for i in range(m):
         tol = _rank_tol(dims[i], C.dtype)
         # pinv(C_ii) = V diag(1/lam | lam > tol lam_max) V^T  via whiten_rows with c=0 (g = lam^-1/2) twice
-        Pinv_half, _, _ = ops.whiten_rows(lams[i], vts[i], 0.0, rank_tol=tol)   # diag(lam^-1/2) V^T
+        Pinv_half, _, _ = ops.whiten_rows(lams_d[i], vts_d[i], 0.0, rank_tol=tol)   # diag(lam^-1/2) V^T
         t1 = ops.gemm(Pinv_half, CP[sl[i]])                                      # (d x k)
         wi = ops.gemm(Pinv_half, t1, transa=True)                                # V lam^-1 V^T CP_i
         out.append(ops.scale(wi, cols=sig[:k], cols_pow=-0.5))

@@ -22,6 +22,8 @@ class GCCA(BaseModel):
     """
 
     _solve_in_float64 = True
+    _covariance_always_centred = True      # np.cov for the regularised blocks (cca_zoo/linear/_gcca.py:98-100)
+    _wants_second_moment = True            # ... but raw products for Q and pinv when center=False (:105,109)
     _parameter_constraints: ClassVar[dict[str, list[Any]]] = {
         **BaseModel._parameter_constraints,
         "c": RIDGE_PARAMETER,
@@ -45,5 +47,6 @@ class GCCA(BaseModel):
     def _solve(self, C, dims, n_total):
         c_ = perview_parameter("c", self.c, 0.0, self.n_views_)
         mu = perview_parameter("view_weights", self.view_weights, 1.0, self.n_views_)
+        second, self._second_moment = getattr(self, "_second_moment", None), None
         return gcca_weights(C, dims, n_total, self.latent_dimensions, [float(x) for x in c_],
-                            [float(x) for x in mu], float(self.eps), solver=self.solver)
+                            [float(x) for x in mu], float(self.eps), solver=self.solver, second_moment=second)

@@ -13,8 +13,6 @@ moment kernel already produced.
 from __future__ import annotations
 
 import warnings
-from typing import Any, ClassVar
-
 import numpy as np
 import torch
 
@@ -22,7 +20,6 @@ from .. import ops
 from .._solvers import mcca_weights
 from .._validation import perview_parameter
 from ._mcca import MCCA
-from ._rcca import RIDGE_PARAMETER
 
 
 def group_map(n_features: int, groups, c: float, mu: float) -> np.ndarray:
@@ -47,10 +44,7 @@ class GRCCA(MCCA):
     ``c`` is the within-group ridge, ``mu`` the group-mean penalty; ``weights_`` live in the original
     feature space."""
 
-    _parameter_constraints: ClassVar[dict[str, list[Any]]] = {
-        **MCCA._parameter_constraints,
-        "mu": RIDGE_PARAMETER,
-    }
+    # ``mu`` is not constrained in the reference either (it only declares MCCA's constraints)
 
     def __init__(self, latent_dimensions: int = 1, center: bool = True, c=0.0, mu=0.0, eps: float = 1e-6,
                  precision: str = "tf32x3", device=None, solver: str = "auto") -> None:

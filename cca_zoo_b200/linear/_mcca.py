@@ -29,6 +29,7 @@ class MCCA(BaseModel):
     """
 
     _solve_in_float64 = True
+    _covariance_always_centred = True      # np.cov in _build_A / _build_B, PCA in the pca=True branch
     _parameter_constraints: ClassVar[dict[str, list[Any]]] = {
         **BaseModel._parameter_constraints,
         "c": RIDGE_PARAMETER,

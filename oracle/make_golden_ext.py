@@ -22,12 +22,50 @@ from oracle import refshim  # noqa: E402
 
 refshim.install()
 
-from cca_zoo.linear import GRCCA, PartialCCA  # noqa: E402
+from cca_zoo.linear import GCCA, GRCCA, MCCA, PartialCCA, rCCA  # noqa: E402
 
 import torch  # noqa: E402
 from cca_zoo.deep.objectives import GCCALoss  # noqa: E402
 
 from oracle.make_golden import DATASETS, build_dataset, loss_inputs  # noqa: E402
+
+
+# extra input recipes (rebuilt by tests/golden_io.py): a base data set of make_golden.DATASETS, then optionally
+# "shift" (adds a constant, so that centring matters) and "dup" = [view, column] (appends a copy of that column)
+EXT_DATASETS = {
+    "three_views_shifted": ("derived", {"base": "three_views", "shift": 1.5}),
+    "joint4_shifted": ("derived", {"base": "joint4_gcca", "shift": -0.8}),
+    "two_views_dup": ("derived", {"base": "two_views", "dup": [1, 0]}),
+}
+
+
+def build_ext_dataset(name):
+    if name not in EXT_DATASETS:
+        return build_dataset(name)
+    args = EXT_DATASETS[name][1]
+    views = [v.copy() for v in build_dataset(args["base"])]
+    if "shift" in args:
+        views = [v + args["shift"] for v in views]
+    if "dup" in args:
+        j, col = args["dup"]
+        views[j] = np.hstack([views[j], views[j][:, col:col + 1]])
+    return views
+
+
+# estimators whose ``center=False`` semantics differ from "skip the centring everywhere" (np.cov centres inside
+# MCCA / GCCA / GRCCA), and the ridge-regularised fit of a rank-deficient view (nothing is dropped when c > 0)
+CENTER_CASES = [
+    # (name, model, kwargs, dataset, dtype)
+    ("mcca_nocenter", "MCCA", dict(latent_dimensions=2, c=0.1, center=False, pca=False), "three_views_shifted", "f64"),
+    ("mcca_nocenter_pca", "MCCA", dict(latent_dimensions=3, center=False), "three_views_shifted", "f64"),
+    ("gcca_nocenter", "GCCA", dict(latent_dimensions=2, c=0.1, center=False), "three_views_shifted", "f64"),
+    ("gcca_nocenter_w", "GCCA", dict(latent_dimensions=3, center=False, view_weights=[1.0, 2.0, 0.5, 1.0]),
+     "joint4_shifted", "f64"),
+    ("gcca_nocenter32", "GCCA", dict(latent_dimensions=3, c=0.2, center=False), "joint4_shifted", "f32"),
+    ("rcca_nocenter_shifted", "rCCA", dict(latent_dimensions=2, c=0.3, center=False), "two_views_dup", "f64"),
+    ("rcca_dup_ridge", "rCCA", dict(latent_dimensions=9, c=0.2), "two_views_dup", "f64"),
+]
+CENTER_MODELS = {"MCCA": MCCA, "GCCA": GCCA, "rCCA": rCCA}
 
 
 def confounds(n, q, seed):
@@ -60,6 +98,7 @@ GROUP_CASES = [
     ("grcca_c0", dict(latent_dimensions=2, c=0.0), "two_views", "f64", [3, 3], 2),
     ("grcca_med", dict(latent_dimensions=5, c=0.2, mu=0.5), "joint3_med", "f64", [8, 6, 5], 4),
     ("grcca_med32", dict(latent_dimensions=5, c=0.2, mu=0.5), "joint3_med", "f32", [8, 6, 5], 4),
+    ("grcca_nocenter", dict(latent_dimensions=2, c=0.4, mu=2.0, center=False), "three_views_shifted", "f64", [3, 2, 2], 5),
 ]
 
 
@@ -73,7 +112,18 @@ GLOSS_CASES = [
 
 
 def main():
-    out, meta = {}, {"datasets": DATASETS, "partial_cases": [], "group_cases": [], "gloss_cases": []}
+    out, meta = {}, {"datasets": {**DATASETS, **EXT_DATASETS}, "partial_cases": [], "group_cases": [],
+                     "gloss_cases": [], "center_cases": []}
+    for name, model, kwargs, ds, dt in CENTER_CASES:
+        views = build_ext_dataset(ds)
+        if dt == "f32":
+            views = [v.astype(np.float32) for v in views]
+        est = CENTER_MODELS[model](**kwargs).fit(views)
+        for i, (w, mu) in enumerate(zip(est.weights_, est.means_)):
+            out[f"{name}/w{i}"], out[f"{name}/mean{i}"] = np.asarray(w), np.asarray(mu)
+        out[f"{name}/score"] = np.asarray(est.score(views))
+        meta["center_cases"].append(dict(name=name, model=model, kwargs=kwargs, dataset=ds, dtype=dt))
+        print(name, out[f"{name}/score"])
     for name, batch, widths, eps, seed in GLOSS_CASES:
         zs = [z.clone().requires_grad_(True) for z in loss_inputs(batch, widths, seed)]
         loss = GCCALoss(eps=eps)(zs)
@@ -98,7 +148,7 @@ def main():
         meta["partial_cases"].append(dict(name=name, kwargs=kwargs, dataset=ds, dtype=dt, q=q, seed=seed))
         print(name, out[f"{name}/partial_corr"])
     for name, kwargs, ds, dt, ng, seed in GROUP_CASES:
-        views = build_dataset(ds)
+        views = build_ext_dataset(ds)
         if dt == "f32":
             views = [v.astype(np.float32) for v in views]
         gs = groups([v.shape[1] for v in views], ng, seed)

@@ -374,14 +374,16 @@ def block_slices(dims):
 def cov_whiten(Cii, c, n_samples, rank_tol=None):
     """Covariance form of svd_whiten (cca_zoo/_utils/_linalg.py:9-41):
     C = V diag(lam) V^T ; W = V diag(((1-c) lam + c)^-1/2), columns by DEscending lam
-    (the SVD order).  Directions with lam <= tol*lam_max are dropped: they are the
-    covariance-space image of the reference's ``s > 0`` filter (:30)."""
+    (the SVD order).  The reference's ``s > 0`` filter (:30) only removes exact zeros in floating point; what makes
+    a direction unusable is a numerically null REGULARISED eigenvalue, so directions are dropped when
+    (1-c) lam + c <= tol ((1-c) lam_max + c): for c = 0 the plain relative filter (the reference itself returns
+    1e13-sized weights there), for any practical ridge nothing is dropped -- as in the reference."""
     lam, V = np.linalg.eigh(Cii)
     lam, V = lam[::-1], V[:, ::-1]
     d = Cii.shape[0]
     if rank_tol is None:
         rank_tol = max(d, n_samples) * np.finfo(Cii.dtype).eps
-    keep = lam > rank_tol * max(lam[0], 0.0)
+    keep = (1.0 - c) * lam + c > rank_tol * ((1.0 - c) * max(lam[0], 0.0) + c)
     keep[min(d, n_samples):] = False  # thin SVD has at most min(n, d) directions
     lam, V = lam[keep], V[:, keep]
     g = 1.0 / np.sqrt((1.0 - c) * lam + c)
@@ -424,10 +426,15 @@ def cov_mcca_fit(C, dims, latent_dimensions=1, c=0.0, eps=1e-6):
     return [vecs[s, :] for s in sl], lam
 
 
-def cov_gcca_fit(C, dims, n_samples, latent_dimensions=1, c=0.0, view_weights=None, eps=1e-6):
+def cov_gcca_fit(C, dims, n_samples, latent_dimensions=1, c=0.0, view_weights=None, eps=1e-6, second_moment=None):
     """Primal (D x D) restatement of GCCA.fit (cca_zoo/linear/_gcca.py:94-109;
     SURVEY.md §3.3).  R_i = ((1-c_i)C_ii + c_i I (+floor))^-1/2, S = blkdiag(sqrt(mu_i) R_i),
-    G = (n-1) S C S ; top-k G U = U diag(sig) ; W_i = pinv(C_ii) [C S U]_i diag(sig)^-1/2."""
+    G = (n-1) S C S ; top-k G U = U diag(sig) ; W_i = pinv(C_ii) [C S U]_i diag(sig)^-1/2.
+
+    ``second_moment`` = X^T X/(n-1) without mean subtraction, for ``center=False``: the reference then still takes
+    the regularised blocks from np.cov (centred, :98-100) but forms v R^-1 v^T and pinv(v) with the raw views
+    (:105,109), so G, C S U and the pseudo-inverses use the second moment, S uses the covariance C."""
+    Cd = C if second_moment is None else second_moment
     m = len(dims)
     c_ = perview(c, 0.0, m)
     mu = perview(view_weights, 1.0, m)
@@ -436,19 +443,19 @@ def cov_gcca_fit(C, dims, n_samples, latent_dimensions=1, c=0.0, view_weights=No
     S = np.zeros_like(C)
     pinvs = []
     for i, s in enumerate(sl):
-        Cii = C[s, s]
-        lam, V = np.linalg.eigh(Cii)
+        lam, V = np.linalg.eigh(C[s, s])
         reg = (1.0 - c_[i]) * lam + c_[i]
         if reg.min() < eps:
             reg = reg + (eps - reg.min())
         S[s, s] = np.sqrt(mu[i]) * (V / np.sqrt(reg)) @ V.T
+        lam, V = np.linalg.eigh(Cd[s, s])
         tol = max(dims[i], n_samples) * np.finfo(C.dtype).eps * max(lam.max(), 0.0)
         inv = np.where(lam > tol, 1.0 / np.where(lam > tol, lam, 1.0), 0.0)
         pinvs.append((V * inv) @ V.T)
-    G = (n_samples - 1) * (S @ C @ S)
+    G = (n_samples - 1) * (S @ Cd @ S)
     k = min(latent_dimensions, D, n_samples)
     sig, U = ref_gevp(G, None, k)
-    CSU = C @ (S @ U)
+    CSU = Cd @ (S @ U)
     ws = [pinvs[i] @ CSU[s, :] / np.sqrt(sig) for i, s in enumerate(sl)]
     return ws, sig
 

@@ -24,6 +24,10 @@ def pytest_collection_modifyitems(config, items):
     skip_gpu = pytest.mark.skip(reason="no CUDA device")
     skip_ref = pytest.mark.skip(reason="/root/reference not present")
     has_ref = os.path.isdir("/root/reference/cca_zoo")
+    # tools/run_gpu_tests_on_standin.py: the kernels are replaced by tests/fake_ops.py, so the estimator-level gpu
+    # tests can check the host logic on a CPU-only machine
+    if os.environ.get("CCAB_TESTS_ON_STANDIN") == "1":
+        has_gpu = True
     for item in items:
         if "gpu" in item.keywords and not has_gpu:
             item.add_marker(skip_gpu)

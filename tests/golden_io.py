@@ -19,8 +19,16 @@ LOSS_CASES = {c["name"]: c for c in META["loss_cases"]}
 
 
 def dataset(name, dtype="f64"):
-    kind, args = META["datasets"][name]
-    views = conftest_views(args["name"]) if kind == "conftest" else joint_data(**args)
+    kind, args = (META["datasets"].get(name) or META_EXT["datasets"][name])
+    if kind == "derived":     # oracle/make_golden_ext.py: a base data set, shifted and / or with a duplicated column
+        views = [v.copy() for v in dataset(args["base"])]
+        if "shift" in args:
+            views = [v + args["shift"] for v in views]
+        if "dup" in args:
+            j, col = args["dup"]
+            views[j] = np.hstack([views[j], views[j][:, col:col + 1]])
+    else:
+        views = conftest_views(args["name"]) if kind == "conftest" else joint_data(**args)
     if dtype == "f32":
         views = [v.astype(np.float32) for v in views]
     return views
@@ -75,13 +83,16 @@ _NPZ_EXT = np.load(os.path.join(_DIR, "reference_outputs_ext.npz"))
 PARTIAL_CASES = {c["name"]: c for c in META_EXT["partial_cases"]}
 GROUP_CASES = {c["name"]: c for c in META_EXT["group_cases"]}
 GLOSS_CASES = {c["name"]: c for c in META_EXT["gloss_cases"]}
+CENTER_CASES = {c["name"]: c for c in META_EXT["center_cases"]}
 
 
 def ext_inputs(name):
     """(views, extra): extra = confound matrix (PartialCCA cases) or per-view group labels (GRCCA cases); the same
     seeded recipes as oracle/make_golden_ext.py."""
-    c = PARTIAL_CASES.get(name) or GROUP_CASES[name]
+    c = PARTIAL_CASES.get(name) or GROUP_CASES.get(name) or CENTER_CASES[name]
     views = dataset(c["dataset"], c["dtype"])
+    if name in CENTER_CASES:
+        return views, None
     rng = np.random.default_rng(c["seed"])
     if name in PARTIAL_CASES:
         extra = rng.standard_normal((views[0].shape[0], c["q"])) + np.linspace(0.3, 1.2, c["q"])

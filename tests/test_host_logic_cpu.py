@@ -231,3 +231,40 @@ def test_sharded_fit_world2_equals_single_process_fit(tmp_path, host):
     assert R.max_rel_err_per_vector([r0[f"pcca{i}"] for i in range(3)], w) < 1e-8
     for i, b in enumerate(betas):
         np.testing.assert_allclose(r0[f"pcca_beta{i}"], b, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", sorted(G.CENTER_CASES))
+def test_center_false_semantics_through_host_logic(host, name):
+    """np.cov centres inside MCCA / GCCA / GRCCA whatever ``center`` says; GCCA mixes in raw second moments; a
+    ridge keeps the null directions of a rank-deficient view (goldens: oracle/make_golden_ext.py CENTER_CASES)."""
+    from cca_zoo_b200 import linear
+
+    case = G.CENTER_CASES[name]
+    views, _ = G.ext_inputs(name)
+    ref = G.ext_outputs(name)
+    est = getattr(linear, case["model"])(**case["kwargs"]).fit(views)
+    assert [w.shape for w in est.weights_] == [w.shape for w in ref["w"]]
+    kk = 8 if name == "rcca_dup_ridge" else est.weights_[0].shape[1]
+    tol = 1e-5 if case["dtype"] == "f32" else 1e-7
+    assert R.max_rel_err_per_vector([w[:, :kk].astype(np.float64) for w in est.weights_],
+                                    [w[:, :kk] for w in ref["w"]]) < tol
+    np.testing.assert_allclose(est.score(views)[:kk], ref["score"][:kk], rtol=1e-5, atol=1e-8)
+    if not case["kwargs"].get("center", True):
+        assert all(np.all(mu == 0) for mu in est.means_)
+
+
+def test_center_false_routes_agree_on_wide_views(host):
+    from cca_zoo_b200.linear import GCCA, GRCCA, MCCA
+
+    views = [v + 0.7 for v in _wide_views()] + [_wide_views(seed=4)[0][:, :260] - 0.3]
+    w_m, _ = R.ref_mcca_fit(views, 3, 0.1, center=False)
+    w_g, _ = R.ref_gcca_fit(views, 3, 0.1, center=False)
+    groups = [np.random.default_rng(i).integers(0, 9, size=v.shape[1]) for i, v in enumerate(views)]
+    w_r, _ = R.ref_grcca_fit(views, groups, 3, 0.3, 0.5, center=False)
+    for solver in ("cholesky", "eigen"):
+        assert R.max_rel_err_per_vector(MCCA(latent_dimensions=3, c=0.1, center=False, solver=solver)
+                                        .fit(views).weights_, w_m) < 1e-7
+        assert R.max_rel_err_per_vector(GCCA(latent_dimensions=3, c=0.1, center=False, solver=solver)
+                                        .fit(views).weights_, w_g) < 1e-7
+        assert R.max_rel_err_per_vector(GRCCA(latent_dimensions=3, c=0.3, mu=0.5, center=False, solver=solver)
+                                        .fit(views, feature_groups=groups).weights_, w_r) < 1e-7

@@ -87,3 +87,42 @@ def test_gccaloss_oracle_matches_golden(name):
     assert abs(L - loss_ref) < 1e-10 * abs(loss_ref)
     for g, gr in zip(grads, grads_ref):
         np.testing.assert_allclose(g, gr, rtol=1e-6, atol=1e-9 * np.abs(gr).max())
+
+
+def _center_case_weights(case, views, form):
+    """center=False semantics per estimator (see oracle/make_golden_ext.py: CENTER_CASES)."""
+    kw = dict(case["kwargs"])
+    k, center, c = kw.pop("latent_dimensions"), kw.pop("center", True), kw.pop("c", 0.0)
+    model = case["model"]
+    v64 = [v.astype(np.float64) for v in views]
+    dims = [v.shape[1] for v in views]
+    if form == "ref":
+        if model == "rCCA":
+            return R.ref_rcca_fit(v64, k, c, center=center)[0]
+        if model == "MCCA":
+            return R.ref_mcca_fit(v64, k, c, kw.get("eps", 1e-6), center=center)[0]
+        return R.ref_gcca_fit(v64, k, c, kw.get("view_weights"), kw.get("eps", 1e-6), center=center)[0]
+    M, s, n = R.moments(v64)
+    C = R.covariance_from_moments(M, s, n, True)
+    Cu = R.covariance_from_moments(M, s, n, False)
+    if model == "rCCA":      # tall SVD of the views as they are: second moments when center=False
+        return R.cov_rcca_fit(C if center else Cu, dims, k, c, n)[0]
+    if model == "MCCA":      # np.cov centres whatever `center` says
+        return R.cov_mcca_fit(C, dims, k, c, kw.get("eps", 1e-6))[0]
+    return R.cov_gcca_fit(C, dims, n, k, c, kw.get("view_weights"), kw.get("eps", 1e-6),
+                          second_moment=None if center else Cu)[0]
+
+
+@pytest.mark.parametrize("form", ["ref", "cov"])
+@pytest.mark.parametrize("name", sorted(G.CENTER_CASES))
+def test_center_false_and_ridge_rank_deficiency_oracle_matches_golden(name, form):
+    case = G.CENTER_CASES[name]
+    views, _ = G.ext_inputs(name)
+    ref = G.ext_outputs(name)
+    w = _center_case_weights(case, views, form)
+    assert [x.shape for x in w] == [x.shape for x in ref["w"]]
+    # rcca_dup_ridge: the 9th singular value of the whitened cross-covariance is exactly zero and its left vector is
+    # arbitrary in a 2-dimensional null space -- compare the 8 determined directions
+    kk = 8 if name == "rcca_dup_ridge" else w[0].shape[1]
+    tol = 1e-5 if case["dtype"] == "f32" else 1e-7
+    assert R.max_rel_err_per_vector([x[:, :kk] for x in w], [x[:, :kk] for x in ref["w"]]) < tol
