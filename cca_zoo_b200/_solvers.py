@@ -257,6 +257,17 @@ def mcca_weights_cholesky(C, dims, latent_dimensions, c, eps):
     return [ops.gemm(Linv[i], Yt[:, sl[i]], transa=True, transb=True, alpha=m ** 0.5) for i in range(m)]
 
 
+def _pad_null_components(weights, k_out):
+    """The reference takes eigenvectors of the n x n matrix, so it returns min(k, n) components even when that
+    exceeds the total width D (cca_zoo/_utils/_linalg.py:65); the extra eigenvectors belong to the zero eigenvalue,
+    are orthogonal to every view's column space, and pinv(X_i) maps them to zero weights.  Same shape, exact zeros."""
+    k = weights[0].shape[1]
+    if k_out <= k:
+        return weights
+    return [torch.cat([w, torch.zeros((w.shape[0], k_out - k), dtype=w.dtype, device=w.device)], dim=1)
+            for w in weights]
+
+
 def gcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c, mu, eps, second_moment=None):
     """GCCA primal form with Cholesky whiteners: Wt_i = sqrt(mu_i) L_i^-1, G = (n-1) Wt C Wt^T (PSD), top-k of
     G by subspace iteration, W_i = C_ii^-1 [C Wt^T U]_i sig^-1/2 (C_ii^-1 from its own Cholesky factor).
@@ -296,7 +307,7 @@ def gcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c, mu, eps, sec
         t1 = ops.gemm(Lc[i], CP[sl[i]])                 # Linv CP_i
         wi = ops.gemm(Lc[i], t1, transa=True)           # Linv^T Linv CP_i = C_ii^-1 CP_i
         out.append(ops.scale(wi, cols=sig, cols_pow=-0.5))
-    return out
+    return _pad_null_components(out, min(latent_dimensions, n_samples))
 
 
 def rcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c):
@@ -466,4 +477,4 @@ def gcca_weights(C, dims, n_samples, latent_dimensions, c, mu, eps, solver="auto
         t1 = ops.gemm(Pinv_half, CP[sl[i]])                                      # (d x k)
         wi = ops.gemm(Pinv_half, t1, transa=True)                                # V lam^-1 V^T CP_i
         out.append(ops.scale(wi, cols=sig[:k], cols_pow=-0.5))
-    return out
+    return _pad_null_components(out, min(latent_dimensions, n_samples))
