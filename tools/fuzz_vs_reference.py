@@ -95,6 +95,12 @@ def main():
             bad += 1
             print("WEIGHT SHAPES", desc, [w.shape for w in r[0].weights_], [w.shape for w in o[0].weights_])
             continue
+        dt_r = [w.dtype for w in r[0].weights_] + [np.asarray(t).dtype for t in r[2]]
+        dt_o = [w.dtype for w in o[0].weights_] + [np.asarray(t).dtype for t in o[2]]
+        if dt_r != dt_o:
+            bad += 1
+            print("DTYPES", desc, dt_r, dt_o)
+            continue
         tol = 2e-3 if f32 else 1e-6
         kmax = min(min(dims), max(n - 2 - q, 0))
         d_score = float(np.max(np.abs(r[1] - o[1])[np.arange(r[1].shape[0]) < max(kmax, 1)])) if True else 0.0
