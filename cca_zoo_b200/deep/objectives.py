@@ -23,6 +23,11 @@ import torch.nn as nn
 from .. import ops
 
 
+def _require_cuda(name, *tensors):
+    if not all(t.is_cuda for t in tensors):
+        raise RuntimeError(f"cca_zoo_b200.{name} needs CUDA tensors (sm_100a); there is no CPU fallback.")
+
+
 def _whiteners_cholesky(C, d1, eps):
     """Cholesky route: S_ii = C_ii + eps I = L_i L_i^T, returns (L_1, L_2) or None.
 
@@ -43,10 +48,7 @@ def _whiteners_cholesky(C, d1, eps):
 class _CCALossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z1, z2, eps, precision):
-        if not (z1.is_cuda and z2.is_cuda):
-            raise RuntimeError(
-                "cca_zoo_b200.CCALoss needs CUDA tensors (sm_100a); there is no CPU fallback."
-            )
+        _require_cuda("CCALoss", z1, z2)
         if z1.dtype != z2.dtype or z1.dtype not in (torch.float32, torch.float64):
             raise ValueError("representations must share a float32/float64 dtype")
         n = z1.shape[0]
@@ -167,8 +169,7 @@ class _GCCALossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, eps, precision, *zs):
-        if not all(z.is_cuda for z in zs):
-            raise RuntimeError("cca_zoo_b200.GCCALoss needs CUDA tensors (sm_100a); there is no CPU fallback.")
+        _require_cuda("GCCALoss", *zs)
         dt = zs[0].dtype
         if dt not in (torch.float32, torch.float64) or any(z.dtype != dt for z in zs):
             raise ValueError("representations must share a float32/float64 dtype")

@@ -185,9 +185,12 @@ def install(monkeypatch):
     from cca_zoo_b200 import _base, _solvers
     from cca_zoo_b200.linear import _grcca, _partialcca
 
+    from cca_zoo_b200.deep import objectives
+
     me = sys.modules[__name__]
-    for mod in (_base, _solvers, _partialcca, _grcca):
+    for mod in (_base, _solvers, _partialcca, _grcca, objectives):
         monkeypatch.setattr(mod, "ops", me)
+    monkeypatch.setattr(objectives, "_require_cuda", lambda name, *tensors: None)
     monkeypatch.setattr(cca_zoo_b200, "ops", me, raising=False)
     monkeypatch.setattr(_solvers, "_two_streams", _no_streams)
     monkeypatch.setattr(_base.BaseModel, "_device", lambda self: torch.device("cpu"))

@@ -17,3 +17,10 @@ def test_fixed_seed_fuzz_has_no_mismatch():
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert "0 mismatches" in out.stdout
+
+
+def test_fixed_seed_loss_fuzz_has_no_mismatch():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_loss_vs_reference.py"), "20240924", "200"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "0 mismatches" in out.stdout

@@ -268,3 +268,29 @@ def test_center_false_routes_agree_on_wide_views(host):
                                         .fit(views).weights_, w_g) < 1e-7
         assert R.max_rel_err_per_vector(GRCCA(latent_dimensions=3, c=0.3, mu=0.5, center=False, solver=solver)
                                         .fit(views, feature_groups=groups).weights_, w_r) < 1e-7
+
+
+@pytest.mark.parametrize("name", sorted(G.LOSS_CASES) + sorted(G.GLOSS_CASES))
+def test_objectives_through_host_logic(host, name):
+    """Route selection and the analytic backward of CCALoss / MCCALoss / GCCALoss against the reference's forward
+    value and autograd gradients (goldens), with the stand-in kernels."""
+    from cca_zoo_b200.deep import CCALoss, GCCALoss, MCCALoss
+
+    c = G.LOSS_CASES.get(name) or G.GLOSS_CASES[name]
+    loss_ref, grads_ref = G.loss_outputs(name)
+    zs = [z.clone().requires_grad_(True) for z in G.loss_inputs(name)]
+    fn = {"cca": CCALoss, "mcca": MCCALoss}.get(c.get("kind"), GCCALoss)(eps=c["eps"])
+    loss = fn(zs)
+    assert loss.dim() == 0 and abs(loss.item() - loss_ref) < 1e-9 * abs(loss_ref)
+    loss.backward()
+    for z, gr in zip(zs, grads_ref):
+        assert np.abs(z.grad.numpy() - gr).max() < 1e-7 * np.abs(gr).max()
+
+
+def test_objectives_reject_cpu_tensors_without_the_standin():
+    from cca_zoo_b200.deep import CCALoss, GCCALoss
+
+    z = [torch.randn(8, 3), torch.randn(8, 3)]
+    for fn in (CCALoss(), GCCALoss()):
+        with pytest.raises(RuntimeError, match="CUDA"):
+            fn(z)
