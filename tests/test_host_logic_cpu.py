@@ -294,3 +294,43 @@ def test_objectives_reject_cpu_tensors_without_the_standin():
     for fn in (CCALoss(), GCCALoss()):
         with pytest.raises(RuntimeError, match="CUDA"):
             fn(z)
+
+
+def test_device_score_path_equals_the_reference_definition(host, monkeypatch):
+    """pairwise correlations from ONE moment pass (W_i^T C_ij W_j normalised) == Pearson correlations of the
+    transformed samples (cca_zoo/_base.py:153-174), on held-out rows, for 2 and 3 views."""
+    from cca_zoo_b200._base import BaseModel
+    from cca_zoo_b200.linear import MCCA, rCCA
+
+    views = G.dataset("joint3_med")
+    train = [v[:1500] for v in views]
+    held = [v[1500:] for v in views]
+    for est in (rCCA(latent_dimensions=4, c=0.1).fit(train[:2]), MCCA(latent_dimensions=3, c=0.05).fit(train)):
+        hv = held[: est.n_views_]
+        host_path = est.pairwise_correlations(hv)
+        monkeypatch.setattr(BaseModel, "_device_score_threshold", 0)
+        monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+        dev_path = est.pairwise_correlations(hv)
+        monkeypatch.undo()
+        fake_ops.install(monkeypatch)
+        np.testing.assert_allclose(dev_path, host_path, atol=1e-10)
+        np.testing.assert_allclose(dev_path, R.pairwise_correlations(R.transform(hv, est.means_, est.weights_)),
+                                   atol=1e-10)
+
+
+def test_partial_fit_batches_and_torch_inputs_equal_one_fit(host):
+    from cca_zoo_b200.linear import GCCA, MCCA, rCCA
+
+    views = G.dataset("joint3_med")
+    for cls, kw, nv in ((rCCA, dict(c=0.1), 2), (MCCA, dict(c=0.05), 3), (GCCA, dict(c=0.1), 3)):
+        one = cls(latent_dimensions=3, **kw).fit(views[:nv])
+        inc = cls(latent_dimensions=3, **kw)
+        cuts = [0, 700, 1500, 2500]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            inc.partial_fit([v[a:b] for v in views[:nv]], solve=b == cuts[-1])
+        assert R.max_rel_err_per_vector(inc.weights_, one.weights_) < 1e-9
+        assert inc.n_samples_ == 2500
+        tt = cls(latent_dimensions=3, **kw).fit([torch.from_numpy(v) for v in views[:nv]])
+        assert R.max_rel_err_per_vector(tt.weights_, one.weights_) < 1e-12
+        with pytest.raises(ValueError, match="keep the view widths"):
+            inc.partial_fit([v[:10, :5] for v in views[:nv]])
