@@ -13,6 +13,7 @@ moment kernel already produced.
 from __future__ import annotations
 
 import warnings
+
 import numpy as np
 import torch
 
