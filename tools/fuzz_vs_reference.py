@@ -31,6 +31,7 @@ def main():
     seed = int(args[0]) if args else 0
     trials = int(args[1]) if len(args) > 1 else 300
     show_all = "--all" in sys.argv
+    medium = "--medium" in sys.argv        # wider views, explicit solver routes (top-k route needs 4k <= width)
     rng = np.random.default_rng(seed)
     bad = 0
     for _ in range(trials):
@@ -39,6 +40,9 @@ def main():
         n = int(rng.integers(6, 120))
         dims = [int(rng.integers(1, 30)) for _ in range(m)]
         k = int(rng.integers(1, 8))
+        if medium:
+            n = int(rng.integers(300, 700))
+            dims = [int(rng.integers(36, 110)) for _ in range(m)]
         lat = rng.standard_normal((n, 3))
         views = [lat @ rng.standard_normal((3, d)) * rng.uniform(0, 1.5) + rng.standard_normal((n, d))
                  + rng.uniform(-1, 1) for d in dims]
@@ -57,6 +61,9 @@ def main():
                 [float(rng.uniform(0, 1)) for _ in range(m)]
             kw["c"] = c
         extra = {}
+        ours_kw = {}
+        if medium and model not in ("CCA", "PLS"):
+            ours_kw["solver"] = str(rng.choice(["auto", "eigen", "cholesky"]))
         if model == "GCCA" and rng.random() < 0.5:
             kw["view_weights"] = [float(rng.uniform(0.5, 2)) for _ in range(m)]
         if model == "MCCA":
@@ -72,13 +79,13 @@ def main():
         # c = 0 needs full-rank blocks; GCCA takes pinv(view) whatever c is; float32 inputs of an under-determined
         # problem amplify the reference's own float32 rounding (centring and pinv run in float32 there)
         well = determined or (cmin > 0 and model != "GCCA" and not f32)
-        desc = f"{'well ' if well else 'ILL  '}{model} n={n} dims={dims} f32={f32} {kw}"
+        desc = f"{'well ' if well else 'ILL  '}{model} n={n} dims={dims} f32={f32} {kw} {ours_kw}"
         out = []
         for lib in (ref, ours):
             try:
                 with warnings.catch_warnings():
                     warnings.simplefilter("ignore")
-                    est = getattr(lib, model)(**kw).fit(views, **extra)
+                    est = getattr(lib, model)(**kw, **(ours_kw if lib is ours else {})).fit(views, **extra)
                     held = [v[: n // 2] for v in views]
                     out.append((est, est.score(views), est.transform(held), est.pairwise_correlations(held)))
             except Exception as e:  # noqa: BLE001
