@@ -113,3 +113,35 @@ def test_grcca(c, mu, nv):
     C, n = _C(v)
     w = R.cov_grcca(C, [x.shape[1] for x in v], gs, 2, c, mu)
     assert R.max_rel_err_per_vector(w, ref.weights_) < 1e-9
+
+
+@pytest.mark.parametrize("model", ["MCCA", "MCCA_pca", "GCCA", "GCCA_w"])
+def test_center_false_semantics(model):
+    """np.cov centres inside MCCA / GCCA even when ``center=False``; GCCA mixes in raw second moments."""
+    v = [x + 1.3 for x in conftest_views("three_views")]
+    M, s, n = R.moments(v)
+    C, Cu = R.covariance_from_moments(M, s, n, True), R.covariance_from_moments(M, s, n, False)
+    dims = [10, 8, 6]
+    if model.startswith("MCCA"):
+        ref = MCCA(latent_dimensions=3, c=0.1, center=False, pca=model.endswith("pca")).fit(v)
+        w, _ = R.ref_mcca_fit(v, 3, 0.1, center=False)
+        wc, _ = R.cov_mcca_fit(C, dims, 3, 0.1)
+    else:
+        vw = [1.0, 2.0, 0.5] if model.endswith("w") else None
+        ref = GCCA(latent_dimensions=3, c=0.1, center=False, view_weights=vw).fit(v)
+        w, _ = R.ref_gcca_fit(v, 3, 0.1, vw, center=False)
+        wc, _ = R.cov_gcca_fit(C, dims, n, 3, 0.1, vw, second_moment=Cu)
+    assert R.max_rel_err_per_vector(w, ref.weights_) < 1e-9
+    assert R.max_rel_err_per_vector(wc, ref.weights_) < 1e-8
+    assert all(np.all(np.asarray(m) == 0) for m in ref.means_)
+
+
+def test_ridge_keeps_the_null_directions_of_a_rank_deficient_view():
+    v = conftest_views("two_views")
+    v = [v[0], np.hstack([v[1], v[1][:, :1]])]          # 9 columns of rank 8
+    ref = rCCA(latent_dimensions=9, c=0.2).fit(v)
+    assert ref.weights_[0].shape == (10, 9)            # nothing dropped: (1-c) lam + c >= c
+    C, n = _C(v)
+    w, sv = R.cov_rcca_fit(C, [10, 9], 9, 0.2, n)
+    assert w[0].shape == (10, 9) and sv[-1] < 1e-7     # the 9th singular value is the null direction
+    assert R.max_rel_err_per_vector([x[:, :8] for x in w], [x[:, :8] for x in ref.weights_]) < 1e-9
