@@ -113,3 +113,50 @@ def ext_outputs(name):
     if f"{name}/partial_corr" in _NPZ_EXT:
         out["partial_corr"] = _NPZ_EXT[f"{name}/partial_corr"]
     return out
+
+
+# ---- BASELINE config 3: CCALoss / MCCALoss at batch 4096 (oracle/make_golden_cfg3.py) ----
+with open(os.path.join(_DIR, "reference_outputs_cfg3.json")) as _f:
+    META_CFG3 = json.load(_f)
+_NPZ_CFG3 = np.load(os.path.join(_DIR, "reference_outputs_cfg3.npz"))
+CFG3_CASES = {c["name"]: c for c in META_CFG3["cases"]}
+
+
+def cfg3_inputs(name):
+    """Same recipe as oracle/make_golden_cfg3.py:cfg3_inputs (16 shared latents + unit noise, torch CPU generator)."""
+    import torch
+
+    c = CFG3_CASES[name]
+    g = torch.Generator().manual_seed(c["seed"])
+    zl = torch.randn(c["batch"], 16, generator=g, dtype=torch.float64)
+    out = []
+    for w in c["widths"]:
+        a = torch.randn(16, w, generator=g, dtype=torch.float64)
+        out.append(zl @ a + torch.randn(c["batch"], w, generator=g, dtype=torch.float64))
+    return out
+
+
+def cfg3_outputs(name):
+    """(loss, [per-view dict(rows, fro, tr, c)]): sub-sampled rows, Frobenius norm and two probe projections."""
+    grads, i = [], 0
+    while f"{name}/grad{i}_rows" in _NPZ_CFG3:
+        grads.append({k: _NPZ_CFG3[f"{name}/grad{i}_{k}"] for k in ("rows", "fro", "tr", "c")})
+        i += 1
+    return float(_NPZ_CFG3[f"{name}/loss"]), grads
+
+
+def cfg3_check_gradient(g, ref, view_index, case, tol):
+    """Compare a full gradient (numpy, float64) with the stored digest of the reference's gradient."""
+    stride = META_CFG3["row_stride"]
+    rng = np.random.default_rng(10_000 + case["seed"] + view_index)
+    r, c = rng.standard_normal(g.shape[0]), rng.standard_normal(g.shape[1])
+    scale = np.abs(ref["rows"]).max()
+    e_rows = np.abs(g[::stride] - ref["rows"]).max() / scale
+    e_fro = abs(np.linalg.norm(g) - float(ref["fro"])) / float(ref["fro"])
+    e_tr = np.abs(g.T @ r - ref["tr"]).max() / np.abs(ref["tr"]).max()
+    e_c = np.abs(g @ c - ref["c"]).max() / np.abs(ref["c"]).max()
+    assert e_rows < tol, f"sampled rows differ: {e_rows:.2e}"
+    assert e_fro < tol, f"Frobenius norm differs: {e_fro:.2e}"
+    assert e_tr < tol, f"batch projection differs: {e_tr:.2e}"
+    assert e_c < tol, f"width projection differs: {e_c:.2e}"
+    return max(e_rows, e_fro, e_tr, e_c)
