@@ -38,11 +38,17 @@ SIGNATURES = {
                              C.POINTER(C.c_int), C.POINTER(C.c_float), _vp, C.c_size_t, _vp]),
     "ccab_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp, C.c_int64, _vp,
                             C.c_int64, C.c_double, _vp, C.c_int64, _vp]),
+    "ccab_gemm_tc": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp, C.c_int64, C.c_int64, _vp,
+                               C.c_int64, C.c_int64, C.c_double, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64,
+                               C.c_int, C.c_int, _vp]),
     "ccab_whiten_rows": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_double, C.c_double, _vp, C.c_double,
                                    C.c_double, C.c_int, C.c_double, _vp, C.c_int64, _vp, _vp, _vp]),
     "ccab_ccaloss_small": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, C.c_double, _vp, _vp, _vp, _vp, _vp,
                                      _vp]),
     "ccab_potrf": (C.c_int, [C.c_int, C.c_int, _vp, C.c_int64, C.c_double, _vp, _vp]),
+    "ccab_potrf_inv_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "ccab_potrf_inv": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64,
+                                 C.c_double, _vp, _vp, C.c_size_t, _vp]),
     "ccab_trsm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp]),
     "ccab_scale": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int64,
                              _vp]),

@@ -9,10 +9,12 @@
 
 #include "ccaloss.cuh"
 #include "chol.cuh"
+#include "cholinv.cuh"
 #include "common.cuh"
 #include "dense.cuh"
 #include "moments.cuh"
 #include "syevj.cuh"
+#include "tgemm.cuh"
 
 namespace ccab {
 static thread_local char g_err[512] = "";
@@ -248,6 +250,42 @@ int ccab_gemm(int dtype, int transa, int transb, int m, int n, int k, double alp
   CCAB_CATCH
 }
 
+int ccab_gemm_tc(int transa, int transb, int m, int n, int k, double alpha, const void* A, int64_t lda,
+                 int64_t stride_a, const void* B, int64_t ldb, int64_t stride_b, double beta, void* C, int64_t ldc,
+                 int64_t stride_c, void* Ct, int64_t ldct, int64_t stride_ct, int batch, int lower_only,
+                 void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(A && B && (C || Ct), "null pointer argument");
+  CCAB_CHECK_ARG(m >= 1 && n >= 1 && k >= 1 && batch >= 1, "bad shape m=%d n=%d k=%d batch=%d", m, n, k, batch);
+  CCAB_CHECK_ARG((!C || ldc >= n) && (!Ct || ldct >= m), "output leading dimension too small");
+  int rc = require_device();
+  if (rc) return rc;
+  TgemmArgs a;
+  a.transa = transa;
+  a.transb = transb;
+  a.m = m;
+  a.n = n;
+  a.k = k;
+  a.alpha = (float)alpha;
+  a.beta = (float)beta;
+  a.A = static_cast<const float*>(A);
+  a.lda = lda;
+  a.strideA = stride_a;
+  a.B = static_cast<const float*>(B);
+  a.ldb = ldb;
+  a.strideB = stride_b;
+  a.C = static_cast<float*>(C);
+  a.ldc = ldc;
+  a.strideC = stride_c;
+  a.Ct = static_cast<float*>(Ct);
+  a.ldct = ldct;
+  a.strideCt = stride_ct;
+  a.batch = batch;
+  a.lower_only = lower_only;
+  return tgemm(a, static_cast<cudaStream_t>(stream));
+  CCAB_CATCH
+}
+
 int ccab_whiten_rows(int dtype, int d, const void* lam, const void* Vt, int64_t ldv, double c, double floor_add,
                      const void* floor_dev, double scale, double rank_tol, int max_rank, double lam_floor, void* Wt,
                      int64_t ldw, void* g_out, int* rank_out, void* stream) {
@@ -295,6 +333,28 @@ int ccab_potrf(int dtype, int n, void* A, int64_t lda, double pivot_tol, int* in
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == CCAB_F32) return potrf<float>(n, static_cast<float*>(A), lda, pivot_tol, info_dev, s);
   return potrf<double>(n, static_cast<double*>(A), lda, pivot_tol, info_dev, s);
+  CCAB_CATCH
+}
+
+size_t ccab_potrf_inv_workspace_bytes(int dtype, int n, int batch) {
+  if (n < 1 || batch < 1) return 0;
+  return dtype == CCAB_F32 ? potrf_inv_workspace_bytes<float>(n, batch) : potrf_inv_workspace_bytes<double>(n, batch);
+}
+
+int ccab_potrf_inv(int dtype, int n, int batch, void* A, int64_t lda, int64_t stride_a, void* Linv, int64_t ldi,
+                   int64_t stride_i, double pivot_tol, int* info_dev, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(A && Linv && info_dev && workspace, "null pointer argument");
+  int rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CCAB_F32)
+    return potrf_inv<float>(n, batch, static_cast<float*>(A), lda, stride_a, static_cast<float*>(Linv), ldi, stride_i,
+                            pivot_tol, info_dev, workspace, workspace_bytes, s);
+  return potrf_inv<double>(n, batch, static_cast<double*>(A), lda, stride_a, static_cast<double*>(Linv), ldi, stride_i,
+                           pivot_tol, info_dev, workspace, workspace_bytes, s);
   CCAB_CATCH
 }
 
@@ -378,6 +438,7 @@ int ccab_debug_set(const char* key, int value) {
   else if (!strcmp(key, "tc_dry_run")) d.dry_run = value < 0 ? 0 : value;
   else if (!strcmp(key, "x3_split")) d.x3_split = value < 0 ? 0 : value;
   else if (!strcmp(key, "f64_simt")) d.f64_simt = value < 0 ? 0 : value;
+  else if (!strcmp(key, "gemm_force_fma")) xgemm_force_fma() = value < 0 ? 0 : value;
   else if (!strcmp(key, "jacobi_inner_sweeps")) jacobi_inner_sweeps() = value;
   else if (!strcmp(key, "jacobi_force_unfused")) jacobi_force_unfused() = value;
   else {

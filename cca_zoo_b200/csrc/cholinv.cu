@@ -1,0 +1,375 @@
+// Blocked Cholesky factorisation WITH the explicit inverse of the factor, batched:
+//     R = L L^T,   Linv = L^-1      (R symmetric positive definite, n x n, lower triangle referenced)
+//
+// This is the whitening step of the solver stage in its GEMM-friendly form: with Linv in hand,
+// T = L1^-1 C12 L2^-T, K_ij = L_i^-1 C_ij L_j^-T, the weights L_i^-T U_k and S_ii^-1 = Linv^T Linv of the deep-CCA
+// objective are all plain products for the tensor-core GEMM (tgemm.cu) -- no triangular solves remain.
+// It replaces LAPACK's potrf/trsm inside scipy.linalg.eigh(A, B) (cca_zoo/_utils/_linalg.py:67-71), the
+// ridge whitening of cca_zoo/_utils/_linalg.py:30-38 in Cholesky form, and _inv_sqrtm's role in
+// cca_zoo/deep/objectives.py:94-97 (round 1 did this with 64-wide kernels: 124 dependent launches for n = 1024).
+//
+//   chol_diag_inv_kernel : one CTA per matrix factors a diagonal block (<= NB x NB, NB = 128 for float, 64 for
+//       double) in shared memory AND inverts the factor.  32 x 32 sub-blocks: warp 0 factors / inverts a sub-block
+//       warp-synchronously in registers (row per lane, shuffles, no block barrier), all warps apply the panel
+//       and trailing updates; the inverse's off-diagonal sub-blocks follow by recursive doubling
+//       (X_BA = -X_BB L_BA X_AA).  ~10 block barriers per 32 columns instead of 64.
+//   potrf_inv (host) : right-looking over NB-wide block columns -- diagonal kernel, panel  P = A_panel Dinv^T  and
+//       trailing update  A22 -= P P^T  as two GEMMs (lower tiles only) -- then Linv assembled from the diagonal
+//       inverses by recursive doubling over block pairs (2 batched GEMMs per level, log2(n / NB) levels).
+//       n = 1024: 24 + 6 launches, batched over the views.
+#include "cholinv.cuh"
+
+#include <type_traits>
+
+#include "dense.cuh"
+#include "tgemm.cuh"
+
+namespace ccab {
+
+template <typename T>
+int potrf_panel_gemm(const GemmArgs<T>& g, T* scratch, int64_t strideScratch, cudaStream_t stream);
+
+namespace {
+
+template <typename T>
+struct DiagCfg;
+template <>
+struct DiagCfg<float> {
+  static constexpr int NB = 128;
+  static constexpr int kThreads = 512;
+};
+template <>
+struct DiagCfg<double> {
+  static constexpr int NB = 64;
+  static constexpr int kThreads = 256;   // warp 0 holds a 32 x 32 row and column in registers: 128+ per thread
+};
+constexpr unsigned kFull = 0xffffffffu;
+
+// Warp-synchronous Cholesky + inverse of one 32 x 32 block held in shared memory at S[rb.., rb..] (row stride LD).
+// Lane i owns row i in registers.  Pivots of rows >= nb (padding: identity) are not tested.
+template <typename T, int LD>
+__device__ __forceinline__ void warp_chol_inv_32(T* S, T* X, int rb, int nb, int j0, T piv_tol, int* bad) {
+  const int lane = threadIdx.x & 31;
+  T a[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) a[j] = S[(rb + lane) * LD + rb + j];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    T piv = __shfl_sync(kFull, a[k], k);
+    if (rb + k < nb && !(piv > piv_tol)) {   // warp-uniform
+      if (lane == 0 && *bad == 0) *bad = j0 + rb + k + 1;
+      piv = T(1);
+    }
+    const T d = sqrt(piv);
+    const T dinv = T(1) / d;
+    const T lik = lane > k ? a[k] * dinv : (lane == k ? d : T(0));
+    a[k] = lik;
+#pragma unroll
+    for (int j = k + 1; j < 32; ++j) {
+      const T ljk = __shfl_sync(kFull, lik, j);
+      a[j] = fma(-lik, ljk, a[j]);    // entries with j > lane are never read
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) S[(rb + lane) * LD + rb + j] = j <= lane ? a[j] : T(0);
+  // inverse: lane c computes column c of L^-1 by forward substitution (x_k = 0 for k < c)
+  T x[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    T s = T(0);
+#pragma unroll
+    for (int k = 0; k < i; ++k) {
+      const T lik = __shfl_sync(kFull, a[k], i);
+      s = fma(lik, x[k], s);
+    }
+    const T lii = __shfl_sync(kFull, a[i], i);
+    x[i] = ((lane == i ? T(1) : T(0)) - s) / lii;
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) X[(rb + i) * LD + rb + lane] = x[i];
+}
+
+template <typename T, int NB, int kDiagThreads>
+__global__ void __launch_bounds__(kDiagThreads, 1)
+chol_diag_inv_kernel(T* __restrict__ A, int64_t lda, int64_t strideA, int nb, int j0, T* __restrict__ Dinv,
+                     int64_t strideDinv, double piv_tol, int* __restrict__ info) {
+  constexpr int LD = NB + 1;
+  constexpr int HB = NB / 2;
+  extern __shared__ __align__(16) unsigned char cdi_smem[];
+  T* S = reinterpret_cast<T*>(cdi_smem);
+  T* X = S + NB * LD;
+  T* Tm = X + NB * LD;            // [HB][HB + 1]
+  __shared__ int bad;
+  T* Ab = A + (size_t)blockIdx.x * strideA;
+  T* Db = Dinv + (size_t)blockIdx.x * strideDinv;
+  const int tid = threadIdx.x;
+  if (tid == 0) bad = 0;
+  for (int e = tid; e < NB * NB; e += kDiagThreads) {
+    const int r = e / NB, c = e % NB;
+    T v = (r == c) ? T(1) : T(0);              // padding: identity
+    if (r < nb && c < nb) v = c <= r ? Ab[(size_t)r * lda + c] : T(0);
+    S[r * LD + c] = v;
+    X[r * LD + c] = T(0);
+  }
+  __syncthreads();
+
+  const int nsub = (nb + 31) / 32;
+  for (int jb = 0; jb < NB / 32; ++jb) {
+    const int rb = jb * 32;
+    if (jb < nsub) {
+      if (tid < 32) warp_chol_inv_32<T, LD>(S, X, rb, nb, j0, (T)piv_tol, &bad);
+    } else if (tid < 32) {
+      X[(rb + tid) * LD + rb + tid] = T(1);     // padding block: L = I, L^-1 = I
+    }
+    __syncthreads();
+    if (jb + 1 >= nsub) continue;               // nothing below / to the right (uniform)
+    const int r0 = rb + 32;
+    const int R = NB - r0;
+    // ---- panel: P[r][c] = sum_{k <= c} S[r][rb + k] * X[rb + c][rb + k]   (= A_panel * L32^-T) ----
+    {
+      constexpr int kGroups = kDiagThreads / 32;
+      constexpr int kMaxRows = (NB - 32 + kGroups - 1) / kGroups;
+      T out[kMaxRows];
+      const int c = tid & 31, g = tid >> 5;
+#pragma unroll
+      for (int q = 0; q < kMaxRows; ++q) {
+        const int r = r0 + g + kGroups * q;
+        T acc = T(0);
+        if (r < NB) {
+          for (int k = 0; k <= c; ++k) acc = fma(S[r * LD + rb + k], X[(rb + c) * LD + rb + k], acc);
+        }
+        out[q] = acc;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < kMaxRows; ++q) {
+        const int r = r0 + g + kGroups * q;
+        if (r < NB) S[r * LD + rb + c] = out[q];
+      }
+    }
+    __syncthreads();
+    // ---- trailing update (lower part): S[r][c] -= sum_k P[r][k] P[c][k] ----
+    for (int e = tid; e < R * R; e += kDiagThreads) {
+      const int r = r0 + e / R, c = r0 + e % R;
+      if (c > r) continue;
+      T acc = T(0);
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) acc = fma(S[r * LD + rb + k], S[c * LD + rb + k], acc);
+      S[r * LD + c] -= acc;
+    }
+    __syncthreads();
+  }
+
+  // ---- inverse, off-diagonal sub-blocks by recursive doubling: X_BA = -X_BB (L_BA X_AA) ----
+  for (int s = 32; s < NB; s *= 2) {
+    const int npairs = NB / (2 * s);
+    const int total = npairs * s * s;
+    for (int e = tid; e < total; e += kDiagThreads) {
+      const int pi = e / (s * s), rr = (e / s) % s, cc = e % s;
+      const int a0 = 2 * pi * s, b0 = a0 + s;
+      T acc = T(0);
+      for (int k = cc; k < s; ++k) acc = fma(S[(b0 + rr) * LD + a0 + k], X[(a0 + k) * LD + a0 + cc], acc);
+      Tm[(pi * s + rr) * (HB + 1) + cc] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < total; e += kDiagThreads) {
+      const int pi = e / (s * s), rr = (e / s) % s, cc = e % s;
+      const int a0 = 2 * pi * s, b0 = a0 + s;
+      T acc = T(0);
+      for (int k = 0; k <= rr; ++k) acc = fma(X[(b0 + rr) * LD + b0 + k], Tm[(pi * s + k) * (HB + 1) + cc], acc);
+      X[(b0 + rr) * LD + a0 + cc] = -acc;
+    }
+    __syncthreads();
+  }
+
+  for (int e = tid; e < NB * NB; e += kDiagThreads) {
+    const int r = e / NB, c = e % NB;
+    if (r < nb && c < nb) Ab[(size_t)r * lda + c] = S[r * LD + c];       // L (strict upper of the block zeroed)
+    Db[(size_t)r * NB + c] = (r < nb && c < nb) ? X[r * LD + c] : T(0);
+  }
+  if (tid == 0 && bad) atomicCAS(info + blockIdx.x, 0, bad);
+}
+
+// Linv <- 0 everywhere, then the inverted diagonal blocks on the block diagonal
+template <typename T>
+__global__ void linv_init_kernel(T* __restrict__ Linv, int64_t ldi, int64_t strideL, int n, int NB,
+                                 const T* __restrict__ Dinv, int64_t strideD) {
+  T* Lb = Linv + (size_t)blockIdx.y * strideL;
+  const T* Db = Dinv + (size_t)blockIdx.y * strideD;
+  const size_t total = (size_t)n * n;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / n), c = (int)(e % n);
+    T v = T(0);
+    if (r / NB == c / NB) v = Db[(size_t)(r / NB) * NB * NB + (size_t)(r % NB) * NB + (c % NB)];
+    Lb[(size_t)r * ldi + c] = v;
+  }
+}
+
+}  // namespace
+
+template <typename T>
+int potrf_inv_block(T* A, int64_t lda, int64_t strideA, int nb, int j0, T* Dinv, int64_t strideDinv, double piv_tol,
+                    int* info, int batch, cudaStream_t stream) {
+  constexpr int NB = DiagCfg<T>::NB;
+  constexpr int kDiagThreads = DiagCfg<T>::kThreads;
+  CCAB_CHECK_ARG(nb >= 1 && nb <= NB, "diagonal block of %d exceeds %d", nb, NB);
+  const size_t smem = sizeof(T) * (2 * NB * (NB + 1) + (NB / 2) * (NB / 2 + 1));
+  static bool attr_done[64] = {};
+  int dev = 0;
+  CCAB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    CCAB_CUDA(cudaFuncSetAttribute(chol_diag_inv_kernel<T, NB, kDiagThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
+  chol_diag_inv_kernel<T, NB, kDiagThreads><<<batch, kDiagThreads, smem, stream>>>(A, lda, strideA, nb, j0, Dinv, strideDinv, piv_tol,
+                                                                    info);
+  count_launches(1);
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int potrf_inv_block_size() {
+  return DiagCfg<T>::NB;
+}
+
+template <typename T>
+size_t potrf_inv_workspace_bytes(int n, int batch) {
+  constexpr int NB = DiagCfg<T>::NB;
+  const size_t nblk = (size_t)ceil_div(n, NB);
+  const size_t dinv = nblk * NB * NB;            // inverted diagonal blocks
+  const size_t tmp = (size_t)n * ((size_t)n / 2 + NB);  // L_BA X_AA of every pair of one doubling level
+  return sizeof(T) * (dinv + tmp) * (size_t)batch + 256;
+}
+
+template <typename T>
+int potrf_inv(int n, int batch, T* A, int64_t lda, int64_t strideA, T* Linv, int64_t ldi, int64_t strideLinv,
+              double piv_tol, int* info, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  constexpr int NB = DiagCfg<T>::NB;
+  CCAB_CHECK_ARG(n >= 1 && batch >= 1 && lda >= n && ldi >= n, "bad potrf_inv shape");
+  CCAB_CHECK_ARG(ws_bytes >= potrf_inv_workspace_bytes<T>(n, batch), "potrf_inv workspace too small");
+  CCAB_CHECK_ARG(batch == 1 || (strideA > 0 && strideLinv > 0), "potrf_inv: batch strides missing");
+  const int nblk = (int)ceil_div(n, NB);
+  T* w = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  const int64_t strideD = (int64_t)nblk * NB * NB;
+  T* Dinv = w;
+  const int64_t strideT = (int64_t)n * (n / 2 + NB);
+  T* Tmp = w + strideD * batch;
+  CCAB_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, stream));
+
+  for (int jb = 0; jb < nblk; ++jb) {
+    const int j0 = jb * NB, nb = std::min(NB, n - j0);
+    int rc = potrf_inv_block<T>(A + (size_t)j0 * lda + j0, lda, strideA, nb, j0, Dinv + (size_t)jb * NB * NB, strideD,
+                                piv_tol, info, batch, stream);
+    if (rc) return rc;
+    const int rows = n - j0 - nb;
+    if (rows <= 0) continue;
+    GemmArgs<T> g;   // panel: P = A_panel * Dinv_jj^T   (in place: a tile reads its rows completely before writing)
+    g.transa = 0; g.transb = 1; g.m = rows; g.n = nb; g.k = nb;
+    g.A = A + (size_t)(j0 + nb) * lda + j0; g.lda = lda; g.strideA = strideA;
+    g.B = Dinv + (size_t)jb * NB * NB; g.ldb = NB; g.strideB = strideD;
+    g.C = A + (size_t)(j0 + nb) * lda + j0; g.ldc = lda; g.strideC = strideA;
+    g.batch = batch;
+    rc = potrf_panel_gemm<T>(g, Tmp, strideT, stream);
+    if (rc) return rc;
+    GemmArgs<T> u;   // trailing: A22 -= P P^T, lower tiles
+    u.transa = 0; u.transb = 1; u.m = rows; u.n = rows; u.k = nb; u.alpha = T(-1); u.beta = T(1);
+    u.A = g.C; u.lda = lda; u.strideA = strideA;
+    u.B = g.C; u.ldb = lda; u.strideB = strideA;
+    u.C = A + (size_t)(j0 + nb) * lda + (j0 + nb); u.ldc = lda; u.strideC = strideA;
+    u.batch = batch; u.lower_only = 1;
+    rc = xgemm<T>(u, stream);
+    if (rc) return rc;
+  }
+
+  // ---- Linv: diagonal blocks, then off-diagonal blocks level by level ----
+  {
+    const size_t total = (size_t)n * n;
+    dim3 grid((unsigned)std::min<size_t>((total + 255) / 256, 1184), (unsigned)batch);
+    linv_init_kernel<T><<<grid, 256, 0, stream>>>(Linv, ldi, strideLinv, n, NB, Dinv, strideD);
+    count_launches(1);
+    CCAB_CUDA(cudaGetLastError());
+  }
+  for (int64_t s = NB; s < n; s *= 2) {
+    const int npairs_all = (int)ceil_div(n, 2 * s);
+    // pairs whose B block is a full s x s block can share one batched launch; a ragged last pair goes alone
+    int nfull = 0;
+    for (int i = 0; i < npairs_all; ++i)
+      if ((2 * i + 2) * s <= n) nfull = i + 1;
+    for (int pass = 0; pass < 2; ++pass) {
+      int i0, np;
+      int64_t bs;
+      if (pass == 0) {
+        if (nfull == 0) continue;
+        i0 = 0; np = nfull; bs = s;
+      } else {
+        if (nfull == npairs_all) continue;
+        i0 = nfull; np = 1;
+        bs = n - (2 * (int64_t)i0 + 1) * s;
+        if (bs <= 0) continue;
+      }
+      const int64_t a0 = 2 * (int64_t)i0 * s, b0 = a0 + s;
+      const int64_t pair_stride_a = 2 * s * (lda + 1), pair_stride_i = 2 * s * (ldi + 1);
+      GemmArgs<T> g1;   // Tmp = L[B, A] * Linv[A, A]
+      g1.m = (int)bs; g1.n = (int)s; g1.k = (int)s;
+      g1.A = A + (size_t)b0 * lda + a0; g1.lda = lda; g1.strideA = pair_stride_a; g1.strideA2 = strideA;
+      g1.B = Linv + (size_t)a0 * ldi + a0; g1.ldb = ldi; g1.strideB = pair_stride_i; g1.strideB2 = strideLinv;
+      g1.C = Tmp + (size_t)i0 * s * s; g1.ldc = s; g1.strideC = s * s; g1.strideC2 = strideT;
+      g1.batch = np; g1.batch2 = batch;
+      int rc = xgemm<T>(g1, stream);
+      if (rc) return rc;
+      GemmArgs<T> g2;   // Linv[B, A] = -Linv[B, B] * Tmp
+      g2.m = (int)bs; g2.n = (int)s; g2.k = (int)bs; g2.alpha = T(-1);
+      g2.A = Linv + (size_t)b0 * ldi + b0; g2.lda = ldi; g2.strideA = pair_stride_i; g2.strideA2 = strideLinv;
+      g2.B = g1.C; g2.ldb = s; g2.strideB = s * s; g2.strideB2 = strideT;
+      g2.C = Linv + (size_t)b0 * ldi + a0; g2.ldc = ldi; g2.strideC = pair_stride_i; g2.strideC2 = strideLinv;
+      g2.batch = np; g2.batch2 = batch;
+      rc = xgemm<T>(g2, stream);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+// The panel product overwrites its own A operand.  The tensor-core kernel reads a tile's whole A rows (all of K)
+// before its epilogue writes them and no other tile reads those rows, so in place is safe there; the FMA kernel
+// tiles N in 64-column blocks whose CTAs would read columns another CTA has already overwritten, so it goes through
+// a scratch copy.
+template <typename T>
+int potrf_panel_gemm(const GemmArgs<T>& g, T* scratch, int64_t strideScratch, cudaStream_t stream) {
+  if (std::is_same<T, float>::value && !xgemm_force_fma() && g.n <= 128) {
+    TgemmArgs a;
+    a.transa = g.transa; a.transb = g.transb; a.m = g.m; a.n = g.n; a.k = g.k;
+    a.A = reinterpret_cast<const float*>(g.A); a.lda = g.lda; a.strideA = g.strideA;
+    a.B = reinterpret_cast<const float*>(g.B); a.ldb = g.ldb; a.strideB = g.strideB;
+    a.C = reinterpret_cast<float*>(g.C); a.ldc = g.ldc; a.strideC = g.strideC;
+    a.batch = g.batch;
+    a.force_bn = 128;   // ONE column tile per row block: the in-place condition
+    if (tgemm_supported(a)) return tgemm(a, stream);
+  }
+  if (g.n <= 64) return gemm_fma<T>(g, stream);   // the FMA kernel's 64-column tile covers the panel: same argument
+  GemmArgs<T> t = g;
+  t.C = scratch; t.ldc = g.n; t.strideC = strideScratch;
+  int rc = gemm_fma<T>(t, stream);
+  if (rc) return rc;
+  for (int b = 0; b < g.batch; ++b) {
+    CCAB_CUDA(cudaMemcpy2DAsync(g.C + (size_t)b * g.strideC, (size_t)g.ldc * sizeof(T), scratch + (size_t)b * strideScratch,
+                                (size_t)g.n * sizeof(T), (size_t)g.n * sizeof(T), (size_t)g.m, cudaMemcpyDeviceToDevice,
+                                stream));
+  }
+  return 0;
+}
+
+template int potrf_inv<float>(int, int, float*, int64_t, int64_t, float*, int64_t, int64_t, double, int*, void*, size_t,
+                              cudaStream_t);
+template int potrf_inv<double>(int, int, double*, int64_t, int64_t, double*, int64_t, int64_t, double, int*, void*,
+                               size_t, cudaStream_t);
+template size_t potrf_inv_workspace_bytes<float>(int, int);
+template size_t potrf_inv_workspace_bytes<double>(int, int);
+template int potrf_inv_block_size<float>();
+template int potrf_inv_block_size<double>();
+template int potrf_inv_block<float>(float*, int64_t, int64_t, int, int, float*, int64_t, double, int*, int, cudaStream_t);
+template int potrf_inv_block<double>(double*, int64_t, int64_t, int, int, double*, int64_t, double, int*, int,
+                                     cudaStream_t);
+
+}  // namespace ccab

@@ -257,6 +257,40 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(uint32_t M, uint32_t N
          | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+
+// 3xTF32 residual: the tensor core TRUNCATES fp32 operands to TF32 (measured, tools/probe_trunc.py), so a raw fp32
+// array is its own "hi" operand; lo = rna_tf32(x - trunc(x)) carries the next 11 bits (x = hi + lo + O(2^-21 |x|)).
+__device__ __forceinline__ float tf32_residual(float v) {
+  const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  uint32_t l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+  return __uint_as_float(l);
+}
+
+// general instruction descriptor for kind::tf32 (fp32 accumulate): *_kmajor = the reduction index is the
+// contiguous one of that operand's shared-memory tile
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t M, uint32_t N, bool a_kmajor, bool b_kmajor) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_kmajor ? 0u : 1u) << 15) | ((b_kmajor ? 0u : 1u) << 16) |
+         ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// 4-D TMA tile load (inner, outer, batch, batch2)
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// 3-D TMA tile load (inner, outer, batch)
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 #endif  // __CUDACC__
 
 }  // namespace ccab

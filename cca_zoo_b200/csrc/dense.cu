@@ -1,16 +1,23 @@
 #include "dense.cuh"
 
+#include "tgemm.cuh"
+
 namespace ccab {
 
-// 64x64 output tile, 16-deep k chunks, 256 threads, 4x4 register tile per thread.
+// 64x64 output tile, 16-deep k chunks, 256 threads, 4x4 register tile per thread.  blockIdx.z walks the batch
+// (b2 * batch1 + b1).  Exact FMA in T: the path for float64, for shapes TMA cannot address and for tiny products.
 template <typename T, int TA, int TB>
-__global__ void __launch_bounds__(256) gemm_kernel(int m, int n, int k, T alpha, const T* __restrict__ A,
-                                                   int64_t lda, const T* __restrict__ B, int64_t ldb, T beta,
-                                                   T* __restrict__ C, int64_t ldc) {
+__global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs<T> g) {
   constexpr int KC = 16;
   __shared__ T As[KC][64 + 4];
   __shared__ T Bs[KC][64 + 4];
+  const int m = g.m, n = g.n, k = g.k;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  if (g.lower_only && n0 >= m0 + 64) return;
+  const int b1 = (int)blockIdx.z % g.batch, b2 = (int)blockIdx.z / g.batch;
+  const T* __restrict__ A = g.A + (size_t)b1 * g.strideA + (size_t)b2 * g.strideA2;
+  const T* __restrict__ B = g.B + (size_t)b1 * g.strideB + (size_t)b2 * g.strideB2;
+  const int64_t lda = g.lda, ldb = g.ldb;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   T acc[4][4];
 #pragma unroll
@@ -64,6 +71,8 @@ __global__ void __launch_bounds__(256) gemm_kernel(int m, int n, int k, T alpha,
     }
     __syncthreads();
   }
+  T* C = g.C ? g.C + (size_t)b1 * g.strideC + (size_t)b2 * g.strideC2 : nullptr;
+  T* Ct = g.Ct ? g.Ct + (size_t)b1 * g.strideCt + (size_t)b2 * g.strideCt2 : nullptr;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = m0 + ty * 4 + i;
@@ -72,31 +81,70 @@ __global__ void __launch_bounds__(256) gemm_kernel(int m, int n, int k, T alpha,
     for (int j = 0; j < 4; ++j) {
       const int cidx = n0 + tx * 4 + j;
       if (cidx >= n) continue;
-      T v = alpha * acc[i][j];
-      if (beta != T(0)) v += beta * C[(size_t)r * ldc + cidx];
-      C[(size_t)r * ldc + cidx] = v;
+      T v = g.alpha * acc[i][j];
+      if (C) {
+        if (g.beta != T(0)) v += g.beta * C[(size_t)r * g.ldc + cidx];
+        C[(size_t)r * g.ldc + cidx] = v;
+      }
+      if (Ct) Ct[(size_t)cidx * g.ldct + r] = v;
     }
   }
 }
 
 template <typename T>
-int gemm(int transa, int transb, int m, int n, int k, T alpha, const T* A, int64_t lda, const T* B, int64_t ldb,
-         T beta, T* C, int64_t ldc, cudaStream_t stream) {
-  CCAB_CHECK_ARG(m >= 0 && n >= 0 && k >= 0, "negative gemm dimension");
-  if (m == 0 || n == 0) return 0;
-  dim3 grid((unsigned)ceil_div(n, 64), (unsigned)ceil_div(m, 64));
-  if (!transa && !transb) gemm_kernel<T, 0, 0><<<grid, 256, 0, stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-  else if (transa && !transb) gemm_kernel<T, 1, 0><<<grid, 256, 0, stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-  else if (!transa && transb) gemm_kernel<T, 0, 1><<<grid, 256, 0, stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-  else gemm_kernel<T, 1, 1><<<grid, 256, 0, stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+int gemm_fma(const GemmArgs<T>& g, cudaStream_t stream) {
+  CCAB_CHECK_ARG(g.m >= 0 && g.n >= 0 && g.k >= 0 && g.batch >= 1 && g.batch2 >= 1, "bad gemm shape");
+  CCAB_CHECK_ARG(g.C || g.Ct, "gemm: no output");
+  CCAB_CHECK_ARG(g.C || g.beta == T(0), "gemm: beta != 0 needs C");
+  if (g.m == 0 || g.n == 0) return 0;
+  dim3 grid((unsigned)ceil_div(g.n, 64), (unsigned)ceil_div(g.m, 64), (unsigned)(g.batch * g.batch2));
+  if (!g.transa && !g.transb) gemm_kernel<T, 0, 0><<<grid, 256, 0, stream>>>(g);
+  else if (g.transa && !g.transb) gemm_kernel<T, 1, 0><<<grid, 256, 0, stream>>>(g);
+  else if (!g.transa && g.transb) gemm_kernel<T, 0, 1><<<grid, 256, 0, stream>>>(g);
+  else gemm_kernel<T, 1, 1><<<grid, 256, 0, stream>>>(g);
   count_launches(1);
   CCAB_CUDA(cudaGetLastError());
   return 0;
+}
+template int gemm_fma<float>(const GemmArgs<float>&, cudaStream_t);
+template int gemm_fma<double>(const GemmArgs<double>&, cudaStream_t);
+
+template <typename T>
+int gemm(int transa, int transb, int m, int n, int k, T alpha, const T* A, int64_t lda, const T* B, int64_t ldb,
+         T beta, T* C, int64_t ldc, cudaStream_t stream) {
+  GemmArgs<T> g;
+  g.transa = transa; g.transb = transb; g.m = m; g.n = n; g.k = k; g.alpha = alpha; g.beta = beta;
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+  return gemm_fma<T>(g, stream);
 }
 template int gemm<float>(int, int, int, int, int, float, const float*, int64_t, const float*, int64_t, float, float*,
                          int64_t, cudaStream_t);
 template int gemm<double>(int, int, int, int, int, double, const double*, int64_t, const double*, int64_t, double,
                           double*, int64_t, cudaStream_t);
+
+// tensor pipe when the operands are float32 and TMA-addressable and the product is big enough to amortise the
+// pipeline fill; exact FMA tiles otherwise
+template <>
+int xgemm<float>(const GemmArgs<float>& g, cudaStream_t stream) {
+  TgemmArgs a;
+  a.transa = g.transa; a.transb = g.transb; a.m = g.m; a.n = g.n; a.k = g.k; a.alpha = g.alpha; a.beta = g.beta;
+  a.A = g.A; a.lda = g.lda; a.strideA = g.strideA; a.strideA2 = g.strideA2;
+  a.B = g.B; a.ldb = g.ldb; a.strideB = g.strideB; a.strideB2 = g.strideB2;
+  a.C = g.C; a.ldc = g.ldc; a.strideC = g.strideC; a.strideC2 = g.strideC2;
+  a.Ct = g.Ct; a.ldct = g.ldct; a.strideCt = g.strideCt; a.strideCt2 = g.strideCt2;
+  a.batch = g.batch; a.batch2 = g.batch2; a.lower_only = g.lower_only;
+  const bool big = (int64_t)g.m * g.n >= 64 * 32 && g.k >= 16;
+  if (big && !xgemm_force_fma() && tgemm_supported(a)) return tgemm(a, stream);
+  return gemm_fma<float>(g, stream);
+}
+template <>
+int xgemm<double>(const GemmArgs<double>& g, cudaStream_t stream) {
+  return gemm_fma<double>(g, stream);
+}
+int& xgemm_force_fma() {
+  static int v = 0;
+  return v;
+}
 
 template <typename T>
 __global__ void whiten_rows_kernel(int d, const T* __restrict__ lam, const T* __restrict__ Vt, int64_t ldv, double c,

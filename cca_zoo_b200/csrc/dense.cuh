@@ -6,6 +6,30 @@
 
 namespace ccab {
 
+// Batched GEMM descriptor shared by the FMA kernel (any T) and the tcgen05 kernel (float, see tgemm.cuh):
+// matrix (b, b2) of the batch lives at X + b * strideX + b2 * strideX2.
+template <typename T>
+struct GemmArgs {
+  int transa = 0, transb = 0;
+  int m = 0, n = 0, k = 0;
+  T alpha = T(1), beta = T(0);
+  const T* A = nullptr;
+  int64_t lda = 0, strideA = 0, strideA2 = 0;
+  const T* B = nullptr;
+  int64_t ldb = 0, strideB = 0, strideB2 = 0;
+  T* C = nullptr;                 // may be NULL when only Ct is wanted
+  int64_t ldc = 0, strideC = 0, strideC2 = 0;
+  T* Ct = nullptr;                // optional transposed copy (n x m, row-major)
+  int64_t ldct = 0, strideCt = 0, strideCt2 = 0;
+  int batch = 1, batch2 = 1;
+  int lower_only = 0;             // skip output tiles strictly above the diagonal
+};
+template <typename T>
+int gemm_fma(const GemmArgs<T>& g, cudaStream_t stream);   // exact FMA tiles on the CUDA cores
+template <typename T>
+int xgemm(const GemmArgs<T>& g, cudaStream_t stream);      // float: tcgen05 when TMA-addressable, else gemm_fma
+int& xgemm_force_fma();                                    // debug knob: 1 = never use the tensor pipe
+
 // C (m x n, row-major, ldc) = alpha * op(A) * op(B) + beta * C ; op(X) = X or X^T, row-major storage.
 template <typename T>
 int gemm(int transa, int transb, int m, int n, int k, T alpha, const T* A, int64_t lda, const T* B, int64_t ldb,

@@ -493,13 +493,6 @@ moments_tf32_2cta_kernel(const __grid_constant__ TcParams2 p) {
 // the residual lo = rna_tf32(x - hi) is materialised (exact subtraction, then 11 significant bits: the
 // hardware's own truncation of lo is a no-op).  x = hi + lo + O(2^-21 |x|).  One HBM-bound pre-pass:
 // reads n*d*4 bytes, writes n*d*4 bytes.
-__device__ __forceinline__ float tf32_residual(float v) {
-  const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-  uint32_t l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
-  return __uint_as_float(l);
-}
-
 // round-to-nearest variant: hi = rna_tf32(x), lo = rna_tf32(x - hi); both operands materialised
 __global__ void tf32_split_rn_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx,
                                      float* __restrict__ hi, float* __restrict__ lo, int64_t ldo) {

@@ -200,6 +200,54 @@ def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, out=None):
     return out
 
 
+def _tc_ok(t: torch.Tensor) -> bool:
+    return (t.dtype == torch.float32 and t.dim() in (2, 3) and t.stride(-1) == 1 and t.data_ptr() % 16 == 0
+            and t.stride(-2) % 4 == 0 and t.stride(-2) >= t.shape[-1] and (t.dim() == 2 or t.stride(0) % 4 == 0))
+
+
+def gemm_tc(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, out=None, out_t=None, want_c=True,
+            lower_only=False):
+    """Tensor-core GEMM (ccab_gemm_tc): float32, 2-D or batched 3-D operands (row-major, unit inner stride).
+
+    out = alpha * op(A) @ op(B) + beta * out; ``out_t`` (optional) receives the transpose as well.  Returns
+    ``out`` (or ``out_t`` when ``want_c`` is False).  Raises ValueError when the operands do not meet the TMA
+    alignment rules (16-byte aligned, leading dimensions % 4 == 0): callers use ``gemm`` then."""
+    lib = _lib.load()
+    _require_cuda(A, "A")
+    _require_cuda(B, "B")
+    if not (_tc_ok(A) and _tc_ok(B)) or A.dim() != B.dim():
+        raise ValueError("gemm_tc: float32 row-major operands, 16-byte aligned, leading dimensions % 4 == 0")
+    batched = A.dim() == 3
+    batch = A.shape[0] if batched else 1
+    if batched and B.shape[0] != batch:
+        raise ValueError("gemm_tc: batch sizes differ")
+    m, k = (A.shape[-1], A.shape[-2]) if transa else (A.shape[-2], A.shape[-1])
+    k2, n = (B.shape[-1], B.shape[-2]) if transb else (B.shape[-2], B.shape[-1])
+    if k != k2:
+        raise ValueError(f"gemm inner dimensions differ: {k} vs {k2}")
+    shape = (batch, m, n) if batched else (m, n)
+    shape_t = (batch, n, m) if batched else (n, m)
+    if out is None and want_c:
+        out = torch.empty(shape, dtype=A.dtype, device=A.device)
+        beta = 0.0
+    for t, shp, nm in ((out, shape, "out"), (out_t, shape_t, "out_t")):
+        if t is not None and (tuple(t.shape) != shp or t.stride(-1) != 1 or t.dtype != A.dtype or t.device != A.device):
+            raise ValueError(f"gemm_tc `{nm}` must be a row-major {shp} float32 tensor on {A.device}")
+    if out is None and out_t is None:
+        raise ValueError("gemm_tc: no output requested")
+    sa = A.stride(0) if batched else 0
+    sb = B.stride(0) if batched else 0
+    with torch.cuda.device(A.device):
+        rc = lib.ccab_gemm_tc(int(transa), int(transb), m, n, k, float(alpha), _ptr(A), A.stride(-2), sa, _ptr(B),
+                              B.stride(-2), sb, float(beta), _ptr(out), 0 if out is None else out.stride(-2),
+                              (out.stride(0) if (batched and out is not None) else 0), _ptr(out_t),
+                              0 if out_t is None else out_t.stride(-2),
+                              (out_t.stride(0) if (batched and out_t is not None) else 0), batch, int(lower_only),
+                              _stream(A))
+    _lib.check(rc, "ccab_gemm_tc")
+    return out if want_c else out_t
+
+
 def whiten_rows(lam, Vt, c, floor_add=0.0, floor_dev=None, scale=1.0, rank_tol=0.0, max_rank=None,
                 lam_floor=-1e300):
     """(Wt, g, rank_dev) -- see ccab_whiten_rows."""
@@ -247,6 +295,28 @@ def potrf_(A, pivot_tol=0.0):
         rc = lib.ccab_potrf(_DT[A.dtype], A.shape[0], _ptr(A), A.stride(0), float(pivot_tol), _ptr(info), _stream(A))
     _lib.check(rc, "ccab_potrf")
     return info
+
+
+def potrf_inv_(A, pivot_tol=0.0):
+    """In place lower Cholesky of A (n x n or batch x n x n, row-major) AND the explicit inverse of the factor.
+
+    Returns (Linv, info): Linv like A (zeros above the diagonal), info int32[batch] on the device (0 = ok)."""
+    lib = _lib.load()
+    _require_cuda(A, "A")
+    squeeze = A.dim() == 2
+    Ab = A.unsqueeze(0) if squeeze else A
+    if Ab.dim() != 3 or Ab.shape[1] != Ab.shape[2] or Ab.stride(2) != 1 or Ab.dtype not in _DT:
+        raise ValueError("square row-major float32/float64 matrices expected")
+    batch, n, _ = Ab.shape
+    Linv = torch.empty((batch, n, n), dtype=A.dtype, device=A.device)
+    info = torch.empty(batch, dtype=torch.int32, device=A.device)
+    dt = _DT[A.dtype]
+    ws = _ws(lib.ccab_potrf_inv_workspace_bytes(dt, n, batch), A.device)
+    with torch.cuda.device(A.device):
+        rc = lib.ccab_potrf_inv(dt, n, batch, _ptr(Ab), Ab.stride(1), Ab.stride(0) if batch > 1 else 0, _ptr(Linv), n,
+                                n * n, float(pivot_tol), _ptr(info), _ptr(ws), ws.numel(), _stream(A))
+    _lib.check(rc, "ccab_potrf_inv")
+    return (Linv[0] if squeeze else Linv), info
 
 
 def trsm_(L, B, side="left", trans=False):

@@ -101,6 +101,17 @@ int ccab_gesvj(int dtype, int m, int n, const void* A, int64_t lda, void* sigma,
 int ccab_gemm(int dtype, int transa, int transb, int m, int n, int k, double alpha, const void* A, int64_t lda,
               const void* B, int64_t ldb, double beta, void* C, int64_t ldc, void* stream);
 
+/* Tensor-core variant of ccab_gemm for float32 (tcgen05.mma kind::tf32, 3xTF32 split formed in shared memory:
+ * fp32-grade products, fp32 accumulation in TMEM), batched: matrix b of the batch lives at X + b * stride_x.
+ * Optionally also (or only: C may be NULL when beta == 0) writes the transpose Ct (n x m, row-major, ldct).
+ * lower_only != 0 skips the 128-row output tiles that lie strictly above the diagonal (SYRK-type updates).
+ * Needs 16-byte aligned A / B with lda, ldb (and the batch strides) multiples of 4; otherwise returns < 0 and the
+ * caller uses ccab_gemm.  Replaces the same reference products as ccab_gemm, on the tensor pipe. */
+int ccab_gemm_tc(int transa, int transb, int m, int n, int k, double alpha, const void* A, int64_t lda,
+                 int64_t stride_a, const void* B, int64_t ldb, int64_t stride_b, double beta, void* C, int64_t ldc,
+                 int64_t stride_c, void* Ct, int64_t ldct, int64_t stride_ct, int batch, int lower_only,
+                 void* stream);
+
 /* Whitening rows from an eigendecomposition (covariance form of svd_whiten,
  * cca_zoo/_utils/_linalg.py:30-38; also B^-1/2 of cca_zoo/linear/_mcca.py:163-173 and R_i of
  * cca_zoo/linear/_gcca.py:101-105):
@@ -137,6 +148,20 @@ int ccab_ccaloss_small(int dtype, int d1, int d2, const void* C, int64_t ldc, do
 int ccab_potrf(int dtype, int n, void* A, int64_t lda, double pivot_tol, int* info_dev, void* stream);
 int ccab_trsm(int dtype, int side, int trans, int n, int m, const void* L, int64_t ldl, void* B, int64_t ldb,
               void* stream);
+
+/* Batched blocked Cholesky WITH the explicit inverse of the factor (the GEMM-friendly form of the whitening):
+ * for each of `batch` SPD matrices A_b = A + b * stride_a (n x n row-major, lower triangle referenced)
+ *   lower triangle of A_b <- L_b,   Linv_b = Linv + b * stride_i (n x n, ldi) <- L_b^-1 (zeros above the diagonal).
+ * info_dev[b] (device int[batch]) = 0 or the 1-based index of the first pivot <= pivot_tol.
+ * Diagonal blocks (128 wide for float, 64 for double) are factored AND inverted by one single-CTA launch each
+ * (warp-synchronous 32 x 32 sub-blocks); panels, trailing updates and the assembly of L^-1 by recursive doubling are
+ * GEMMs (tcgen05 for float).  With Linv,  T = L1^-1 C12 L2^-T  and the weights  L_i^-T U_k  are plain products.
+ * Replaces LAPACK potrf / trsm inside scipy.linalg.eigh(A, B) (cca_zoo/_utils/_linalg.py:67-71) and, in Cholesky
+ * form, the whitening of cca_zoo/_utils/_linalg.py:30-38 and _inv_sqrtm of cca_zoo/deep/objectives.py:9-21. */
+size_t ccab_potrf_inv_workspace_bytes(int dtype, int n, int batch);
+int ccab_potrf_inv(int dtype, int n, int batch, void* A, int64_t lda, int64_t stride_a, void* Linv, int64_t ldi,
+                   int64_t stride_i, double pivot_tol, int* info_dev, void* workspace, size_t workspace_bytes,
+                   void* stream);
 
 /* B[i,j] = A[i,j] * f(r[i]) * f(c[j]); r / c may be NULL; *_pow: 0 -> x, 1 -> 1/x, 2 -> 1/sqrt(x).
  * (column scalings such as diag(sigma)^-1/2 in the GCCA back-substitution, cca_zoo/linear/_gcca.py:109) */
