@@ -158,9 +158,13 @@ class BaseModel(BaseEstimator, ABC):
         mom.add_(part)
         return mom
 
-    def _covariance_stage(self, mom, n_local, dims, in_dtype, check_finite):
-        """All-reduce (if sharded), finalise the covariance, record the fitted metadata (_base.py:94-101)."""
-        mom, n_total = parallel.allreduce_moments(mom, n_local)
+    def _covariance_stage(self, mom, n_local, dims, in_dtype, check_finite, reduced=False):
+        """All-reduce (if sharded and not ``reduced`` already), finalise the covariance, record the fitted metadata
+        (_base.py:94-101)."""
+        if reduced:
+            n_total = int(n_local)
+        else:
+            mom, n_total = parallel.allreduce_moments(mom, n_local)
         # NaN / inf anywhere in the inputs poisons the moments: one tiny device-side check replaces the
         # reference's host scan (check_array) for tensors that never visit the host
         if check_finite and not bool(torch.isfinite(mom).all()):
@@ -193,6 +197,55 @@ class BaseModel(BaseEstimator, ABC):
         self._partial = None
         return self._covariance_stage(mom, n_local, dims, in_dtype, True)
 
+    # ------------------------------------------------------------------ device-side fit (the fit behind the C ABI)
+    def _device_fit_plan(self, dims, n_local, in_dtype):
+        """None, or the arguments of the estimator's device-side fit (csrc/fit.cu) when this problem qualifies."""
+        return None
+
+    def _fit_moments(self, mom, n_local, dims, in_dtype):
+        """From this process's moment buffer to ``weights_``: the exchange step, then either the device-side fit (one
+        asynchronous library call, one copy of the result block, no other host synchronisation) or -- when the
+        problem does not qualify or the device-side status word says so -- the host-assembled routes of
+        ``_solvers.py``."""
+        plan = self._device_fit_plan(dims, n_local, in_dtype)
+        if plan is None:
+            C, dims, n_total = self._covariance_stage(mom, n_local, dims, in_dtype, True)
+            return self._finish(self._solve(C, dims, n_total))
+        mom, n_host, n_dev = parallel.allreduce_moments_lazy(mom, n_local)
+        solve_dtype = torch.float64 if (self._solve_in_float64 or in_dtype == torch.float64) else torch.float32
+        attempts = plan.pop("iters")
+        hdr = None
+        for iters in attempts:
+            block, offsets = plan["call"](mom, dims, n_host, n_dev, solve_dtype, iters)
+            host = block.cpu()                                   # THE host synchronisation of the fit
+            hdr, mean, sig, ws = ops.decode_fit_block(host, offsets, dims, plan["k"], solve_dtype)
+            status = int(hdr[0])
+            if status & ops.FIT_NON_FINITE:
+                raise ValueError("Input contains NaN or infinity.")
+            if status == 0:
+                n_total = int(round(float(hdr[1])))
+                self.n_views_ = len(dims)
+                self.n_features_in_ = dims
+                self.n_samples_ = n_total
+                np_dtype = np.float32 if in_dtype == torch.float32 else np.float64
+                off = np.concatenate([[0], np.cumsum(dims)]).astype(int)
+                if self.center:
+                    self.means_ = [mean[off[i]:off[i + 1]].astype(np_dtype) for i in range(len(dims))]
+                else:
+                    self.means_ = [np.zeros(p) for p in dims]
+                self._second_moment = None
+                self.weights_ = [np.array(w) for w in ws]
+                self._fit_info = {"route": "device", "iters": iters, "residual": float(hdr[2]), "sigma_1": float(hdr[3]),
+                                  "ritz_sweeps": int(hdr[5])}
+                return self
+            if status != ops.FIT_NOT_CONVERGED:                  # only a missed tolerance is worth more iterations
+                break
+        # declined (a block is not positive definite, too few samples, no spectral gap): the host-assembled routes
+        n_total = int(round(float(hdr[1])))
+        C, dims, n_total = self._covariance_stage(mom, n_total, dims, in_dtype, False, reduced=True)
+        self._fit_info = {"route": "host", "device_status": int(hdr[0])}
+        return self._finish(self._solve(C, dims, n_total))
+
     def partial_fit(self, views, y=None, solve: bool = True):
         """Incremental fit on a batch of rows (a capability the reference lacks: its streaming answer is the
         stochastic EY family).  The block moments are additive over rows, so batches can arrive from disk or a
@@ -211,10 +264,9 @@ class BaseModel(BaseEstimator, ABC):
             n_local += state["n"]
         self._partial = {"mom": mom, "n": n_local, "dims": dims, "dtype": in_dtype}
         if solve:
-            C, dims, n_total = self._covariance_stage(mom.clone(), n_local, dims, in_dtype, True)
             if type(self)._requires_two_views and len(dims) != 2:
                 raise ValueError(f"rCCA requires exactly 2 views, got {len(dims)}. Use MCCA for more than 2 views.")
-            self._finish(self._solve(C, dims, n_total))
+            self._fit_moments(mom.clone(), n_local, dims, in_dtype)
         return self
 
     _requires_two_views: ClassVar[bool] = False

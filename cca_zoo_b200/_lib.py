@@ -33,6 +33,7 @@ SIGNATURES = {
     "ccab_syevj_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "ccab_syevj": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, C.c_int64, C.c_double, _vp, _vp, C.c_int64,
                              C.POINTER(C.c_int), C.POINTER(C.c_float), _vp, C.c_size_t, _vp]),
+    "ccab_syevj_small": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp]),
     "ccab_gesvj_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "ccab_gesvj": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int64, _vp, C.c_int64,
                              C.POINTER(C.c_int), C.POINTER(C.c_float), _vp, C.c_size_t, _vp]),
@@ -49,6 +50,10 @@ SIGNATURES = {
     "ccab_potrf_inv_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "ccab_potrf_inv": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64,
                                  C.c_double, _vp, _vp, C.c_size_t, _vp]),
+    "ccab_rcca_fit_workspace_bytes": (C.c_size_t, [C.c_int, _i64p, C.c_int, C.c_int]),
+    "ccab_rcca_fit_result_layout": (C.c_int, [C.c_int, _i64p, C.c_int, C.c_int, _i64p]),
+    "ccab_rcca_fit": (C.c_int, [C.c_int, _i64p, _vp, _vp, C.c_double, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int,
+                                C.c_int, _vp, C.c_size_t, _vp, C.c_size_t, _vp]),
     "ccab_trsm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp]),
     "ccab_scale": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int64,
                              _vp]),

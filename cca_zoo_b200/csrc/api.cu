@@ -12,8 +12,10 @@
 #include "cholinv.cuh"
 #include "common.cuh"
 #include "dense.cuh"
+#include "fit.cuh"
 #include "moments.cuh"
 #include "syevj.cuh"
+#include "syevj_small.cuh"
 #include "tgemm.cuh"
 
 namespace ccab {
@@ -178,6 +180,22 @@ int ccab_syevj(int dtype, int n, int batch, const void* A, int64_t lda, int64_t 
                           workspace_bytes, s);
   return syevj_t<double>(n, batch, A, lda, batch_stride, shift, evals, evecs_t, ldv, info, info_offdiag, workspace,
                          workspace_bytes, s);
+  CCAB_CATCH
+}
+
+int ccab_syevj_small(int dtype, int n, int batch, const void* A, int64_t lda, int64_t stride_a, void* evals,
+                     void* evecs_t, int64_t ldv, int* info_dev, void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(A != nullptr, "null pointer argument");
+  int rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CCAB_F32)
+    return syevj_small<float>(n, batch, static_cast<const float*>(A), lda, stride_a, static_cast<float*>(evals), n,
+                              static_cast<float*>(evecs_t), ldv, (int64_t)n * ldv, info_dev, s);
+  return syevj_small<double>(n, batch, static_cast<const double*>(A), lda, stride_a, static_cast<double*>(evals), n,
+                             static_cast<double*>(evecs_t), ldv, (int64_t)n * ldv, info_dev, s);
   CCAB_CATCH
 }
 
@@ -352,9 +370,9 @@ int ccab_potrf_inv(int dtype, int n, int batch, void* A, int64_t lda, int64_t st
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == CCAB_F32)
     return potrf_inv<float>(n, batch, static_cast<float*>(A), lda, stride_a, static_cast<float*>(Linv), ldi, stride_i,
-                            pivot_tol, info_dev, workspace, workspace_bytes, s);
+                            pivot_tol, nullptr, info_dev, workspace, workspace_bytes, s);
   return potrf_inv<double>(n, batch, static_cast<double*>(A), lda, stride_a, static_cast<double*>(Linv), ldi, stride_i,
-                           pivot_tol, info_dev, workspace, workspace_bytes, s);
+                           pivot_tol, nullptr, info_dev, workspace, workspace_bytes, s);
   CCAB_CATCH
 }
 
@@ -375,6 +393,41 @@ int ccab_trsm(int dtype, int side, int trans, int n, int m, const void* L, int64
   if (dtype == CCAB_F32)
     return trsm_right_lt<float>(n, m, static_cast<const float*>(L), ldl, static_cast<float*>(B), ldb, s);
   return trsm_right_lt<double>(n, m, static_cast<const double*>(L), ldl, static_cast<double*>(B), ldb, s);
+  CCAB_CATCH
+}
+
+size_t ccab_rcca_fit_workspace_bytes(int dtype, const int64_t* dims, int k, int p) {
+  if (!dims || dims[0] < 1 || dims[1] < 1 || k < 1 || p < k) return 0;
+  return dtype == CCAB_F32 ? rcca_fit_workspace_bytes<float>((int)dims[0], (int)dims[1], k, p)
+                           : rcca_fit_workspace_bytes<double>((int)dims[0], (int)dims[1], k, p);
+}
+
+int ccab_rcca_fit_result_layout(int dtype, const int64_t* dims, int k, int p, int64_t* offsets) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dims && offsets && dims[0] >= 1 && dims[1] >= 1 && k >= 1 && p >= k, "bad argument");
+  if (dtype == CCAB_F32) rcca_fit_result_layout<float>((int)dims[0], (int)dims[1], k, p, offsets);
+  else rcca_fit_result_layout<double>((int)dims[0], (int)dims[1], k, p, offsets);
+  return 0;
+  CCAB_CATCH
+}
+
+int ccab_rcca_fit(int dtype, const int64_t* dims, const double* moments, const double* n_total_dev, double n_total,
+                  int center, const double* c, int k, int p, int iters, void* result, size_t result_bytes,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(dims && moments && c && result && workspace, "null pointer argument");
+  ColumnLayout L;
+  int rc = make_layout(2, dims, &L);
+  if (rc) return rc;
+  rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CCAB_F32)
+    return rcca_fit<float>(L, moments, n_total_dev, n_total, center, c, k, p, iters, result, result_bytes, workspace,
+                           workspace_bytes, s);
+  return rcca_fit<double>(L, moments, n_total_dev, n_total, center, c, k, p, iters, result, result_bytes, workspace,
+                          workspace_bytes, s);
   CCAB_CATCH
 }
 

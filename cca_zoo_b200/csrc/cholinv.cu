@@ -45,10 +45,17 @@ struct DiagCfg<double> {
 };
 constexpr unsigned kFull = 0xffffffffu;
 
-// Warp-synchronous Cholesky + inverse of one 32 x 32 block held in shared memory at S[rb.., rb..] (row stride LD).
-// Lane i owns row i in registers.  Pivots of rows >= nb (padding: identity) are not tested.
+__device__ __forceinline__ float fast_rsqrt(float x) {
+  float r = rsqrtf(x);
+  return r * fmaf(-0.5f * x * r, r, 1.5f);   // one Newton step: ~1 ulp
+}
+__device__ __forceinline__ double fast_rsqrt(double x) { return 1.0 / sqrt(x); }
+
+// Warp-synchronous Cholesky of one 32 x 32 block held in shared memory at S[rb.., rb..] (row stride LD): lane i owns
+// row i in registers, column k is broadcast by shuffles.  dinv[rb + k] <- 1 / L_kk.  Pivots of rows >= nb (padding:
+// identity) are not tested.
 template <typename T, int LD>
-__device__ __forceinline__ void warp_chol_inv_32(T* S, T* X, int rb, int nb, int j0, T piv_tol, int* bad) {
+__device__ __forceinline__ void warp_chol_32(T* S, T* dinv_s, int rb, int nb, int j0, T piv_tol, int* bad) {
   const int lane = threadIdx.x & 31;
   T a[32];
 #pragma unroll
@@ -60,10 +67,10 @@ __device__ __forceinline__ void warp_chol_inv_32(T* S, T* X, int rb, int nb, int
       if (lane == 0 && *bad == 0) *bad = j0 + rb + k + 1;
       piv = T(1);
     }
-    const T d = sqrt(piv);
-    const T dinv = T(1) / d;
-    const T lik = lane > k ? a[k] * dinv : (lane == k ? d : T(0));
+    const T dinv = fast_rsqrt(piv);
+    const T lik = lane > k ? a[k] * dinv : (lane == k ? piv * dinv : T(0));
     a[k] = lik;
+    if (lane == k) dinv_s[rb + k] = dinv;
 #pragma unroll
     for (int j = k + 1; j < 32; ++j) {
       const T ljk = __shfl_sync(kFull, lik, j);
@@ -72,37 +79,86 @@ __device__ __forceinline__ void warp_chol_inv_32(T* S, T* X, int rb, int nb, int
   }
 #pragma unroll
   for (int j = 0; j < 32; ++j) S[(rb + lane) * LD + rb + j] = j <= lane ? a[j] : T(0);
-  // inverse: lane c computes column c of L^-1 by forward substitution (x_k = 0 for k < c)
+}
+
+// Inverse of the 32 x 32 lower-triangular block S[rb.., rb..]: lane c computes column c by forward substitution
+// (x_k = 0 for k < c), L read from shared memory (broadcast), result into X[rb.., rb..].
+template <typename T, int LD>
+__device__ __forceinline__ void warp_trinv_32(const T* S, const T* dinv_s, T* X, int rb) {
+  const int lane = threadIdx.x & 31;
   T x[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
-    T s = T(0);
+    T s = (lane == i) ? T(1) : T(0);
 #pragma unroll
-    for (int k = 0; k < i; ++k) {
-      const T lik = __shfl_sync(kFull, a[k], i);
-      s = fma(lik, x[k], s);
-    }
-    const T lii = __shfl_sync(kFull, a[i], i);
-    x[i] = ((lane == i ? T(1) : T(0)) - s) / lii;
+    for (int k = 0; k < i; ++k) s = fma(-S[(rb + i) * LD + rb + k], x[k], s);
+    x[i] = s * dinv_s[rb + i];
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) X[(rb + i) * LD + rb + lane] = x[i];
 }
 
+// C[r][c] (+)= sign * sum_{k in [k0, k1)} A(r, k) * B(k, c) for r in [0, M), c in [0, Nc), all in shared memory.
+// Warp-centric register tiling: a warp takes 4 rows at a time, lane l the columns l, l + 32, ... -- the A values are
+// warp broadcasts, the B values conflict-free; 4 + NT loads per 4 * NT FMAs.  BT: B(k, c) = Bm[c * ldb + k] (the
+// A A^T form of the trailing update) else Bm[k * ldb + c].  tri: 0 none, 1 = only c <= r is needed (lower part),
+// klo / khi: per-tile reduction bounds for triangular operands (see the callers).
+template <typename T, int NT, bool BT, typename KLo, typename KHi>
+__device__ __forceinline__ void smem_mm(T* Cm, int ldc, const T* Am, int lda, const T* Bm, int ldb, int M, int Nc,
+                                        T sign, bool accumulate, bool lower_only, KLo klo, KHi khi, int nthreads) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = nthreads >> 5;
+  for (int r0 = warp * 4; r0 < M; r0 += nwarps * 4) {
+    T acc[4][NT];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) acc[i][j] = T(0);
+    const int kb = klo(r0), ke = khi(r0);
+    for (int k = kb; k < ke; ++k) {
+      T a[4], b[NT];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = (r0 + i < M) ? Am[(r0 + i) * lda + k] : T(0);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int c = lane + 32 * j;
+        b[j] = (c < Nc) ? (BT ? Bm[c * ldb + k] : Bm[k * ldb + c]) : T(0);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int r = r0 + i, c = lane + 32 * j;
+        if (r < M && c < Nc && (!lower_only || c <= r)) {
+          const T v = sign * acc[i][j];
+          Cm[r * ldc + c] = accumulate ? Cm[r * ldc + c] + v : v;
+        }
+      }
+  }
+}
+
 template <typename T, int NB, int kDiagThreads>
 __global__ void __launch_bounds__(kDiagThreads, 1)
 chol_diag_inv_kernel(T* __restrict__ A, int64_t lda, int64_t strideA, int nb, int j0, T* __restrict__ Dinv,
-                     int64_t strideDinv, double piv_tol, int* __restrict__ info) {
+                     int64_t strideDinv, double piv_tol, const double* __restrict__ piv_tol_dev,
+                     int* __restrict__ info) {
   constexpr int LD = NB + 1;
   constexpr int HB = NB / 2;
+  constexpr int NSUB = NB / 32;
   extern __shared__ __align__(16) unsigned char cdi_smem[];
   T* S = reinterpret_cast<T*>(cdi_smem);
   T* X = S + NB * LD;
   T* Tm = X + NB * LD;            // [HB][HB + 1]
+  T* dinv_s = Tm + HB * (HB + 1); // [NB]
   __shared__ int bad;
   T* Ab = A + (size_t)blockIdx.x * strideA;
   T* Db = Dinv + (size_t)blockIdx.x * strideDinv;
   const int tid = threadIdx.x;
+  const T tol = (T)(piv_tol_dev ? piv_tol_dev[blockIdx.x] : piv_tol);
   if (tid == 0) bad = 0;
   for (int e = tid; e < NB * NB; e += kDiagThreads) {
     const int r = e / NB, c = e % NB;
@@ -111,73 +167,71 @@ chol_diag_inv_kernel(T* __restrict__ A, int64_t lda, int64_t strideA, int nb, in
     S[r * LD + c] = v;
     X[r * LD + c] = T(0);
   }
+  if (tid < NB) dinv_s[tid] = T(1);
   __syncthreads();
 
   const int nsub = (nb + 31) / 32;
-  for (int jb = 0; jb < NB / 32; ++jb) {
+  for (int jb = 0; jb < nsub; ++jb) {
     const int rb = jb * 32;
-    if (jb < nsub) {
-      if (tid < 32) warp_chol_inv_32<T, LD>(S, X, rb, nb, j0, (T)piv_tol, &bad);
-    } else if (tid < 32) {
-      X[(rb + tid) * LD + rb + tid] = T(1);     // padding block: L = I, L^-1 = I
-    }
+    if (tid < 32) warp_chol_32<T, LD>(S, dinv_s, rb, nb, j0, tol, &bad);
     __syncthreads();
-    if (jb + 1 >= nsub) continue;               // nothing below / to the right (uniform)
+    if (jb + 1 >= nsub) break;                  // nothing below / to the right
     const int r0 = rb + 32;
-    const int R = NB - r0;
-    // ---- panel: P[r][c] = sum_{k <= c} S[r][rb + k] * X[rb + c][rb + k]   (= A_panel * L32^-T) ----
-    {
-      constexpr int kGroups = kDiagThreads / 32;
-      constexpr int kMaxRows = (NB - 32 + kGroups - 1) / kGroups;
-      T out[kMaxRows];
-      const int c = tid & 31, g = tid >> 5;
+    const int R = nsub * 32 - r0;               // rows that hold data
+    // ---- panel: row r of the block column <- a_r L_jj^-T by forward substitution, one thread per row ----
+    if (tid < R) {
+      T* row = S + (r0 + tid) * LD + rb;
+      T a[32];
 #pragma unroll
-      for (int q = 0; q < kMaxRows; ++q) {
-        const int r = r0 + g + kGroups * q;
-        T acc = T(0);
-        if (r < NB) {
-          for (int k = 0; k <= c; ++k) acc = fma(S[r * LD + rb + k], X[(rb + c) * LD + rb + k], acc);
-        }
-        out[q] = acc;
-      }
-      __syncthreads();
+      for (int c = 0; c < 32; ++c) a[c] = row[c];
 #pragma unroll
-      for (int q = 0; q < kMaxRows; ++q) {
-        const int r = r0 + g + kGroups * q;
-        if (r < NB) S[r * LD + rb + c] = out[q];
+      for (int c = 0; c < 32; ++c) {
+        T v = a[c];
+#pragma unroll
+        for (int k = 0; k < c; ++k) v = fma(-a[k], S[(rb + c) * LD + rb + k], v);   // warp broadcast
+        a[c] = v * dinv_s[rb + c];
       }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) row[c] = a[c];
     }
     __syncthreads();
     // ---- trailing update (lower part): S[r][c] -= sum_k P[r][k] P[c][k] ----
-    for (int e = tid; e < R * R; e += kDiagThreads) {
-      const int r = r0 + e / R, c = r0 + e % R;
-      if (c > r) continue;
-      T acc = T(0);
-#pragma unroll 8
-      for (int k = 0; k < 32; ++k) acc = fma(S[r * LD + rb + k], S[c * LD + rb + k], acc);
-      S[r * LD + c] -= acc;
-    }
+    smem_mm<T, NSUB - 1, true>(S + r0 * LD + r0, LD, S + r0 * LD + rb, LD, S + r0 * LD + rb, LD, R, R, T(-1), true,
+                               true, [](int) { return 0; }, [](int) { return 32; }, kDiagThreads);
     __syncthreads();
   }
 
-  // ---- inverse, off-diagonal sub-blocks by recursive doubling: X_BA = -X_BB (L_BA X_AA) ----
+  // ---- inverse: the diagonal sub-blocks by one warp each ... ----
+  if (tid < 32 * NSUB) {
+    const int w = tid >> 5;
+    if (w < nsub) warp_trinv_32<T, LD>(S, dinv_s, X, w * 32);
+    else if ((tid & 31) == 0)
+      for (int i = 0; i < 32; ++i) X[(w * 32 + i) * LD + w * 32 + i] = T(1);    // padding block: identity
+  }
+  __syncthreads();
+  // ---- ... the off-diagonal sub-blocks by recursive doubling: X_BA = -X_BB (L_BA X_AA) ----
   for (int s = 32; s < NB; s *= 2) {
     const int npairs = NB / (2 * s);
-    const int total = npairs * s * s;
-    for (int e = tid; e < total; e += kDiagThreads) {
-      const int pi = e / (s * s), rr = (e / s) % s, cc = e % s;
+    for (int pi = 0; pi < npairs; ++pi) {
       const int a0 = 2 * pi * s, b0 = a0 + s;
-      T acc = T(0);
-      for (int k = cc; k < s; ++k) acc = fma(S[(b0 + rr) * LD + a0 + k], X[(a0 + k) * LD + a0 + cc], acc);
-      Tm[(pi * s + rr) * (HB + 1) + cc] = acc;
+      // Tm = L_BA X_AA: X_AA is lower triangular, column c needs k >= c only -- a 4-row tile shares the bound 0
+      if (s == 32)
+        smem_mm<T, 1, false>(Tm + pi * s * (HB + 1), HB + 1, S + b0 * LD + a0, LD, X + a0 * LD + a0, LD, s, s, T(1),
+                             false, false, [](int) { return 0; }, [s](int) { return s; }, kDiagThreads);
+      else
+        smem_mm<T, 2, false>(Tm + pi * s * (HB + 1), HB + 1, S + b0 * LD + a0, LD, X + a0 * LD + a0, LD, s, s, T(1),
+                             false, false, [](int) { return 0; }, [s](int) { return s; }, kDiagThreads);
     }
     __syncthreads();
-    for (int e = tid; e < total; e += kDiagThreads) {
-      const int pi = e / (s * s), rr = (e / s) % s, cc = e % s;
+    for (int pi = 0; pi < npairs; ++pi) {
       const int a0 = 2 * pi * s, b0 = a0 + s;
-      T acc = T(0);
-      for (int k = 0; k <= rr; ++k) acc = fma(X[(b0 + rr) * LD + b0 + k], Tm[(pi * s + k) * (HB + 1) + cc], acc);
-      X[(b0 + rr) * LD + a0 + cc] = -acc;
+      // X_BA = -X_BB Tm: X_BB lower triangular, row r needs k <= r only
+      if (s == 32)
+        smem_mm<T, 1, false>(X + b0 * LD + a0, LD, X + b0 * LD + b0, LD, Tm + pi * s * (HB + 1), HB + 1, s, s, T(-1),
+                             false, false, [](int) { return 0; }, [s](int r0) { return min(s, r0 + 4); }, kDiagThreads);
+      else
+        smem_mm<T, 2, false>(X + b0 * LD + a0, LD, X + b0 * LD + b0, LD, Tm + pi * s * (HB + 1), HB + 1, s, s, T(-1),
+                             false, false, [](int) { return 0; }, [s](int r0) { return min(s, r0 + 4); }, kDiagThreads);
     }
     __syncthreads();
   }
@@ -209,11 +263,11 @@ __global__ void linv_init_kernel(T* __restrict__ Linv, int64_t ldi, int64_t stri
 
 template <typename T>
 int potrf_inv_block(T* A, int64_t lda, int64_t strideA, int nb, int j0, T* Dinv, int64_t strideDinv, double piv_tol,
-                    int* info, int batch, cudaStream_t stream) {
+                    const double* piv_tol_dev, int* info, int batch, cudaStream_t stream) {
   constexpr int NB = DiagCfg<T>::NB;
   constexpr int kDiagThreads = DiagCfg<T>::kThreads;
   CCAB_CHECK_ARG(nb >= 1 && nb <= NB, "diagonal block of %d exceeds %d", nb, NB);
-  const size_t smem = sizeof(T) * (2 * NB * (NB + 1) + (NB / 2) * (NB / 2 + 1));
+  const size_t smem = sizeof(T) * (2 * NB * (NB + 1) + (NB / 2) * (NB / 2 + 1) + NB);
   static bool attr_done[64] = {};
   int dev = 0;
   CCAB_CUDA(cudaGetDevice(&dev));
@@ -222,7 +276,7 @@ int potrf_inv_block(T* A, int64_t lda, int64_t strideA, int nb, int j0, T* Dinv,
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   chol_diag_inv_kernel<T, NB, kDiagThreads><<<batch, kDiagThreads, smem, stream>>>(A, lda, strideA, nb, j0, Dinv, strideDinv, piv_tol,
-                                                                    info);
+                                                                                  piv_tol_dev, info);
   count_launches(1);
   CCAB_CUDA(cudaGetLastError());
   return 0;
@@ -244,7 +298,7 @@ size_t potrf_inv_workspace_bytes(int n, int batch) {
 
 template <typename T>
 int potrf_inv(int n, int batch, T* A, int64_t lda, int64_t strideA, T* Linv, int64_t ldi, int64_t strideLinv,
-              double piv_tol, int* info, void* ws, size_t ws_bytes, cudaStream_t stream) {
+              double piv_tol, const double* piv_tol_dev, int* info, void* ws, size_t ws_bytes, cudaStream_t stream) {
   constexpr int NB = DiagCfg<T>::NB;
   CCAB_CHECK_ARG(n >= 1 && batch >= 1 && lda >= n && ldi >= n, "bad potrf_inv shape");
   CCAB_CHECK_ARG(ws_bytes >= potrf_inv_workspace_bytes<T>(n, batch), "potrf_inv workspace too small");
@@ -260,7 +314,7 @@ int potrf_inv(int n, int batch, T* A, int64_t lda, int64_t strideA, T* Linv, int
   for (int jb = 0; jb < nblk; ++jb) {
     const int j0 = jb * NB, nb = std::min(NB, n - j0);
     int rc = potrf_inv_block<T>(A + (size_t)j0 * lda + j0, lda, strideA, nb, j0, Dinv + (size_t)jb * NB * NB, strideD,
-                                piv_tol, info, batch, stream);
+                                piv_tol, piv_tol_dev, info, batch, stream);
     if (rc) return rc;
     const int rows = n - j0 - nb;
     if (rows <= 0) continue;
@@ -360,16 +414,17 @@ int potrf_panel_gemm(const GemmArgs<T>& g, T* scratch, int64_t strideScratch, cu
   return 0;
 }
 
-template int potrf_inv<float>(int, int, float*, int64_t, int64_t, float*, int64_t, int64_t, double, int*, void*, size_t,
-                              cudaStream_t);
-template int potrf_inv<double>(int, int, double*, int64_t, int64_t, double*, int64_t, int64_t, double, int*, void*,
-                               size_t, cudaStream_t);
+template int potrf_inv<float>(int, int, float*, int64_t, int64_t, float*, int64_t, int64_t, double, const double*, int*,
+                              void*, size_t, cudaStream_t);
+template int potrf_inv<double>(int, int, double*, int64_t, int64_t, double*, int64_t, int64_t, double, const double*,
+                               int*, void*, size_t, cudaStream_t);
 template size_t potrf_inv_workspace_bytes<float>(int, int);
 template size_t potrf_inv_workspace_bytes<double>(int, int);
 template int potrf_inv_block_size<float>();
 template int potrf_inv_block_size<double>();
-template int potrf_inv_block<float>(float*, int64_t, int64_t, int, int, float*, int64_t, double, int*, int, cudaStream_t);
-template int potrf_inv_block<double>(double*, int64_t, int64_t, int, int, double*, int64_t, double, int*, int,
-                                     cudaStream_t);
+template int potrf_inv_block<float>(float*, int64_t, int64_t, int, int, float*, int64_t, double, const double*, int*,
+                                    int, cudaStream_t);
+template int potrf_inv_block<double>(double*, int64_t, int64_t, int, int, double*, int64_t, double, const double*, int*,
+                                     int, cudaStream_t);
 
 }  // namespace ccab

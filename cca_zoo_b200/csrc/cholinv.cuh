@@ -13,7 +13,8 @@ template <typename T>
 size_t potrf_inv_workspace_bytes(int n, int batch);
 template <typename T>
 int potrf_inv(int n, int batch, T* A, int64_t lda, int64_t strideA, T* Linv, int64_t ldi, int64_t strideLinv,
-              double piv_tol, int* info, void* ws, size_t ws_bytes, cudaStream_t stream);
+              double piv_tol, const double* piv_tol_dev /* device, [batch], overrides piv_tol when non-NULL */, int* info,
+              void* ws, size_t ws_bytes, cudaStream_t stream);
 
 // One diagonal block (nb <= potrf_inv_block_size<T>()) per matrix, single launch: factor in place and write the
 // dense NB x NB inverse (leading dimension NB, zero padded) to Dinv + b * strideDinv.  info is NOT cleared here.
@@ -21,6 +22,6 @@ template <typename T>
 int potrf_inv_block_size();
 template <typename T>
 int potrf_inv_block(T* A, int64_t lda, int64_t strideA, int nb, int j0, T* Dinv, int64_t strideDinv, double piv_tol,
-                    int* info, int batch, cudaStream_t stream);
+                    const double* piv_tol_dev, int* info, int batch, cudaStream_t stream);
 
 }  // namespace ccab

@@ -1,0 +1,449 @@
+// Fit assembly on the device: from the (all-reduced) moment buffer to the weights, as ONE asynchronous call per
+// estimator -- no host read-back between the moment pass and the result (the fit behind the C ABI).
+//
+//   rcca_fit : cca_zoo/linear/_rcca.py:83-101 in covariance / Cholesky form
+//       C = (M - s s^T / n) / (n - 1)                      cov_ridge_kernel (also R_i = (1-c_i) C_ii + c_i I, max diag,
+//                                                           finiteness flag; n is read from device memory)
+//       R_i = L_i L_i^T, Linv_i = L_i^-1                    potrf_inv (cholinv.cu), both views batched when d1 == d2
+//       T = Linv_1 C_12 Linv_2^T                            2 GEMMs (tgemm.cu for float)
+//       leading k singular triplets of T                    blocked subspace iteration: Z <- orth(T^T T Z) with CholQR
+//                                                           (Gram GEMM + single-launch Cholesky/inverse + GEMM), then
+//                                                           Rayleigh-Ritz through the single-CTA Jacobi eigensolver
+//       weights_i = Linv_i^T U_k / V_k                      2 GEMMs, written into the result block
+//   Every decision the host used to take from a read-back (pivot failures, CholQR rank loss, convergence of the
+//   iteration, finiteness of the input, n > d) is written into the header of the result block instead; the host copies
+//   the block once, checks the status word and re-runs through the eigen route when it is non-zero.
+#include "fit.cuh"
+
+#include <cmath>
+#include <type_traits>
+
+#include "cholinv.cuh"
+#include "dense.cuh"
+#include "moments.cuh"
+#include "syevj_small.cuh"
+
+namespace ccab {
+
+namespace {
+
+inline size_t al256(size_t x) { return (x + 255) & ~size_t(255); }
+inline int64_t r4(int64_t x) { return (x + 3) & ~int64_t(3); }
+
+struct CovRidgeParams {
+  int n_views, D, Dp;
+  int dims[kMaxViews];
+  int coff[kMaxViews + 1];
+  int poff[kMaxViews + 1];
+  double c[kMaxViews];
+  void* R[kMaxViews];          // ridge block of view v (may be NULL)
+  long long ldr[kMaxViews];
+};
+struct PivotTolParams {
+  int n_views;
+  double c[kMaxViews], rank_tol[kMaxViews];
+};
+
+__device__ __forceinline__ int view_of(const CovRidgeParams& p, int g) {
+  int v = 0;
+  while (v + 1 < p.n_views && p.coff[v + 1] <= g) ++v;
+  return v;
+}
+
+// C (D x D, ldc) = covariance from the moments; R_v (dims[v] x dims[v], ldr[v]) = (1 - c_v) C_vv + c_v I;
+// dmax[v] = max diag(C_vv) (float bits, atomicMax: non-negative values order like integers); flags[0] |= 1 when a
+// moment is not finite; mean (double[D]).
+template <typename T>
+__global__ void cov_ridge_kernel(const CovRidgeParams p, const double* __restrict__ mom, const double* __restrict__ n_dev,
+                                 double n_host, int center, T* __restrict__ C, int64_t ldc, double* __restrict__ mean,
+                                 unsigned* __restrict__ dmax, int* __restrict__ flags) {
+  const double n_total = n_dev ? n_dev[0] : n_host;
+  const double* M = mom;
+  const double* s = mom + (size_t)p.Dp * p.Dp;
+  const int gi = blockIdx.y * blockDim.y + threadIdx.y;
+  const int gj = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= p.D || gj >= p.D) return;
+  const int vi = view_of(p, gi), vj = view_of(p, gj);
+  const int pi = p.poff[vi] + gi - p.coff[vi], pj = p.poff[vj] + gj - p.coff[vj];
+  const int r = min(pi, pj), c = max(pi, pj);
+  double v = M[(size_t)r * p.Dp + c];
+  if (!isfinite(v)) atomicOr(flags, 1);
+  if (center) v -= s[pi] * s[pj] / n_total;
+  v /= (n_total - 1.0);
+  C[(size_t)gi * ldc + gj] = (T)v;
+  if (vi == vj && p.R[vi]) {
+    const double cv = p.c[vi];
+    const double rv = (1.0 - cv) * v + (gi == gj ? cv : 0.0);
+    static_cast<T*>(p.R[vi])[(size_t)(gi - p.coff[vi]) * p.ldr[vi] + (gj - p.coff[vj])] = (T)rv;
+    if (gi == gj && dmax) atomicMax(dmax + vi, __float_as_uint(fmaxf((float)v, 0.f)));
+  }
+  if (gi == 0 && mean) mean[gj] = center ? s[pj] / n_total : 0.0;
+  if (gi == 0 && gj == 0 && !(n_total >= 2.0)) atomicOr(flags, 2);
+}
+
+// pivot tolerance of view v: rank_tol_v * ((1 - c_v) dmax_v + c_v)   (the covariance-space image of the reference's
+// s > 0 filter on the regularised spectrum, _solvers._rank_tol)
+__global__ void pivot_tol_kernel(const PivotTolParams q, const unsigned* __restrict__ dmax, double* __restrict__ tol) {
+  const int v = threadIdx.x;
+  if (v < q.n_views) tol[v] = q.rank_tol[v] * ((1.0 - q.c[v]) * (double)__uint_as_float(dmax[v]) + q.c[v]);
+}
+
+// counter-based standard normal start block (splitmix64 hash + Box-Muller): reproducible, no generator state
+template <typename T>
+__global__ void randn_kernel(T* __restrict__ Z, int64_t ld, int rows, int cols, unsigned long long seed) {
+  const size_t total = (size_t)rows * cols;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (e + 1);
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    const double u1 = ((double)(unsigned)(x >> 32) + 1.0) * (1.0 / 4294967297.0);
+    const double u2 = (double)(unsigned)(x & 0xffffffffu) * (1.0 / 4294967296.0);
+    const double g = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    Z[(e / cols) * ld + (e % cols)] = (T)g;
+  }
+}
+
+// sig_j = sqrt(max(lam_j, 0)) for j < k; U[:, j] *= 1 / sig_j (0 when sig_j == 0)
+template <typename T>
+__global__ void ritz_scale_kernel(T* __restrict__ U, int64_t ldu, int rows, int k, const T* __restrict__ lam,
+                                  T* __restrict__ sig) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= k) return;
+  const T s = sqrt(fmax(lam[j], T(0)));
+  if (i == 0 && sig) sig[j] = s;
+  U[(size_t)i * ldu + j] *= s > T(0) ? T(1) / s : T(0);
+}
+
+// stats[0] = || E - V diag(sig) ||_F^2, stats[1] = sig_0 (single block, fixed order: deterministic)
+template <typename T>
+__global__ void residual_kernel(const T* __restrict__ E, int64_t lde, const T* __restrict__ V, int64_t ldv, int rows,
+                                int k, const T* __restrict__ sig, double* __restrict__ stats) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < rows * k; e += blockDim.x) {
+    const int i = e / k, j = e % k;
+    const double d = (double)E[(size_t)i * lde + j] - (double)V[(size_t)i * ldv + j] * (double)sig[j];
+    acc += d * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    stats[0] = t;
+    stats[1] = (double)sig[0];
+  }
+}
+
+// header of the result block: see FitHeader in fit.cuh
+__global__ void fit_status_kernel(double* __restrict__ hdr, const int* __restrict__ flags, const int* __restrict__ infos,
+                                  int n_infos, const int* __restrict__ rr_info, const double* __restrict__ stats,
+                                  const double* __restrict__ n_dev, double n_host, double resid_tol, int k, int max_d) {
+  if (threadIdx.x != 0) return;
+  const double n_total = n_dev ? n_dev[0] : n_host;
+  int status = 0;
+  if (flags[0] & 1) status |= kFitNonFinite;
+  if (flags[0] & 2) status |= kFitTooFewSamples;
+  int first_bad = 0;
+  for (int i = 0; i < n_infos; ++i)
+    if (infos[i] != 0 && !first_bad) first_bad = i + 1;
+  if (first_bad) status |= kFitNotPositiveDefinite;
+  const double resid = sqrt(fmax(stats[0], 0.0)), s1 = stats[1];
+  if (!(s1 > 0.0) || !(resid <= resid_tol * s1 * sqrt((double)k))) status |= kFitNotConverged;
+  if (rr_info && rr_info[0] <= 0) status |= kFitNotConverged;
+  if (!(n_total > (double)max_d)) status |= kFitTooFewSamples;
+  hdr[0] = (double)status;
+  hdr[1] = n_total;
+  hdr[2] = resid;
+  hdr[3] = s1;
+  hdr[4] = (double)first_bad;
+  hdr[5] = rr_info ? (double)rr_info[0] : 0.0;
+}
+
+template <typename T>
+double eps_of() {
+  return std::is_same<T, float>::value ? 1.1920928955078125e-7 : 2.220446049250313e-16;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CholQR: Zout (rows x p) = Zin * chol(Zin^T Zin)^-T ; info slot must be zero on entry
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct CholQrWs {
+  T* G;      // p x ldg
+  T* Ginv;   // max(p, NB) square
+  void* pws;
+  size_t pws_bytes;
+  int64_t ldg;
+};
+
+template <typename T>
+int cholqr(const T* Zin, int64_t ldz, T* Zout, int64_t ldo, int rows, int p, const CholQrWs<T>& w, int* info,
+           cudaStream_t s) {
+  GemmArgs<T> g;
+  g.transa = 1; g.m = p; g.n = p; g.k = rows;
+  g.A = Zin; g.lda = ldz; g.B = Zin; g.ldb = ldz; g.C = w.G; g.ldc = w.ldg;
+  int rc = xgemm<T>(g, s);
+  if (rc) return rc;
+  const int NB = potrf_inv_block_size<T>();
+  int64_t ldi;
+  if (p <= NB) {
+    rc = potrf_inv_block<T>(w.G, w.ldg, 0, p, 0, w.Ginv, 0, 0.0, nullptr, info, 1, s);
+    ldi = NB;
+  } else {
+    int* tmp_info = info;   // potrf_inv clears its info slot itself: accumulate through a scratch int
+    rc = potrf_inv<T>(p, 1, w.G, w.ldg, 0, w.Ginv, w.ldg, 0, 0.0, nullptr, tmp_info, w.pws, w.pws_bytes, s);
+    ldi = w.ldg;
+  }
+  if (rc) return rc;
+  GemmArgs<T> q;   // Zout = Zin * Ginv^T
+  q.transb = 1; q.m = rows; q.n = p; q.k = p;
+  q.A = Zin; q.lda = ldz; q.B = w.Ginv; q.ldb = ldi; q.C = Zout; q.ldc = ldo;
+  return xgemm<T>(q, s);
+}
+
+struct RccaPlan {
+  int d1, d2, D, k, p;
+  int64_t ldC, ld1, ld2, ldT, ldp, ldk;
+  size_t oC, oR, oLinv, oT1, oT, oZ, oZ2, oY, oG, oGinv, oH, oLam, oVy, oU, oV, oE, oPws, oSmall, total;
+  size_t pws_bytes;
+  size_t r_mean, r_sig, r_w1, r_w2, r_total;
+};
+
+template <typename T>
+RccaPlan make_rcca_plan(int d1, int d2, int k, int p) {
+  RccaPlan P;
+  P.d1 = d1; P.d2 = d2; P.D = d1 + d2; P.k = k; P.p = p;
+  P.ldC = r4(P.D); P.ld1 = r4(d1); P.ld2 = r4(d2); P.ldT = r4(d2); P.ldp = r4(p); P.ldk = r4(k);
+  const int NB = potrf_inv_block_size<T>();
+  const int dm = std::max(d1, d2);
+  size_t o = 0;
+  auto take = [&](size_t elems) { size_t at = o; o += al256(elems * sizeof(T)); return at; };
+  P.oC = take((size_t)P.D * P.ldC);
+  // the two ridge blocks / inverses as ONE strided batch when the views have the same width
+  P.oR = take(2 * (size_t)dm * r4(dm));
+  P.oLinv = take(2 * (size_t)dm * r4(dm));
+  P.oT1 = take((size_t)d1 * P.ldT);
+  P.oT = take((size_t)d1 * P.ldT);
+  P.oZ = take((size_t)d2 * P.ldp);
+  P.oZ2 = take((size_t)d2 * P.ldp);
+  P.oY = take((size_t)d1 * P.ldp);
+  P.oG = take((size_t)p * P.ldp);
+  P.oGinv = take((size_t)std::max(p, NB) * std::max<int64_t>(P.ldp, NB));
+  P.oH = take((size_t)p * P.ldp);
+  P.oLam = take((size_t)p);
+  P.oVy = take((size_t)p * P.ldp);
+  P.oU = take((size_t)d1 * P.ldk);
+  P.oV = take((size_t)d2 * P.ldk);
+  P.oE = take((size_t)d2 * P.ldk);
+  P.pws_bytes = std::max(potrf_inv_workspace_bytes<T>(dm, 2), potrf_inv_workspace_bytes<T>(p, 1));
+  P.oPws = o; o += al256(P.pws_bytes);
+  P.oSmall = o; o += 4096;   // flags, infos, dmax, tolerances, stats, device pointer tables
+  P.total = o + 256;
+  size_t r = sizeof(double) * kFitHeaderDoubles;
+  P.r_mean = r; r += al256(sizeof(double) * P.D);
+  P.r_sig = r; r += al256(sizeof(T) * k);
+  P.r_w1 = r; r += al256(sizeof(T) * (size_t)d1 * k);
+  P.r_w2 = r; r += al256(sizeof(T) * (size_t)d2 * k);
+  P.r_total = r;
+  return P;
+}
+
+}  // namespace
+
+template <typename T>
+size_t rcca_fit_workspace_bytes(int d1, int d2, int k, int p) {
+  return make_rcca_plan<T>(d1, d2, k, p).total;
+}
+
+template <typename T>
+void rcca_fit_result_layout(int d1, int d2, int k, int p, int64_t* offsets) {
+  RccaPlan P = make_rcca_plan<T>(d1, d2, k, p);
+  offsets[0] = (int64_t)P.r_mean;
+  offsets[1] = (int64_t)P.r_sig;
+  offsets[2] = (int64_t)P.r_w1;
+  offsets[3] = (int64_t)P.r_w2;
+  offsets[4] = (int64_t)P.r_total;
+}
+
+template <typename T>
+int rcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, double n_host, int center,
+             const double* c, int k, int p, int iters, void* result, size_t result_bytes, void* ws, size_t ws_bytes,
+             cudaStream_t s) {
+  CCAB_CHECK_ARG(L.n_views == 2, "rcca_fit needs exactly 2 views");
+  const int d1 = L.dims[0], d2 = L.dims[1], D = L.D;
+  CCAB_CHECK_ARG(k >= 1 && p >= k && p <= std::min(d1, d2), "rcca_fit: need 1 <= k <= p <= min(d1, d2), got k=%d p=%d", k,
+                 p);
+  CCAB_CHECK_ARG(syevj_small_supported<T>(p), "rcca_fit: subspace width %d exceeds the single-CTA eigensolver", p);
+  CCAB_CHECK_ARG(iters >= 1 && iters <= 64, "rcca_fit: bad iteration count %d", iters);
+  RccaPlan P = make_rcca_plan<T>(d1, d2, k, p);
+  CCAB_CHECK_ARG(ws_bytes >= P.total, "rcca_fit workspace too small: %zu < %zu", ws_bytes, P.total);
+  CCAB_CHECK_ARG(result_bytes >= P.r_total, "rcca_fit result block too small: %zu < %zu", result_bytes, P.r_total);
+  uint8_t* w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  uint8_t* res = static_cast<uint8_t*>(result);
+  CCAB_CHECK_ARG((reinterpret_cast<uintptr_t>(res) & 255) == 0, "rcca_fit: result block must be 256-byte aligned");
+  auto at = [&](size_t off) { return reinterpret_cast<T*>(w + off); };
+  T* C = at(P.oC);
+  const bool batched = d1 == d2;
+  const int64_t ldR = r4(std::max(d1, d2));
+  const int64_t strideR = (int64_t)std::max(d1, d2) * ldR;
+  T* R1 = at(P.oR);
+  T* R2 = R1 + strideR;
+  T* Li1 = at(P.oLinv);
+  T* Li2 = Li1 + strideR;
+  const int64_t ldr1 = batched ? ldR : P.ld1, ldr2 = batched ? ldR : P.ld2;
+  T *T1 = at(P.oT1), *Tm = at(P.oT), *Z = at(P.oZ), *Z2 = at(P.oZ2), *Y = at(P.oY), *H = at(P.oH), *lam = at(P.oLam),
+    *Vy = at(P.oVy), *U = at(P.oU), *V = at(P.oV), *E = at(P.oE);
+  CholQrWs<T> cq;
+  cq.G = at(P.oG);
+  cq.Ginv = at(P.oGinv);
+  cq.pws = w + P.oPws;
+  cq.pws_bytes = P.pws_bytes;
+  cq.ldg = P.ldp;
+  // small device scratch
+  uint8_t* sm = w + P.oSmall;
+  int* flags = reinterpret_cast<int*>(sm);                     // [1]
+  int* infos = flags + 4;                                      // [2 + iters + 2] potrf, CholQR passes
+  const int n_infos = 2 + iters + 2;
+  int* rr_info = infos + 80;                                   // [1]
+  unsigned* dmax = reinterpret_cast<unsigned*>(sm + 512);      // [2]
+  double* tol = reinterpret_cast<double*>(sm + 1024);          // [2]
+  double* stats = tol + 8;                                     // [2]
+
+  CCAB_CUDA(cudaMemsetAsync(sm, 0, 2048, s));
+  double* hdr = reinterpret_cast<double*>(res);
+  double* mean = reinterpret_cast<double*>(res + P.r_mean);
+  T* sig = reinterpret_cast<T*>(res + P.r_sig);
+  T* W1 = reinterpret_cast<T*>(res + P.r_w1);
+  T* W2 = reinterpret_cast<T*>(res + P.r_w2);
+
+  // ---- covariance + ridge blocks ----
+  {
+    CovRidgeParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.n_views = 2; cp.D = D; cp.Dp = L.Dp;
+    for (int v = 0; v < 2; ++v) { cp.dims[v] = L.dims[v]; cp.c[v] = c[v]; }
+    for (int v = 0; v <= 2; ++v) { cp.coff[v] = L.coff[v]; cp.poff[v] = L.poff[v]; }
+    cp.R[0] = R1; cp.R[1] = R2; cp.ldr[0] = ldr1; cp.ldr[1] = ldr2;
+    dim3 block(32, 8), grid((unsigned)ceil_div(D, 32), (unsigned)ceil_div(D, 8));
+    cov_ridge_kernel<T><<<grid, block, 0, s>>>(cp, moments, n_dev, n_host, center, C, P.ldC, mean, dmax, flags);
+    count_launches(1);
+    PivotTolParams q;
+    memset(&q, 0, sizeof(q));
+    q.n_views = 2;
+    q.c[0] = c[0]; q.c[1] = c[1];
+    q.rank_tol[0] = d1 * eps_of<T>(); q.rank_tol[1] = d2 * eps_of<T>();
+    pivot_tol_kernel<<<1, 32, 0, s>>>(q, dmax, tol);
+    count_launches(1);
+    CCAB_CUDA(cudaGetLastError());
+  }
+  // ---- Cholesky + inverse of both ridge blocks ----
+  int rc;
+  if (batched) {
+    rc = potrf_inv<T>(d1, 2, R1, ldR, strideR, Li1, ldR, strideR, 0.0, tol, infos, cq.pws, cq.pws_bytes, s);
+    if (rc) return rc;
+  } else {
+    rc = potrf_inv<T>(d1, 1, R1, ldr1, 0, Li1, ldr1, 0, 0.0, tol, infos, cq.pws, cq.pws_bytes, s);
+    if (rc) return rc;
+    rc = potrf_inv<T>(d2, 1, R2, ldr2, 0, Li2, ldr2, 0, 0.0, tol + 1, infos + 1, cq.pws, cq.pws_bytes, s);
+    if (rc) return rc;
+  }
+  // ---- T = Linv1 C12 Linv2^T ----
+  {
+    GemmArgs<T> g;
+    g.m = d1; g.n = d2; g.k = d1;
+    g.A = Li1; g.lda = ldr1; g.B = C + d1; g.ldb = P.ldC; g.C = T1; g.ldc = P.ldT;
+    rc = xgemm<T>(g, s);
+    if (rc) return rc;
+    GemmArgs<T> h;
+    h.transb = 1; h.m = d1; h.n = d2; h.k = d2;
+    h.A = T1; h.lda = P.ldT; h.B = Li2; h.ldb = ldr2; h.C = Tm; h.ldc = P.ldT;
+    rc = xgemm<T>(h, s);
+    if (rc) return rc;
+  }
+  // ---- subspace iteration: Z <- orth(T^T (T Z)) ----
+  {
+    const size_t total = (size_t)d2 * p;
+    randn_kernel<T><<<(unsigned)std::min<size_t>((total + 255) / 256, 592), 256, 0, s>>>(Z, P.ldp, d2, p, 0x1234ull);
+    count_launches(1);
+    CCAB_CUDA(cudaGetLastError());
+  }
+  int info_slot = 2;
+  for (int it = 0; it < iters; ++it) {
+    GemmArgs<T> a;   // Y = T Z
+    a.m = d1; a.n = p; a.k = d2; a.A = Tm; a.lda = P.ldT; a.B = Z; a.ldb = P.ldp; a.C = Y; a.ldc = P.ldp;
+    rc = xgemm<T>(a, s);
+    if (rc) return rc;
+    GemmArgs<T> b;   // Z2 = T^T Y
+    b.transa = 1; b.m = d2; b.n = p; b.k = d1; b.A = Tm; b.lda = P.ldT; b.B = Y; b.ldb = P.ldp; b.C = Z2; b.ldc = P.ldp;
+    rc = xgemm<T>(b, s);
+    if (rc) return rc;
+    rc = cholqr<T>(Z2, P.ldp, Z, P.ldp, d2, p, cq, infos + info_slot++, s);
+    if (rc) return rc;
+    if (it == iters - 1) {   // second pass on the last iterate: orthonormal to working precision
+      rc = cholqr<T>(Z, P.ldp, Z2, P.ldp, d2, p, cq, infos + info_slot++, s);
+      if (rc) return rc;
+      std::swap(Z, Z2);
+    }
+  }
+  // ---- Rayleigh-Ritz on Y = T Z: Y^T Y = Vy diag(sig^2) Vy^T ; U = Y Vy diag(1/sig), V = Z Vy ----
+  {
+    GemmArgs<T> a;
+    a.m = d1; a.n = p; a.k = d2; a.A = Tm; a.lda = P.ldT; a.B = Z; a.ldb = P.ldp; a.C = Y; a.ldc = P.ldp;
+    rc = xgemm<T>(a, s);
+    if (rc) return rc;
+    GemmArgs<T> h;
+    h.transa = 1; h.m = p; h.n = p; h.k = d1; h.A = Y; h.lda = P.ldp; h.B = Y; h.ldb = P.ldp; h.C = H; h.ldc = P.ldp;
+    rc = xgemm<T>(h, s);
+    if (rc) return rc;
+    rc = syevj_small<T>(p, 1, H, P.ldp, 0, lam, p, Vy, P.ldp, 0, rr_info, s);
+    if (rc) return rc;
+    GemmArgs<T> u;   // U = Y Vy_k   (rows of Vy are the eigenvectors: op(B) = Vy[:k]^T)
+    u.transb = 1; u.m = d1; u.n = k; u.k = p; u.A = Y; u.lda = P.ldp; u.B = Vy; u.ldb = P.ldp; u.C = U; u.ldc = P.ldk;
+    rc = xgemm<T>(u, s);
+    if (rc) return rc;
+    ritz_scale_kernel<T><<<dim3((unsigned)ceil_div(k, 128), (unsigned)d1), 128, 0, s>>>(U, P.ldk, d1, k, lam, sig);
+    count_launches(1);
+    GemmArgs<T> v;   // V = Z Vy_k
+    v.transb = 1; v.m = d2; v.n = k; v.k = p; v.A = Z; v.lda = P.ldp; v.B = Vy; v.ldb = P.ldp; v.C = V; v.ldc = P.ldk;
+    rc = xgemm<T>(v, s);
+    if (rc) return rc;
+    GemmArgs<T> e;   // E = T^T U  (compare with V diag(sig))
+    e.transa = 1; e.m = d2; e.n = k; e.k = d1; e.A = Tm; e.lda = P.ldT; e.B = U; e.ldb = P.ldk; e.C = E; e.ldc = P.ldk;
+    rc = xgemm<T>(e, s);
+    if (rc) return rc;
+    residual_kernel<T><<<1, 1024, 0, s>>>(E, P.ldk, V, P.ldk, d2, k, sig, stats);
+    count_launches(1);
+    CCAB_CUDA(cudaGetLastError());
+  }
+  // ---- weights = Linv^T U / V ----
+  {
+    GemmArgs<T> a;
+    a.transa = 1; a.m = d1; a.n = k; a.k = d1; a.A = Li1; a.lda = ldr1; a.B = U; a.ldb = P.ldk; a.C = W1; a.ldc = k;
+    rc = xgemm<T>(a, s);
+    if (rc) return rc;
+    GemmArgs<T> b;
+    b.transa = 1; b.m = d2; b.n = k; b.k = d2; b.A = Li2; b.lda = ldr2; b.B = V; b.ldb = P.ldk; b.C = W2; b.ldc = k;
+    rc = xgemm<T>(b, s);
+    if (rc) return rc;
+  }
+  fit_status_kernel<<<1, 32, 0, s>>>(hdr, flags, infos, n_infos, rr_info, stats, n_dev, n_host, 200.0 * eps_of<T>(), k,
+                                    std::max(d1, d2));
+  count_launches(1);
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template size_t rcca_fit_workspace_bytes<float>(int, int, int, int);
+template size_t rcca_fit_workspace_bytes<double>(int, int, int, int);
+template void rcca_fit_result_layout<float>(int, int, int, int, int64_t*);
+template void rcca_fit_result_layout<double>(int, int, int, int, int64_t*);
+template int rcca_fit<float>(const ColumnLayout&, const double*, const double*, double, int, const double*, int, int, int,
+                             void*, size_t, void*, size_t, cudaStream_t);
+template int rcca_fit<double>(const ColumnLayout&, const double*, const double*, double, int, const double*, int, int,
+                              int, void*, size_t, void*, size_t, cudaStream_t);
+
+}  // namespace ccab

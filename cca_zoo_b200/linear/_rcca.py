@@ -7,8 +7,9 @@ from typing import Any, ClassVar
 from sklearn.utils._param_validation import Interval, StrOptions
 
 from .._base import BaseModel
+from .. import ops
 from .._solvers import rcca_weights
-from .._validation import perview_parameter
+from .._validation import perview_parameter, validate_views
 
 #: cca_zoo/_utils/_param_constraints.py:18 (RIDGE_PARAMETER)
 RIDGE_PARAMETER: list[Any] = [Interval(Real, 0, 1, closed="both"), "array-like"]
@@ -52,13 +53,38 @@ class rCCA(BaseModel):
 
     def fit(self, views, y=None):
         """Fit on a list of exactly two ``(n_samples, n_features_i)`` arrays (numpy or torch)."""
-        C, dims, n_total = self._fit_device(views)
-        if self.n_views_ != 2:
+        self._validate_params()
+        validated = validate_views(views)
+        device = self._device()
+        mom, n_local, dims, in_dtype = self._local_moments(validated, device)
+        self._partial = None
+        if len(dims) != 2:
             raise ValueError(
-                f"rCCA requires exactly 2 views, got {self.n_views_}. "
+                f"rCCA requires exactly 2 views, got {len(dims)}. "
                 "Use MCCA for more than 2 views."
             )
-        return self._finish(self._solve(C, dims, n_total))
+        return self._fit_moments(mom, n_local, dims, in_dtype)
+
+    def _device_fit_plan(self, dims, n_local, in_dtype):
+        """The device-side fit (csrc/fit.cu: Cholesky whitening + subspace iteration, everything on the stream) is
+        taken for large, well-posed problems: ``solver`` allows it, k is small against the widths (4k <= min d_i) and
+        the iterated block fits the single-CTA Ritz solve (p <= 128).  Whether n > max d_i holds for the TOTAL sample
+        count, and whether the blocks are positive definite, is decided on the device (status word)."""
+        if self.solver == "eigen":
+            return None
+        if self.solver == "auto" and not (min(dims) >= 256 and n_local > max(dims)):
+            return None
+        k = min(int(self.latent_dimensions), dims[0], dims[1])
+        p = min(min(dims), k + max(32, k // 2))
+        if 4 * k > min(dims) or p > 128:
+            return None
+        c_ = [float(x) for x in perview_parameter("c", self.c, 0.0, 2)]
+        center = bool(self.center)
+
+        def call(mom, dims_, n_host, n_dev, solve_dtype, iters):
+            return ops.rcca_fit(mom, dims_, n_host, n_dev, center, c_, k, p, iters, solve_dtype)
+
+        return {"call": call, "k": k, "iters": [5, 20]}
 
     def _solve(self, C, dims, n_total):
         c_ = perview_parameter("c", self.c, 0.0, 2)

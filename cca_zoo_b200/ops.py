@@ -145,6 +145,26 @@ def syevj(A: torch.Tensor, shift: float = 0.0, return_info: bool = False):
     return evals, evt
 
 
+def syevj_small(A: torch.Tensor):
+    """Single-launch eigensolver for small symmetric matrices (n <= 128 float32 / 96 float64), (n,n) or (batch,n,n).
+    Returns (evals desc, evecs_t rows, info int32[batch] on the device: sweeps, negative = not converged)."""
+    lib = _lib.load()
+    _require_cuda(A, "A")
+    squeeze = A.dim() == 2
+    Ab = (A.unsqueeze(0) if squeeze else A).contiguous()
+    batch, n, _ = Ab.shape
+    evals = torch.empty((batch, n), dtype=Ab.dtype, device=Ab.device)
+    evt = torch.empty((batch, n, n), dtype=Ab.dtype, device=Ab.device)
+    info = torch.empty(batch, dtype=torch.int32, device=Ab.device)
+    with torch.cuda.device(Ab.device):
+        rc = lib.ccab_syevj_small(_DT[Ab.dtype], n, batch, _ptr(Ab), n, n * n, _ptr(evals), _ptr(evt), n, _ptr(info),
+                                  _stream(Ab))
+    _lib.check(rc, "ccab_syevj_small")
+    if squeeze:
+        return evals[0], evt[0], info
+    return evals, evt, info
+
+
 def gesvj(Gt: torch.Tensor, return_info: bool = False):
     """SVD of G (m x n) given as its transpose ``Gt`` (n x m, row-major: row j = column j of G).
 
@@ -338,6 +358,54 @@ def trsm_(L, B, side="left", trans=False):
         rc = lib.ccab_trsm(_DT[B.dtype], *args, _ptr(L), L.stride(0), _ptr(B), B.stride(0), _stream(B))
     _lib.check(rc, "ccab_trsm")
     return B
+
+
+# status bits of the device-side fit (csrc/fit.cuh)
+FIT_NOT_POSITIVE_DEFINITE, FIT_NOT_CONVERGED, FIT_NON_FINITE, FIT_TOO_FEW_SAMPLES = 1, 2, 4, 8
+FIT_HEADER_DOUBLES = 32
+
+
+def rcca_fit(mom: torch.Tensor, dims, n_host, n_dev, center: bool, c, k: int, p: int, iters: int, dtype):
+    """Device-side rCCA fit (ccab_rcca_fit): moments -> result block, asynchronous, nothing read back.
+
+    Returns (block, offsets): ``block`` is a uint8 CUDA tensor, ``offsets`` = byte offsets of
+    (mean float64[D], sigma[k], W1[d1 x k], W2[d2 x k], total).  ``decode_fit_block`` turns a host copy into arrays."""
+    lib = _lib.load()
+    _require_cuda(mom, "moments")
+    dt = _DT[dtype]
+    d = _lib.i64_array(dims)
+    offs = (C.c_int64 * 5)()
+    _lib.check(lib.ccab_rcca_fit_result_layout(dt, d, int(k), int(p), offs), "ccab_rcca_fit_result_layout")
+    offsets = [int(x) for x in offs]
+    block = torch.empty(offsets[4] + 256, dtype=torch.uint8, device=mom.device)
+    shift = (-block.data_ptr()) % 256
+    block = block[shift:shift + offsets[4]]
+    wsb = lib.ccab_rcca_fit_workspace_bytes(dt, d, int(k), int(p))
+    ws = _ws(wsb, mom.device)
+    cc = (C.c_double * 2)(float(c[0]), float(c[1]))
+    with torch.cuda.device(mom.device):
+        rc = lib.ccab_rcca_fit(dt, d, _ptr(mom), _ptr(n_dev), float(n_host if n_host is not None else 0.0),
+                               1 if center else 0, cc, int(k), int(p), int(iters), _ptr(block), block.numel(), _ptr(ws),
+                               ws.numel(), _stream(mom))
+    _lib.check(rc, "ccab_rcca_fit")
+    return block, offsets
+
+
+def decode_fit_block(host: torch.Tensor, offsets, dims, k: int, dtype):
+    """(header float64[32], mean float64[D], sigma[k], [W_i (d_i x k)]) as numpy views of a HOST copy of the block."""
+    import numpy as np
+
+    buf = host.numpy()
+    np_dt = np.float32 if dtype == torch.float32 else np.float64
+    D = int(sum(dims))
+    hdr = buf[:8 * FIT_HEADER_DOUBLES].view(np.float64)
+    mean = buf[offsets[0]:offsets[0] + 8 * D].view(np.float64)
+    sig = buf[offsets[1]:offsets[1] + np_dt().itemsize * k].view(np_dt)
+    ws = []
+    for i, d in enumerate(dims):
+        o = offsets[2 + i]
+        ws.append(buf[o:o + np_dt().itemsize * d * k].view(np_dt).reshape(d, k))
+    return hdr, mean, sig, ws
 
 
 _POW = {None: 0, 1: 0, -1: 1, -0.5: 2}

@@ -31,6 +31,18 @@ def allreduce_moments(moments: torch.Tensor, n_local: int, group=None):
     return packed[:-1], n_total
 
 
+def allreduce_moments_lazy(moments: torch.Tensor, n_local: int, group=None):
+    """Like ``allreduce_moments`` but WITHOUT reading the sample count back: returns
+    ``(moments_total, n_host, n_dev)`` where exactly one of ``n_host`` (int, single process) and ``n_dev`` (1-element
+    float64 device tensor, sharded fit) is not None.  The device-side fit (``ops.rcca_fit``) takes ``n_dev`` as it is,
+    so a sharded fit has no host synchronisation between the moment pass and the final copy of the weights."""
+    if not is_distributed(group):
+        return moments, int(n_local), None
+    packed = pack_moments(moments, n_local)
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return packed[:-1], None, packed[-1:]
+
+
 def shard_rows(n_rows: int, rank: int, world: int):
     """Contiguous row block [lo, hi) of rank ``rank``."""
     base, rem = divmod(n_rows, world)

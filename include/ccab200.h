@@ -83,6 +83,16 @@ int ccab_syevj(int dtype, int n, int batch, const void* A, int64_t lda, int64_t 
                void* evals, void* evecs_t, int64_t ldv, int* info, float* info_offdiag, void* workspace,
                size_t workspace_bytes, void* stream);
 
+/* Small symmetric eigenproblems (n <= 128 float / 96 double), batched, ONE single-CTA launch per matrix, no host
+ * synchronisation: two-sided Jacobi with tournament ordering in shared memory.  Same outputs as ccab_syevj
+ * (descending eigenvalues, eigenvectors as rows; evals / evecs_t contiguous per matrix: n and n x ldv); absolute
+ * accuracy eps * ||A|| (use ccab_syevj when tiny eigenvalues matter relatively).  info_dev[b] (device int[batch],
+ * may be NULL) = sweeps used, negated if the tolerance was not reached.
+ * Replaces the Rayleigh-Ritz eigensolve of the top-k route (scipy.linalg.eigh subset_by_index,
+ * cca_zoo/_utils/_linalg.py:64-73). */
+int ccab_syevj_small(int dtype, int n, int batch, const void* A, int64_t lda, int64_t stride_a, void* evals,
+                     void* evecs_t, int64_t ldv, int* info_dev, void* stream);
+
 /* ---- K4: singular value decomposition (one-sided Jacobi) -----------------------------------------
  * G is m x n given by COLUMNS: column j is the contiguous array A + j*lda (length m) -- i.e. a
  * row-major n x m buffer holds G^T.  Outputs (descending): sigma[n]; right_t (n x n, ldr): row j =
@@ -162,6 +172,26 @@ size_t ccab_potrf_inv_workspace_bytes(int dtype, int n, int batch);
 int ccab_potrf_inv(int dtype, int n, int batch, void* A, int64_t lda, int64_t stride_a, void* Linv, int64_t ldi,
                    int64_t stride_i, double pivot_tol, int* info_dev, void* workspace, size_t workspace_bytes,
                    void* stream);
+
+/* ---- the fit behind the ABI: rCCA / CCA / PLS ----------------------------------------------------------------------
+ * From the (all-reduced) moment buffer of ccab_moments to the weights in ONE asynchronous call: covariance, ridge
+ * blocks R_i = (1-c_i) C_ii + c_i I, batched Cholesky + inverse, T = L1^-1 C12 L2^-T, the leading k singular triplets
+ * of T by blocked subspace iteration (block width p >= k, `iters` products with T^T T, CholQR, Rayleigh-Ritz) and
+ * weights_i = L_i^-T U_k / V_k.  Nothing is read back by the library: every decision that needs a host (pivot
+ * failures, rank loss, convergence, NaN / inf in the input, n <= d) is reported in the header of the result block.
+ *   result (device, 256-byte aligned, ccab_rcca_fit_result_layout offsets[4] bytes):
+ *     double header[32] | double mean[D] | T sigma[k] | T W1[d1 x k] | T W2[d2 x k]      (offsets[0..3] = byte offsets)
+ *     header[0] = status bits (0 = valid): 1 a block is not positive definite, 2 not converged, 4 non-finite input,
+ *                 8 too few samples (n <= max d_i);  header[1] = n_total;  [2] residual;  [3] sigma_1;
+ *                 [4] index of the first failed factorisation;  [5] sweeps of the Ritz eigensolve
+ *   n_total_dev (device double, may be NULL) overrides n_total: the sample count can ride in the all-reduced message.
+ *   p must satisfy k <= p <= min(d1, d2, 128).  dtype = arithmetic of the whole solve (CCAB_F32 uses tcgen05 GEMMs).
+ * Replaces cca_zoo/linear/_rcca.py:83-101 (via cca_zoo/_utils/_linalg.py:9-41) after the moment pass. */
+size_t ccab_rcca_fit_workspace_bytes(int dtype, const int64_t* dims, int k, int p);
+int ccab_rcca_fit_result_layout(int dtype, const int64_t* dims, int k, int p, int64_t* offsets /* [5] */);
+int ccab_rcca_fit(int dtype, const int64_t* dims, const double* moments, const double* n_total_dev, double n_total,
+                  int center, const double* c, int k, int p, int iters, void* result, size_t result_bytes,
+                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* B[i,j] = A[i,j] * f(r[i]) * f(c[j]); r / c may be NULL; *_pow: 0 -> x, 1 -> 1/x, 2 -> 1/sqrt(x).
  * (column scalings such as diag(sigma)^-1/2 in the GCCA back-substitution, cca_zoo/linear/_gcca.py:109) */

@@ -172,6 +172,67 @@ def debug_set(key, value):
     return None
 
 
+# ---- device-side fit (csrc/fit.cu) stand-in: same result-block layout and status bits, LAPACK arithmetic ----
+FIT_NOT_POSITIVE_DEFINITE, FIT_NOT_CONVERGED, FIT_NON_FINITE, FIT_TOO_FEW_SAMPLES = 1, 2, 4, 8
+FIT_HEADER_DOUBLES = 32
+
+
+def _al256(x):
+    return (x + 255) // 256 * 256
+
+
+def rcca_fit(mom, dims, n_host, n_dev, center, c, k, p, iters, dtype):
+    from cca_zoo_b200.ops import decode_fit_block  # noqa: F401  (layout documented there)
+
+    item = 4 if dtype == torch.float32 else 8
+    D = int(sum(dims))
+    o_mean = 8 * FIT_HEADER_DOUBLES
+    o_sig = o_mean + _al256(8 * D)
+    o_w1 = o_sig + _al256(item * k)
+    o_w2 = o_w1 + _al256(item * dims[0] * k)
+    total = o_w2 + _al256(item * dims[1] * k)
+    offsets = [o_mean, o_sig, o_w1, o_w2, total]
+    block = torch.zeros(total, dtype=torch.uint8)
+    buf = block.numpy()
+    hdr = buf[:8 * FIT_HEADER_DOUBLES].view(np.float64)
+    n = float(n_host) if n_host is not None else float(n_dev[0])
+    status = 0
+    if not bool(torch.isfinite(mom).all()):
+        status |= FIT_NON_FINITE
+    if not n > max(dims):
+        status |= FIT_TOO_FEW_SAMPLES
+    hdr[1] = n
+    if status == 0:
+        C, mean = covariance(mom, dims, n, center, torch.float64)
+        d1 = dims[0]
+        Linv = []
+        for i, sl in enumerate((slice(0, d1), slice(d1, D))):
+            R = (1.0 - c[i]) * C[sl, sl] + c[i] * torch.eye(dims[i], dtype=torch.float64)
+            L, info = torch.linalg.cholesky_ex(R)
+            tol = dims[i] * float(torch.finfo(dtype).eps) * ((1.0 - c[i]) * float(C[sl, sl].diagonal().max()) + c[i])
+            if int(info) != 0 or bool((L.diagonal() ** 2 <= tol).any()):
+                status |= FIT_NOT_POSITIVE_DEFINITE
+                break
+            Linv.append(torch.linalg.inv(L))
+        if status == 0:
+            T = Linv[0] @ C[:d1, d1:] @ Linv[1].T
+            U, S, Vh = torch.linalg.svd(T, full_matrices=False)
+            np_dt = np.float32 if dtype == torch.float32 else np.float64
+            buf[o_mean:o_mean + 8 * D].view(np.float64)[:] = mean.numpy()
+            buf[o_sig:o_sig + item * k].view(np_dt)[:] = S[:k].numpy()
+            buf[o_w1:o_w1 + item * dims[0] * k].view(np_dt)[:] = (Linv[0].T @ U[:, :k]).numpy().reshape(-1)
+            buf[o_w2:o_w2 + item * dims[1] * k].view(np_dt)[:] = (Linv[1].T @ Vh[:k].T).numpy().reshape(-1)
+            hdr[3] = float(S[0])
+    hdr[0] = status
+    return block, offsets
+
+
+def decode_fit_block(host, offsets, dims, k, dtype):
+    from cca_zoo_b200.ops import decode_fit_block as real
+
+    return real(host, offsets, dims, k, dtype)
+
+
 @contextlib.contextmanager
 def _no_streams(device):
     yield [None, None]
@@ -183,12 +244,12 @@ def install(monkeypatch):
 
     import cca_zoo_b200
     from cca_zoo_b200 import _base, _solvers
-    from cca_zoo_b200.linear import _grcca, _partialcca
+    from cca_zoo_b200.linear import _grcca, _partialcca, _rcca
 
     from cca_zoo_b200.deep import objectives
 
     me = sys.modules[__name__]
-    for mod in (_base, _solvers, _partialcca, _grcca, objectives):
+    for mod in (_base, _solvers, _partialcca, _grcca, _rcca, objectives):
         monkeypatch.setattr(mod, "ops", me)
     monkeypatch.setattr(objectives, "_require_cuda", lambda name, *tensors: None)
     monkeypatch.setattr(cca_zoo_b200, "ops", me, raising=False)

@@ -88,12 +88,15 @@ def _wide_views(n=3000, dims=(300, 280), k=6, seed=3, dtype=np.float64):
 
 
 def test_cholesky_and_eigen_routes_agree_on_wide_views(host):
-    """min(dims) >= 256 and n > max(dims): ``auto`` takes the Cholesky + subspace-iteration route."""
+    """min(dims) >= 256 and n > max(dims): ``auto`` takes the device-side fit (one library call); when that is not
+    available the host-assembled Cholesky + subspace-iteration route; both agree with the eigen route."""
     from cca_zoo_b200 import _solvers
     from cca_zoo_b200.linear import MCCA, GCCA, rCCA
 
     views = _wide_views()
     w_ref, _ = R.ref_rcca_fit(views, 4, 0.2)
+    auto = rCCA(latent_dimensions=4, c=0.2).fit(views)
+    assert auto._fit_info["route"] == "device"
     calls = {"n": 0}
     real = _solvers.topk_svd
 
@@ -102,11 +105,14 @@ def test_cholesky_and_eigen_routes_agree_on_wide_views(host):
         return real(*a, **kw)
 
     _solvers.topk_svd, keep = spy, real
+    plan, rCCA._device_fit_plan = rCCA._device_fit_plan, lambda self, *a: None
     try:
-        auto = rCCA(latent_dimensions=4, c=0.2).fit(views)
+        hosted = rCCA(latent_dimensions=4, c=0.2).fit(views)
     finally:
         _solvers.topk_svd = keep
-    assert calls["n"] == 1, "auto must take the top-k route here"
+        rCCA._device_fit_plan = plan
+    assert calls["n"] == 1, "without the device-side fit, auto must take the host-assembled top-k route here"
+    assert R.max_rel_err_per_vector(hosted.weights_, w_ref) < 1e-8
     eig = rCCA(latent_dimensions=4, c=0.2, solver="eigen").fit(views)
     assert R.max_rel_err_per_vector(auto.weights_, w_ref) < 1e-8
     assert R.max_rel_err_per_vector(eig.weights_, w_ref) < 1e-8
