@@ -260,9 +260,13 @@ int ccab_gemm(int dtype, int transa, int transb, int m, int n, int k, double alp
   int rc = require_device();
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (dtype == CCAB_F32)
-    return gemm<float>(transa, transb, m, n, k, (float)alpha, static_cast<const float*>(A), lda,
-                       static_cast<const float*>(B), ldb, (float)beta, static_cast<float*>(C), ldc, s);
+  if (dtype == CCAB_F32) {   // tensor pipe (tcgen05, 3xTF32) when TMA can address the operands, FMA tiles otherwise
+    GemmArgs<float> g;
+    g.transa = transa; g.transb = transb; g.m = m; g.n = n; g.k = k; g.alpha = (float)alpha; g.beta = (float)beta;
+    g.A = static_cast<const float*>(A); g.lda = lda; g.B = static_cast<const float*>(B); g.ldb = ldb;
+    g.C = static_cast<float*>(C); g.ldc = ldc;
+    return xgemm<float>(g, s);
+  }
   return gemm<double>(transa, transb, m, n, k, alpha, static_cast<const double*>(A), lda,
                       static_cast<const double*>(B), ldb, beta, static_cast<double*>(C), ldc, s);
   CCAB_CATCH
@@ -428,6 +432,58 @@ int ccab_rcca_fit(int dtype, const int64_t* dims, const double* moments, const d
                            workspace_bytes, s);
   return rcca_fit<double>(L, moments, n_total_dev, n_total, center, c, k, p, iters, result, result_bytes, workspace,
                           workspace_bytes, s);
+  CCAB_CATCH
+}
+
+size_t ccab_ccaloss_workspace_bytes(int dtype, int precision, int d1, int d2, int64_t n) {
+  int64_t dims[2] = {d1, d2};
+  ColumnLayout L;
+  if (make_layout(2, dims, &L)) return 0;
+  if (dtype == CCAB_F64) precision = CCAB_PREC_EXACT;
+  return dtype == CCAB_F32 ? ccaloss_workspace_bytes<float>(L, n, precision)
+                           : ccaloss_workspace_bytes<double>(L, n, precision);
+}
+
+int ccab_ccaloss_fwd(int dtype, int precision, const void* z1, int64_t ld1, const void* z2, int64_t ld2, int64_t n,
+                     int d1, int d2, double eps, void* loss, void* saved, int* flags_dev, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(precision >= 0 && precision <= 2, "bad precision %d", precision);
+  CCAB_CHECK_ARG(z1 && z2 && loss && saved && flags_dev && workspace, "null pointer argument");
+  CCAB_CHECK_ARG(ld1 >= d1 && ld2 >= d2, "leading dimension too small");
+  int64_t dims[2] = {d1, d2};
+  ColumnLayout L;
+  int rc = make_layout(2, dims, &L);
+  if (rc) return rc;
+  rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CCAB_F32)
+    return ccaloss_forward<float>(L, precision, z1, ld1, z2, ld2, n, eps, static_cast<float*>(loss),
+                                  static_cast<float*>(saved), flags_dev, workspace, workspace_bytes, s);
+  return ccaloss_forward<double>(L, CCAB_PREC_EXACT, z1, ld1, z2, ld2, n, eps, static_cast<double*>(loss),
+                                 static_cast<double*>(saved), flags_dev, workspace, workspace_bytes, s);
+  CCAB_CATCH
+}
+
+int ccab_ccaloss_bwd(int dtype, const void* z1, int64_t ld1, const void* z2, int64_t ld2, int64_t n, int d1, int d2,
+                     const void* saved, const void* grad_out, void* g1, int64_t ldg1, void* g2, int64_t ldg2,
+                     void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(z1 && z2 && saved && g1 && g2, "null pointer argument");
+  CCAB_CHECK_ARG(ld1 >= d1 && ld2 >= d2 && ldg1 >= d1 && ldg2 >= d2, "leading dimension too small");
+  int rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CCAB_F32)
+    return ccaloss_backward<float>(d1, d2, static_cast<const float*>(z1), ld1, static_cast<const float*>(z2), ld2, n,
+                                   static_cast<const float*>(saved), static_cast<const float*>(grad_out),
+                                   static_cast<float*>(g1), ldg1, static_cast<float*>(g2), ldg2, s);
+  return ccaloss_backward<double>(d1, d2, static_cast<const double*>(z1), ld1, static_cast<const double*>(z2), ld2, n,
+                                  static_cast<const double*>(saved), static_cast<const double*>(grad_out),
+                                  static_cast<double*>(g1), ldg1, static_cast<double*>(g2), ldg2, s);
   CCAB_CATCH
 }
 

@@ -36,6 +36,7 @@ struct CovRidgeParams {
   int coff[kMaxViews + 1];
   int poff[kMaxViews + 1];
   double c[kMaxViews];
+  double ridge_add[kMaxViews]; // R_v = (1 - c_v) C_vv + (c_v + ridge_add_v) I
   void* R[kMaxViews];          // ridge block of view v (may be NULL)
   long long ldr[kMaxViews];
 };
@@ -73,7 +74,7 @@ __global__ void cov_ridge_kernel(const CovRidgeParams p, const double* __restric
   C[(size_t)gi * ldc + gj] = (T)v;
   if (vi == vj && p.R[vi]) {
     const double cv = p.c[vi];
-    const double rv = (1.0 - cv) * v + (gi == gj ? cv : 0.0);
+    const double rv = (1.0 - cv) * v + (gi == gj ? cv + p.ridge_add[vi] : 0.0);
     static_cast<T*>(p.R[vi])[(size_t)(gi - p.coff[vi]) * p.ldr[vi] + (gj - p.coff[vj])] = (T)rv;
     if (gi == gj && dmax) atomicMax(dmax + vi, __float_as_uint(fmaxf((float)v, 0.f)));
   }
@@ -436,6 +437,265 @@ int rcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
   CCAB_CUDA(cudaGetLastError());
   return 0;
 }
+
+
+// =============================================================================================================
+// Deep-CCA objective (cca_zoo/deep/objectives.py:61-102) on the device, any widths, no host read-back.
+//   forward : moments of [z1 z2] -> S_ii = C_ii + eps I, S_12 -> batched Cholesky + inverse ->
+//             A_i = S_ii^-1 = Linv_i^T Linv_i, Q = A_1 S_12, Q2 = S_12 A_2, P = Q A_2 = S_11^-1 S_12 S_22^-1,
+//             loss = -<P, S_12> (= -||S_11^-1/2 S_12 S_22^-1/2||_F^2: the reference's eigvalsh(T^T T).sum() is a trace),
+//             G_11 = P Q^T = P S_21 S_11^-1, G_22 = Q2^T P = S_22^-1 S_21 P        (7 GEMMs, tcgen05 for float)
+//   backward: dL/dz_1 = 2/(n-1) center(z_1 G_11 - z_2 P^T) go, dL/dz_2 = 2/(n-1) center(z_2 G_22 - z_1 P) go
+//             (4 tall GEMMs + 2 centring passes; `go` is the upstream gradient, read on the device)
+//   flags[0..1] = Cholesky status of S_11 / S_22 with pivot^2 <= eps / 4 counted as failure (S_ii = C_ii + eps I has
+//   lambda_min >= eps in exact arithmetic: a smaller pivot means rounding destroyed the ridge; the caller re-runs through
+//   the eigen route, which clamps like the reference); checked lazily by the host.
+// =============================================================================================================
+namespace {
+
+// loss[0] = -sum_ij P[i][j] * S12[i][j]   (one block, fixed order)
+template <typename T>
+__global__ void loss_dot_kernel(const T* __restrict__ P, int64_t ldp, const T* __restrict__ S, int64_t lds, int d1, int d2,
+                                T* __restrict__ loss) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < d1 * d2; e += blockDim.x) {
+    const int i = e / d2, j = e % d2;
+    acc += (double)P[(size_t)i * ldp + j] * (double)S[(size_t)i * lds + j];
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    loss[0] = (T)(-t);
+  }
+}
+
+// A[:, j] = (A[:, j] - mean_i A[i, j]) * scale[0]   (one block per 32 columns; fixed-order reduction)
+template <typename T>
+__global__ void center_scale_kernel(int m, int n, T* __restrict__ A, int64_t lda, const T* __restrict__ scale) {
+  __shared__ double part[32][33];
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rg = threadIdx.x >> 5;
+  double acc = 0.0;
+  if (j < n)
+    for (int i = rg; i < m; i += 32) acc += (double)A[(size_t)i * lda + j];
+  part[rg][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (rg == 0) {
+    double s = 0.0;
+    for (int k = 0; k < 32; ++k) s += part[k][threadIdx.x & 31];
+    part[0][threadIdx.x & 31] = s / (double)m;
+  }
+  __syncthreads();
+  const T mu = (T)part[0][threadIdx.x & 31];
+  const T sc = scale ? scale[0] : T(1);
+  if (j < n)
+    for (int i = rg; i < m; i += 32) A[(size_t)i * lda + j] = (A[(size_t)i * lda + j] - mu) * sc;
+}
+
+struct LossPlan {
+  int d1, d2, D, Dp;
+  int64_t ldC, ldR, strideR;
+  bool batched;
+  size_t oMom, oMomWs, oC, oR, oLinv, oA, oQ, oQ2, oPws, oSmall, total;
+  size_t mom_ws_bytes, pws_bytes;
+  size_t sG11, sP, sG22, s_total;   // element offsets inside `saved`
+};
+
+template <typename T>
+LossPlan make_loss_plan(const ColumnLayout& L, int64_t n, int precision) {
+  LossPlan P;
+  P.d1 = L.dims[0]; P.d2 = L.dims[1]; P.D = L.D; P.Dp = L.Dp;
+  P.ldC = r4(P.D);
+  const int dm = std::max(P.d1, P.d2);
+  P.ldR = r4(dm);
+  P.strideR = (int64_t)dm * P.ldR;
+  P.batched = P.d1 == P.d2;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += al256(bytes); return at; };
+  P.oMom = take(sizeof(double) * ((size_t)P.Dp * P.Dp + P.Dp));
+  P.mom_ws_bytes = moments_workspace_bytes(std::is_same<T, float>::value ? 0 : 1, precision, L, n) + 512;
+  P.oMomWs = take(P.mom_ws_bytes);
+  P.oC = take(sizeof(T) * (size_t)P.D * P.ldC);
+  P.oR = take(sizeof(T) * 2 * (size_t)P.strideR);
+  P.oLinv = take(sizeof(T) * 2 * (size_t)P.strideR);
+  P.oA = take(sizeof(T) * 2 * (size_t)P.strideR);
+  P.oQ = take(sizeof(T) * (size_t)P.d1 * r4(P.d2));
+  P.oQ2 = take(sizeof(T) * (size_t)P.d1 * r4(P.d2));
+  P.pws_bytes = potrf_inv_workspace_bytes<T>(dm, 2);
+  P.oPws = take(P.pws_bytes);
+  P.oSmall = take(4096);
+  P.total = o + 256;
+  P.sG11 = 0;
+  P.sP = (size_t)P.d1 * P.d1;
+  P.sG22 = P.sP + (size_t)P.d1 * P.d2;
+  P.s_total = P.sG22 + (size_t)P.d2 * P.d2;
+  return P;
+}
+
+}  // namespace
+
+template <typename T>
+size_t ccaloss_workspace_bytes(const ColumnLayout& L, int64_t n, int precision) {
+  return make_loss_plan<T>(L, n, precision).total;
+}
+
+template <typename T>
+int ccaloss_forward(const ColumnLayout& L, int precision, const void* z1, int64_t ld1, const void* z2, int64_t ld2,
+                    int64_t n, double eps, T* loss, T* saved, int* flags_out, void* ws, size_t ws_bytes, cudaStream_t s) {
+  CCAB_CHECK_ARG(L.n_views == 2 && n >= 2, "ccaloss_forward: two views and at least 2 samples");
+  LossPlan P = make_loss_plan<T>(L, n, precision);
+  CCAB_CHECK_ARG(ws_bytes >= P.total, "ccaloss workspace too small: %zu < %zu", ws_bytes, P.total);
+  uint8_t* w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  const int d1 = P.d1, d2 = P.d2, D = P.D;
+  double* mom = reinterpret_cast<double*>(w + P.oMom);
+  T* C = reinterpret_cast<T*>(w + P.oC);
+  T* R1 = reinterpret_cast<T*>(w + P.oR);
+  T* R2 = R1 + P.strideR;
+  T* Li1 = reinterpret_cast<T*>(w + P.oLinv);
+  T* Li2 = Li1 + P.strideR;
+  T* A1 = reinterpret_cast<T*>(w + P.oA);
+  T* A2 = A1 + P.strideR;
+  T* Q = reinterpret_cast<T*>(w + P.oQ);
+  T* Q2 = reinterpret_cast<T*>(w + P.oQ2);
+  const int64_t ldq = r4(d2);
+  uint8_t* sm = w + P.oSmall;
+  int* flags = reinterpret_cast<int*>(sm);
+  unsigned* dmax = reinterpret_cast<unsigned*>(sm + 512);
+  const int64_t ldr1 = P.batched ? P.ldR : r4(d1), ldr2 = P.batched ? P.ldR : r4(d2);
+  T* G11 = saved + P.sG11;
+  T* Pm = saved + P.sP;
+  T* G22 = saved + P.sG22;
+
+  // ---- moments of [z1 z2] ----
+  const void* views[2] = {z1, z2};
+  const int64_t lds[2] = {ld1, ld2};
+  int rc;
+  if (std::is_same<T, float>::value && precision != 2)
+    rc = moments_tf32(L, views, lds, n, precision == 1, mom, w + P.oMomWs, P.mom_ws_bytes, s);
+  else
+    rc = moments_simt<T>(L, views, lds, n, mom, w + P.oMomWs, P.mom_ws_bytes, s);
+  if (rc) return rc;
+  CCAB_CUDA(cudaMemsetAsync(sm, 0, 1024, s));
+  {
+    CovRidgeParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.n_views = 2; cp.D = D; cp.Dp = L.Dp;
+    for (int v = 0; v < 2; ++v) { cp.dims[v] = L.dims[v]; cp.c[v] = 0.0; cp.ridge_add[v] = eps; }
+    for (int v = 0; v <= 2; ++v) { cp.coff[v] = L.coff[v]; cp.poff[v] = L.poff[v]; }
+    cp.R[0] = R1; cp.R[1] = R2; cp.ldr[0] = ldr1; cp.ldr[1] = ldr2;
+    dim3 block(32, 8), grid((unsigned)ceil_div(D, 32), (unsigned)ceil_div(D, 8));
+    cov_ridge_kernel<T><<<grid, block, 0, s>>>(cp, mom, nullptr, (double)n, 1, C, P.ldC, nullptr, dmax, flags + 4);
+    count_launches(1);
+    CCAB_CUDA(cudaGetLastError());
+  }
+  const double piv_tol = 0.25 * eps;   // a pivot^2 below the ridge itself: S_ii lost its definiteness to rounding
+  if (P.batched) {
+    rc = potrf_inv<T>(d1, 2, R1, P.ldR, P.strideR, Li1, P.ldR, P.strideR, piv_tol, nullptr, flags, w + P.oPws, P.pws_bytes, s);
+    if (rc) return rc;
+  } else {
+    rc = potrf_inv<T>(d1, 1, R1, ldr1, 0, Li1, ldr1, 0, piv_tol, nullptr, flags, w + P.oPws, P.pws_bytes, s);
+    if (rc) return rc;
+    rc = potrf_inv<T>(d2, 1, R2, ldr2, 0, Li2, ldr2, 0, piv_tol, nullptr, flags + 1, w + P.oPws, P.pws_bytes, s);
+    if (rc) return rc;
+  }
+  // A_i = Linv_i^T Linv_i
+  if (P.batched) {
+    GemmArgs<T> g;
+    g.transa = 1; g.m = d1; g.n = d1; g.k = d1;
+    g.A = Li1; g.lda = P.ldR; g.strideA = P.strideR; g.B = Li1; g.ldb = P.ldR; g.strideB = P.strideR;
+    g.C = A1; g.ldc = P.ldR; g.strideC = P.strideR; g.batch = 2;
+    rc = xgemm<T>(g, s);
+    if (rc) return rc;
+  } else {
+    for (int v = 0; v < 2; ++v) {
+      GemmArgs<T> g;
+      const int d = v ? d2 : d1;
+      const int64_t ld = v ? ldr2 : ldr1;
+      g.transa = 1; g.m = d; g.n = d; g.k = d;
+      g.A = v ? Li2 : Li1; g.lda = ld; g.B = g.A; g.ldb = ld; g.C = v ? A2 : A1; g.ldc = ld;
+      rc = xgemm<T>(g, s);
+      if (rc) return rc;
+    }
+  }
+  const T* S12 = C + d1;
+  {
+    GemmArgs<T> g;   // Q = A1 S12
+    g.m = d1; g.n = d2; g.k = d1; g.A = A1; g.lda = ldr1; g.B = S12; g.ldb = P.ldC; g.C = Q; g.ldc = ldq;
+    rc = xgemm<T>(g, s);
+    if (rc) return rc;
+    GemmArgs<T> h;   // Q2 = S12 A2
+    h.m = d1; h.n = d2; h.k = d2; h.A = S12; h.lda = P.ldC; h.B = A2; h.ldb = ldr2; h.C = Q2; h.ldc = ldq;
+    rc = xgemm<T>(h, s);
+    if (rc) return rc;
+    GemmArgs<T> p;   // P = Q A2
+    p.m = d1; p.n = d2; p.k = d2; p.A = Q; p.lda = ldq; p.B = A2; p.ldb = ldr2; p.C = Pm; p.ldc = d2;
+    rc = xgemm<T>(p, s);
+    if (rc) return rc;
+    GemmArgs<T> a;   // G11 = P Q^T
+    a.transb = 1; a.m = d1; a.n = d1; a.k = d2; a.A = Pm; a.lda = d2; a.B = Q; a.ldb = ldq; a.C = G11; a.ldc = d1;
+    rc = xgemm<T>(a, s);
+    if (rc) return rc;
+    GemmArgs<T> b;   // G22 = Q2^T P
+    b.transa = 1; b.m = d2; b.n = d2; b.k = d1; b.A = Q2; b.lda = ldq; b.B = Pm; b.ldb = d2; b.C = G22; b.ldc = d2;
+    rc = xgemm<T>(b, s);
+    if (rc) return rc;
+  }
+  loss_dot_kernel<T><<<1, 1024, 0, s>>>(Pm, d2, S12, P.ldC, d1, d2, loss);
+  count_launches(1);
+  CCAB_CUDA(cudaGetLastError());
+  // flags_out[0..1] = Cholesky status, [2] = non-finite moments
+  CCAB_CUDA(cudaMemcpyAsync(flags_out, flags, 2 * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  CCAB_CUDA(cudaMemcpyAsync(flags_out + 2, flags + 4, sizeof(int), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+template <typename T>
+int ccaloss_backward(int d1, int d2, const T* z1, int64_t ld1, const T* z2, int64_t ld2, int64_t n, const T* saved,
+                     const T* grad_out, T* g1, int64_t ldg1, T* g2, int64_t ldg2, cudaStream_t s) {
+  CCAB_CHECK_ARG(n >= 2 && d1 >= 1 && d2 >= 1, "ccaloss_backward: bad shape");
+  const T* G11 = saved;
+  const T* Pm = saved + (size_t)d1 * d1;
+  const T* G22 = Pm + (size_t)d1 * d2;
+  const T a = (T)(2.0 / (double)(n - 1));
+  GemmArgs<T> g;
+  g.m = (int)n; g.n = d1; g.k = d1; g.alpha = a; g.A = z1; g.lda = ld1; g.B = G11; g.ldb = d1; g.C = g1; g.ldc = ldg1;
+  int rc = xgemm<T>(g, s);
+  if (rc) return rc;
+  GemmArgs<T> h;   // g1 -= a z2 P^T
+  h.transb = 1; h.m = (int)n; h.n = d1; h.k = d2; h.alpha = -a; h.beta = T(1);
+  h.A = z2; h.lda = ld2; h.B = Pm; h.ldb = d2; h.C = g1; h.ldc = ldg1;
+  rc = xgemm<T>(h, s);
+  if (rc) return rc;
+  GemmArgs<T> u;
+  u.m = (int)n; u.n = d2; u.k = d2; u.alpha = a; u.A = z2; u.lda = ld2; u.B = G22; u.ldb = d2; u.C = g2; u.ldc = ldg2;
+  rc = xgemm<T>(u, s);
+  if (rc) return rc;
+  GemmArgs<T> v;   // g2 -= a z1 P
+  v.m = (int)n; v.n = d2; v.k = d1; v.alpha = -a; v.beta = T(1);
+  v.A = z1; v.lda = ld1; v.B = Pm; v.ldb = d2; v.C = g2; v.ldc = ldg2;
+  rc = xgemm<T>(v, s);
+  if (rc) return rc;
+  center_scale_kernel<T><<<(unsigned)ceil_div(d1, 32), 1024, 0, s>>>((int)n, d1, g1, ldg1, grad_out);
+  center_scale_kernel<T><<<(unsigned)ceil_div(d2, 32), 1024, 0, s>>>((int)n, d2, g2, ldg2, grad_out);
+  count_launches(2);
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template size_t ccaloss_workspace_bytes<float>(const ColumnLayout&, int64_t, int);
+template size_t ccaloss_workspace_bytes<double>(const ColumnLayout&, int64_t, int);
+template int ccaloss_forward<float>(const ColumnLayout&, int, const void*, int64_t, const void*, int64_t, int64_t, double,
+                                    float*, float*, int*, void*, size_t, cudaStream_t);
+template int ccaloss_forward<double>(const ColumnLayout&, int, const void*, int64_t, const void*, int64_t, int64_t, double,
+                                     double*, double*, int*, void*, size_t, cudaStream_t);
+template int ccaloss_backward<float>(int, int, const float*, int64_t, const float*, int64_t, int64_t, const float*,
+                                     const float*, float*, int64_t, float*, int64_t, cudaStream_t);
+template int ccaloss_backward<double>(int, int, const double*, int64_t, const double*, int64_t, int64_t, const double*,
+                                      const double*, double*, int64_t, double*, int64_t, cudaStream_t);
 
 template size_t rcca_fit_workspace_bytes<float>(int, int, int, int);
 template size_t rcca_fit_workspace_bytes<double>(int, int, int, int);

@@ -25,4 +25,18 @@ int rcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
              const double* c, int k, int p, int iters, void* result, size_t result_bytes, void* ws, size_t ws_bytes,
              cudaStream_t stream);
 
+// ---- deep-CCA objective on the device (cca_zoo/deep/objectives.py:61-102), any widths, nothing read back ----
+// saved (T[d1*d1 + d1*d2 + d2*d2]) = G11 | P | G22 for the analytic backward; flags_out (device int[3]) = Cholesky
+// status of S11, S22 (pivot^2 <= eps / 4 counts as failure) and a non-finite-input flag, to be checked lazily.
+template <typename T>
+size_t ccaloss_workspace_bytes(const ColumnLayout& L, int64_t n, int precision);
+template <typename T>
+int ccaloss_forward(const ColumnLayout& L, int precision, const void* z1, int64_t ld1, const void* z2, int64_t ld2,
+                    int64_t n, double eps, T* loss, T* saved, int* flags_out, void* ws, size_t ws_bytes,
+                    cudaStream_t stream);
+// g1 / g2 (n x d1 / n x d2) <- 2/(n-1) center(z1 G11 - z2 P^T) * grad_out[0] and the symmetric expression
+template <typename T>
+int ccaloss_backward(int d1, int d2, const T* z1, int64_t ld1, const T* z2, int64_t ld2, int64_t n, const T* saved,
+                     const T* grad_out, T* g1, int64_t ldg1, T* g2, int64_t ldg2, cudaStream_t stream);
+
 }  // namespace ccab

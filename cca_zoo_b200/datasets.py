@@ -39,6 +39,35 @@ def joint_data(n_views=2, n_samples=100, latent_dimensions=1, n_features=10,
     return views
 
 
+def joint_data_device(n_views=2, n_samples=100, latent_dimensions=1, n_features=10, signal_to_noise=1.0,
+                      random_state=0, dtype=None, device=None, weights_seed=None):
+    """The same latent-variable model (cca_zoo/datasets/_simulated.py:113-125) generated ON THE DEVICE: the views of a
+    large configuration (BASELINE configs 4 and 5: 16 GB and 65 GB of float64 on the host) never exist in host memory.
+    ``x_i = z W_i^T + N(0, 1/snr_i)`` with ``W_i`` drawn from ``weights_seed`` (default: ``random_state``) and the
+    latent draws / noise from ``random_state`` -- ranks of a sharded fit pass one ``weights_seed`` and their own
+    ``random_state`` so that their row shards are samples of ONE population.  Not draw-for-draw identical to the
+    host generator (different RNG); returns a list of CUDA tensors."""
+    import torch
+
+    from . import ops
+
+    dtype = torch.float32 if dtype is None else dtype
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    feats = _per_view(n_features, n_views, "n_features")
+    snrs = _per_view(signal_to_noise, n_views, "signal_to_noise")
+    gw = torch.Generator(device=device).manual_seed(int(random_state if weights_seed is None else weights_seed))
+    g = torch.Generator(device=device).manual_seed(int(random_state) + 7919)
+    weights = [torch.randn((p, latent_dimensions), generator=gw, device=device, dtype=dtype) for p in feats]
+    z = torch.randn((n_samples, latent_dimensions), generator=g, device=device, dtype=dtype)
+    views = []
+    for w, snr in zip(weights, snrs):
+        x = torch.randn((n_samples, w.shape[0]), generator=g, device=device, dtype=dtype)
+        noise_std = 1.0 / float(np.sqrt(snr)) if snr > 0 else 1.0
+        ops.gemm(z, w, transb=True, alpha=1.0, beta=noise_std, out=x)      # x <- z W^T + noise_std * x
+        views.append(x)
+    return views
+
+
 def conftest_views(name):
     """The seeded fixtures of the reference test-suite (tests/conftest.py:9-59)."""
     rng = np.random.default_rng(42 if name == "two_views_test" else 0)

@@ -268,6 +268,14 @@ def gemm_tc(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, out=None, out
     return out if want_c else out_t
 
 
+def gemm_batched(A, B, transa=False, transb=False, alpha=1.0):
+    """Batched product of (batch, m, k) x (batch, k, n) stacks: tensor cores for TMA-addressable float32 operands,
+    a loop over ``gemm`` otherwise."""
+    if _tc_ok(A) and _tc_ok(B):
+        return gemm_tc(A, B, transa=transa, transb=transb, alpha=alpha)
+    return torch.stack([gemm(A[i], B[i], transa=transa, transb=transb, alpha=alpha) for i in range(A.shape[0])])
+
+
 def whiten_rows(lam, Vt, c, floor_add=0.0, floor_dev=None, scale=1.0, rank_tol=0.0, max_rank=None,
                 lam_floor=-1e300):
     """(Wt, g, rank_dev) -- see ccab_whiten_rows."""
@@ -302,6 +310,41 @@ def ccaloss_small(Cm, d1, d2, eps):
                                     _ptr(G22), _ptr(minp), _stream(Cm))
     _lib.check(rc, "ccab_ccaloss_small")
     return loss, G11, P, G22, minp
+
+
+def ccaloss_fwd(z1, z2, eps, precision="exact"):
+    """Device-side deep-CCA objective (ccab_ccaloss_fwd): returns (loss[1], saved, flags int32[3]) -- all on the device,
+    nothing read back.  z1 / z2: row-major CUDA tensors of one dtype."""
+    lib = _lib.load()
+    _require_cuda(z1, "z1")
+    _require_cuda(z2, "z2")
+    n, d1, d2 = z1.shape[0], z1.shape[1], z2.shape[1]
+    dt = _DT[z1.dtype]
+    prec = {"tf32": _lib.PREC_TF32, "tf32x3": _lib.PREC_TF32X3, "exact": _lib.PREC_EXACT}[precision]
+    if z1.dtype == torch.float64:
+        prec = _lib.PREC_EXACT
+    loss = torch.empty(1, dtype=z1.dtype, device=z1.device)
+    saved = torch.empty(d1 * d1 + d1 * d2 + d2 * d2, dtype=z1.dtype, device=z1.device)
+    flags = torch.empty(3, dtype=torch.int32, device=z1.device)
+    ws = _ws(lib.ccab_ccaloss_workspace_bytes(dt, prec, d1, d2, n), z1.device)
+    with torch.cuda.device(z1.device):
+        rc = lib.ccab_ccaloss_fwd(dt, prec, _ptr(z1), z1.stride(0), _ptr(z2), z2.stride(0), n, d1, d2, float(eps),
+                                  _ptr(loss), _ptr(saved), _ptr(flags), _ptr(ws), ws.numel(), _stream(z1))
+    _lib.check(rc, "ccab_ccaloss_fwd")
+    return loss, saved, flags
+
+
+def ccaloss_bwd(z1, z2, saved, grad_out):
+    """Analytic backward of the deep-CCA objective (ccab_ccaloss_bwd): (dL/dz1, dL/dz2), already scaled by grad_out."""
+    lib = _lib.load()
+    n, d1, d2 = z1.shape[0], z1.shape[1], z2.shape[1]
+    g1 = torch.empty((n, d1), dtype=z1.dtype, device=z1.device)
+    g2 = torch.empty((n, d2), dtype=z1.dtype, device=z1.device)
+    with torch.cuda.device(z1.device):
+        rc = lib.ccab_ccaloss_bwd(_DT[z1.dtype], _ptr(z1), z1.stride(0), _ptr(z2), z2.stride(0), n, d1, d2, _ptr(saved),
+                                  _ptr(grad_out), _ptr(g1), d1, _ptr(g2), d2, _stream(z1))
+    _lib.check(rc, "ccab_ccaloss_bwd")
+    return g1, g2
 
 
 def potrf_(A, pivot_tol=0.0):

@@ -106,6 +106,8 @@ int ccab_gesvj(int dtype, int m, int n, const void* A, int64_t lda, void* sigma,
 
 /* ---- dense glue ----------------------------------------------------------------------------------
  * C (m x n) = alpha * op(A) * op(B) + beta * C, row-major; transX != 0 means op(X) = X^T.
+ * float32 operands that TMA can address (16-byte aligned, leading dimensions % 4 == 0) run on the tensor pipe
+ * (ccab_gemm_tc: 3xTF32, fp32-grade); everything else as exact FMA tiles.
  * Replaces the small products W1^T C12 W2, W @ U (cca_zoo/linear/_rcca.py:96,100), components_.T @ w
  * (cca_zoo/linear/_mcca.py:131) and the S11^-1/2 S12 S22^-1/2 chain (cca_zoo/deep/objectives.py:97). */
 int ccab_gemm(int dtype, int transa, int transb, int m, int n, int k, double alpha, const void* A, int64_t lda,
@@ -192,6 +194,24 @@ int ccab_rcca_fit_result_layout(int dtype, const int64_t* dims, int k, int p, in
 int ccab_rcca_fit(int dtype, const int64_t* dims, const double* moments, const double* n_total_dev, double n_total,
                   int center, const double* c, int k, int p, int iters, void* result, size_t result_bytes,
                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the deep-CCA objective behind the ABI (any widths) ---------------------------------------------------------
+ * ccab_ccaloss_fwd: loss[0] = -|| S11^-1/2 S12 S22^-1/2 ||_F^2 with S_ii = cov(z_i) + eps I, from the moment pass over
+ * [z1 z2] (precision as in ccab_moments), a batched Cholesky + inverse and 7 GEMMs; `saved`
+ * (T[d1*d1 + d1*d2 + d2*d2]) receives G11 = P S21 S11^-1 | P = S11^-1 S12 S22^-1 | G22 = S22^-1 S21 P for the backward.
+ * Nothing is read back: flags_dev (device int[3]) = Cholesky status of S11, S22 (a pivot^2 <= eps / 4 counts as a failure:
+ * rounding destroyed the ridge; the caller re-runs through the eigen route, which clamps like the reference) and a
+ * non-finite-input flag -- check lazily.
+ * ccab_ccaloss_bwd: g1 = 2/(n-1) center(z1 G11 - z2 P^T) * grad_out[0], g2 = 2/(n-1) center(z2 G22 - z1 P) * grad_out[0]
+ * (grad_out: device scalar, may be NULL = 1).  4 tall GEMMs (tcgen05 for float) + 2 centring passes.
+ * Replaces cca_zoo/deep/objectives.py:9-21,79-102 and torch autograd through two eigh + eigvalsh. */
+size_t ccab_ccaloss_workspace_bytes(int dtype, int precision, int d1, int d2, int64_t n);
+int ccab_ccaloss_fwd(int dtype, int precision, const void* z1, int64_t ld1, const void* z2, int64_t ld2, int64_t n,
+                     int d1, int d2, double eps, void* loss, void* saved, int* flags_dev, void* workspace,
+                     size_t workspace_bytes, void* stream);
+int ccab_ccaloss_bwd(int dtype, const void* z1, int64_t ld1, const void* z2, int64_t ld2, int64_t n, int d1, int d2,
+                     const void* saved, const void* grad_out, void* g1, int64_t ldg1, void* g2, int64_t ldg2,
+                     void* stream);
 
 /* B[i,j] = A[i,j] * f(r[i]) * f(c[j]); r / c may be NULL; *_pow: 0 -> x, 1 -> 1/x, 2 -> 1/sqrt(x).
  * (column scalings such as diag(sigma)^-1/2 in the GCCA back-substitution, cca_zoo/linear/_gcca.py:109) */

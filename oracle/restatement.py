@@ -286,6 +286,32 @@ def ref_ccaloss(z1, z2, eps=1e-5):
     return -np.maximum(ev, 0.0).sum()
 
 
+def ref_ccaloss_torch_fwdbwd(z1, z2, eps=1e-5):
+    """cca_zoo/deep/objectives.py:9-21,79-102 restated with torch on the CPU, forward AND autograd backward: the
+    arithmetic (eigh-based inverse square roots, eigvalsh of T^T T, torch autograd through them) the reference runs
+    in a training step.  ``z1``, ``z2``: torch CPU tensors.  Returns (loss, grad1, grad2).  Used as the CPU arm of
+    bench.py's config-3 workloads and checked against tests/golden (reference outputs) by tests/test_oracle_golden."""
+    import torch
+
+    def inv_sqrtm(A):
+        L, V = torch.linalg.eigh(A)
+        L = torch.clamp(L, min=eps)
+        return V @ torch.diag(1.0 / torch.sqrt(L)) @ V.T
+
+    a = z1.detach().clone().requires_grad_(True)
+    b = z2.detach().clone().requires_grad_(True)
+    n, d1, d2 = a.shape[0], a.shape[1], b.shape[1]
+    x1 = a - a.mean(dim=0)
+    x2 = b - b.mean(dim=0)
+    s11 = (x1.T @ x1) / (n - 1) + eps * torch.eye(d1, dtype=a.dtype)
+    s22 = (x2.T @ x2) / (n - 1) + eps * torch.eye(d2, dtype=a.dtype)
+    s12 = (x1.T @ x2) / (n - 1)
+    t = inv_sqrtm(s11) @ s12 @ inv_sqrtm(s22)
+    loss = -torch.clamp(torch.linalg.eigvalsh(t.T @ t), min=0.0).sum()
+    loss.backward()
+    return loss.detach(), a.grad, b.grad
+
+
 def ref_gccaloss(zs, eps=1e-5):
     """cca_zoo/deep/objectives.py:196-220 (forward only; forms the n x n matrix like the reference)."""
     n = zs[0].shape[0]

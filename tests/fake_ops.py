@@ -168,6 +168,63 @@ def ccaloss_small(Cm, d1, d2, eps):
     return loss.reshape(1).to(dt), G11.to(dt), P.to(dt), G22.to(dt), minp.reshape(1).to(dt)
 
 
+def potrf_inv_(A, pivot_tol=0.0):
+    squeeze = A.dim() == 2
+    Ab = A.unsqueeze(0) if squeeze else A
+    infos, invs = [], []
+    for b in range(Ab.shape[0]):
+        info = potrf_(Ab[b], pivot_tol)
+        infos.append(info)
+        L = torch.tril(Ab[b]).to(torch.float64)
+        invs.append(torch.linalg.inv(L).to(A.dtype) if int(info) == 0 else torch.zeros_like(Ab[b]))
+    Linv = torch.stack(invs)
+    return (Linv[0] if squeeze else Linv), torch.cat(infos)
+
+
+def gemm_batched(A, B, transa=False, transb=False, alpha=1.0):
+    return torch.stack([gemm(A[i], B[i], transa=transa, transb=transb, alpha=alpha) for i in range(A.shape[0])])
+
+
+def ccaloss_fwd(z1, z2, eps, precision="exact"):
+    n, d1, d2 = z1.shape[0], z1.shape[1], z2.shape[1]
+    dt = z1.dtype
+    mom = moments([z1, z2])
+    flags = torch.zeros(3, dtype=torch.int32)
+    if not bool(torch.isfinite(mom).all()):
+        flags[2] = 1
+    C, _ = covariance(mom, [d1, d2], n, True, torch.float64)
+    S11 = C[:d1, :d1] + eps * torch.eye(d1, dtype=torch.float64)
+    S22 = C[d1:, d1:] + eps * torch.eye(d2, dtype=torch.float64)
+    S12 = C[:d1, d1:]
+    for i, S in enumerate((S11, S22)):
+        L, info = torch.linalg.cholesky_ex(S)
+        if int(info) != 0 or bool((L.diagonal() ** 2 <= 0.25 * eps).any()):
+            flags[i] = 1
+    A1, A2 = torch.linalg.inv(S11), torch.linalg.inv(S22)
+    P = A1 @ S12 @ A2
+    G11 = P @ S12.T @ A1
+    G22 = A2 @ S12.T @ P
+    loss = -(P * S12).sum()
+    saved = torch.cat([G11.reshape(-1), P.reshape(-1), G22.reshape(-1)]).to(dt)
+    return loss.reshape(1).to(dt), saved, flags
+
+
+def ccaloss_bwd(z1, z2, saved, grad_out):
+    n, d1, d2 = z1.shape[0], z1.shape[1], z2.shape[1]
+    s64 = saved.to(torch.float64)
+    G11 = s64[:d1 * d1].reshape(d1, d1)
+    P = s64[d1 * d1:d1 * d1 + d1 * d2].reshape(d1, d2)
+    G22 = s64[d1 * d1 + d1 * d2:].reshape(d2, d2)
+    a = 2.0 / (n - 1)
+    x1, x2 = z1.to(torch.float64), z2.to(torch.float64)
+    g1 = a * (x1 @ G11 - x2 @ P.T)
+    g2 = a * (x2 @ G22 - x1 @ P)
+    go = float(grad_out.reshape(-1)[0]) if grad_out is not None else 1.0
+    g1 = (g1 - g1.mean(dim=0, keepdim=True)) * go
+    g2 = (g2 - g2.mean(dim=0, keepdim=True)) * go
+    return g1.to(z1.dtype), g2.to(z1.dtype)
+
+
 def debug_set(key, value):
     return None
 

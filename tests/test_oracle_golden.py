@@ -98,6 +98,20 @@ def test_loss_oracle_matches_golden(name):
             np.testing.assert_allclose(g, gr, rtol=1e-7, atol=1e-12)
 
 
+def test_torch_restatement_of_the_loss_matches_reference_autograd():
+    """oracle.ref_ccaloss_torch_fwdbwd (the CPU arm of bench.py's config-3 workloads) against the reference's own
+    forward + autograd gradients stored in tests/golden."""
+    for name, c in G.LOSS_CASES.items():
+        if c["kind"] != "cca":
+            continue
+        loss_ref, grads_ref = G.loss_outputs(name)
+        z = G.loss_inputs(name)
+        L, ga, gb = R.ref_ccaloss_torch_fwdbwd(z[0], z[1], c["eps"])
+        assert abs(float(L) - loss_ref) < 1e-10 * abs(loss_ref)
+        np.testing.assert_allclose(ga.numpy(), grads_ref[0], rtol=1e-7, atol=1e-11)
+        np.testing.assert_allclose(gb.numpy(), grads_ref[1], rtol=1e-7, atol=1e-11)
+
+
 def test_known_answers_from_survey():
     """Known answers recorded in SURVEY.md §8c from the reference run."""
     from cca_zoo_b200.datasets import conftest_views
