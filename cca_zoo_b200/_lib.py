@@ -59,6 +59,10 @@ SIGNATURES = {
                                    C.c_double, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "ccab_ccaloss_bwd": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp,
                                    C.c_int64, _vp, C.c_int64, _vp]),
+    "ccab_mcca_fit_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, _i64p, C.c_int, C.c_int]),
+    "ccab_mcca_fit_result_layout": (C.c_int, [C.c_int, C.c_int, _i64p, C.c_int, C.c_int, _i64p]),
+    "ccab_mcca_fit": (C.c_int, [C.c_int, C.c_int, _i64p, _vp, _vp, C.c_double, C.c_int, C.POINTER(C.c_double),
+                                C.c_double, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp, C.c_size_t, _vp]),
     "ccab_trsm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp]),
     "ccab_scale": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int64,
                              _vp]),

@@ -487,6 +487,44 @@ int ccab_ccaloss_bwd(int dtype, const void* z1, int64_t ld1, const void* z2, int
   CCAB_CATCH
 }
 
+size_t ccab_mcca_fit_workspace_bytes(int dtype, int n_views, const int64_t* dims, int k, int p) {
+  ColumnLayout L;
+  if (!dims || make_layout(n_views, dims, &L) || k < 1 || p < k) return 0;
+  return dtype == CCAB_F32 ? mcca_fit_workspace_bytes<float>(L, k, p) : mcca_fit_workspace_bytes<double>(L, k, p);
+}
+
+int ccab_mcca_fit_result_layout(int dtype, int n_views, const int64_t* dims, int k, int p, int64_t* offsets) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dims && offsets && k >= 1 && p >= k, "bad argument");
+  ColumnLayout L;
+  int rc = make_layout(n_views, dims, &L);
+  if (rc) return rc;
+  if (dtype == CCAB_F32) mcca_fit_result_layout<float>(L, k, p, offsets);
+  else mcca_fit_result_layout<double>(L, k, p, offsets);
+  return 0;
+  CCAB_CATCH
+}
+
+int ccab_mcca_fit(int dtype, int n_views, const int64_t* dims, const double* moments, const double* n_total_dev,
+                  double n_total, int center, const double* c, double eps, int k, int p, int iters, void* result,
+                  size_t result_bytes, void* workspace, size_t workspace_bytes, void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(dims && moments && c && result && workspace, "null pointer argument");
+  ColumnLayout L;
+  int rc = make_layout(n_views, dims, &L);
+  if (rc) return rc;
+  rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CCAB_F32)
+    return mcca_fit<float>(L, moments, n_total_dev, n_total, center, c, eps, k, p, iters, result, result_bytes,
+                           workspace, workspace_bytes, s);
+  return mcca_fit<double>(L, moments, n_total_dev, n_total, center, c, eps, k, p, iters, result, result_bytes, workspace,
+                          workspace_bytes, s);
+  CCAB_CATCH
+}
+
 int ccab_scale(int dtype, int m, int n, const void* A, int64_t lda, const void* r, int r_pow, const void* c,
                int c_pow, void* B, int64_t ldb, void* stream) {
   CCAB_TRY

@@ -43,6 +43,7 @@ struct CovRidgeParams {
 struct PivotTolParams {
   int n_views;
   double c[kMaxViews], rank_tol[kMaxViews];
+  double floor;   // lower bound of the tolerance (MCCA's eps floor: lambda_min(B) < eps must not pass)
 };
 
 __device__ __forceinline__ int view_of(const CovRidgeParams& p, int g) {
@@ -86,7 +87,7 @@ __global__ void cov_ridge_kernel(const CovRidgeParams p, const double* __restric
 // s > 0 filter on the regularised spectrum, _solvers._rank_tol)
 __global__ void pivot_tol_kernel(const PivotTolParams q, const unsigned* __restrict__ dmax, double* __restrict__ tol) {
   const int v = threadIdx.x;
-  if (v < q.n_views) tol[v] = q.rank_tol[v] * ((1.0 - q.c[v]) * (double)__uint_as_float(dmax[v]) + q.c[v]);
+  if (v < q.n_views) tol[v] = fmax(q.floor, q.rank_tol[v] * ((1.0 - q.c[v]) * (double)__uint_as_float(dmax[v]) + q.c[v]));
 }
 
 // counter-based standard normal start block (splitmix64 hash + Box-Muller): reproducible, no generator state
@@ -438,6 +439,283 @@ int rcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
   return 0;
 }
 
+
+// =============================================================================================================
+// mcca_fit : cca_zoo/linear/_mcca.py:113-173 (pca=False form) through the Cholesky reduction of A v = lam B v
+//   B_i = (1-c_i) C_ii + c_i I = L_i L_i^T (batched when the views have one width), K_ij = L_i^-1 C_ij L_j^-T (i != j,
+//   zero diagonal blocks), largest k eigenpairs of K by blocked subspace iteration on K + shift I
+//   (shift = 1 / (1 - max c) >= -lambda_min(K): the whitened cross blocks have ||K|| <= (m-1) / (1 - max c) ... the
+//   shift only has to make the iterated matrix positive on the wanted end), Rayleigh-Ritz through the two-sided
+//   single-CTA Jacobi (which needs no shift), v_i = sqrt(m) L_i^-T y_i  (v^T B v = 1 with B / m, scipy's normalisation).
+//   The eps floor of _build_B (:170-172) is only active when lambda_min(B) < eps: the pivot tolerance of the Cholesky
+//   is raised to eps so that such problems fail the factorisation and are declined to the host-assembled eigen route.
+// =============================================================================================================
+namespace {
+
+struct MccaPlan {
+  int m, D, k, p, dmax;
+  bool equal;
+  int64_t ldC, ldR, strideR, ldp, ldk;
+  int off[kMaxViews + 1];
+  size_t oC, oR, oLinv, oTmp, oK, oZ, oZ2, oY, oG, oGinv, oH, oLam, oVy, oZr, oE, oPws, oSmall, total;
+  size_t pws_bytes;
+  size_t r_mean, r_val, r_w[kMaxViews], r_total;
+};
+
+template <typename T>
+MccaPlan make_mcca_plan(const ColumnLayout& L, int k, int p) {
+  MccaPlan P;
+  P.m = L.n_views; P.D = L.D; P.k = k; P.p = p;
+  P.dmax = 0;
+  P.equal = true;
+  for (int v = 0; v < P.m; ++v) {
+    P.dmax = std::max(P.dmax, L.dims[v]);
+    if (L.dims[v] != L.dims[0]) P.equal = false;
+    P.off[v] = L.coff[v];
+  }
+  P.off[P.m] = L.D;
+  P.ldC = r4(P.D); P.ldR = r4(P.dmax); P.strideR = (int64_t)P.dmax * P.ldR; P.ldp = r4(p); P.ldk = r4(k);
+  const int NB = potrf_inv_block_size<T>();
+  size_t o = 0;
+  auto take = [&](size_t elems) { size_t at = o; o += al256(elems * sizeof(T)); return at; };
+  P.oC = take((size_t)P.D * P.ldC);
+  P.oR = take((size_t)P.m * P.strideR);
+  P.oLinv = take((size_t)P.m * P.strideR);
+  P.oTmp = take((size_t)P.dmax * P.ldR);
+  P.oK = take((size_t)P.D * P.ldC);
+  P.oZ = take((size_t)P.D * P.ldp);
+  P.oZ2 = take((size_t)P.D * P.ldp);
+  P.oY = take((size_t)P.D * P.ldp);
+  P.oG = take((size_t)p * P.ldp);
+  P.oGinv = take((size_t)std::max(p, NB) * std::max<int64_t>(P.ldp, NB));
+  P.oH = take((size_t)p * P.ldp);
+  P.oLam = take((size_t)p);
+  P.oVy = take((size_t)p * P.ldp);
+  P.oZr = take((size_t)P.D * P.ldk);
+  P.oE = take((size_t)P.D * P.ldk);
+  P.pws_bytes = std::max(potrf_inv_workspace_bytes<T>(P.dmax, P.m), potrf_inv_workspace_bytes<T>(p, 1));
+  P.oPws = o; o += al256(P.pws_bytes);
+  P.oSmall = o; o += 4096;
+  P.total = o + 256;
+  size_t r = sizeof(double) * kFitHeaderDoubles;
+  P.r_mean = r; r += al256(sizeof(double) * P.D);
+  P.r_val = r; r += al256(sizeof(T) * k);
+  for (int v = 0; v < P.m; ++v) { P.r_w[v] = r; r += al256(sizeof(T) * (size_t)L.dims[v] * k); }
+  P.r_total = r;
+  return P;
+}
+
+// stats[0] = || E - Zr diag(theta) ||_F^2 over the D x k blocks, stats[1] = |theta_0| + shift
+template <typename T>
+__global__ void sym_residual_kernel(const T* __restrict__ E, int64_t lde, const T* __restrict__ Zr, int64_t ldz, int rows,
+                                    int k, const T* __restrict__ theta, double shift, double* __restrict__ stats) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < rows * k; e += blockDim.x) {
+    const int i = e / k, j = e % k;
+    const double d = (double)E[(size_t)i * lde + j] - (double)Zr[(size_t)i * ldz + j] * (double)theta[j];
+    acc += d * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    stats[0] = t;
+    stats[1] = fabs((double)theta[0]) + shift;
+  }
+}
+
+template <typename T>
+__global__ void copy_vals_kernel(const T* __restrict__ src, T* __restrict__ dst, int k) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < k) dst[j] = src[j];
+}
+
+}  // namespace
+
+template <typename T>
+size_t mcca_fit_workspace_bytes(const ColumnLayout& L, int k, int p) {
+  return make_mcca_plan<T>(L, k, p).total;
+}
+
+template <typename T>
+void mcca_fit_result_layout(const ColumnLayout& L, int k, int p, int64_t* offsets) {
+  MccaPlan P = make_mcca_plan<T>(L, k, p);
+  offsets[0] = (int64_t)P.r_mean;
+  offsets[1] = (int64_t)P.r_val;
+  for (int v = 0; v < P.m; ++v) offsets[2 + v] = (int64_t)P.r_w[v];
+  offsets[2 + P.m] = (int64_t)P.r_total;
+}
+
+template <typename T>
+int mcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, double n_host, int center,
+             const double* c, double eps_floor, int k, int p, int iters, void* result, size_t result_bytes, void* ws,
+             size_t ws_bytes, cudaStream_t s) {
+  const int m = L.n_views, D = L.D;
+  CCAB_CHECK_ARG(m >= 2, "mcca_fit needs at least 2 views");
+  CCAB_CHECK_ARG(k >= 1 && p >= k && p <= D, "mcca_fit: need 1 <= k <= p <= D, got k=%d p=%d", k, p);
+  CCAB_CHECK_ARG(syevj_small_supported<T>(p), "mcca_fit: subspace width %d exceeds the single-CTA eigensolver", p);
+  CCAB_CHECK_ARG(iters >= 1 && iters <= 60, "mcca_fit: bad iteration count %d", iters);
+  double cmax = 0.0;
+  for (int v = 0; v < m; ++v) cmax = std::max(cmax, c[v]);
+  CCAB_CHECK_ARG(cmax <= 0.9, "mcca_fit: max c = %g > 0.9 (no a-priori shift); use the host-assembled route", cmax);
+  MccaPlan P = make_mcca_plan<T>(L, k, p);
+  CCAB_CHECK_ARG(ws_bytes >= P.total, "mcca_fit workspace too small: %zu < %zu", ws_bytes, P.total);
+  CCAB_CHECK_ARG(result_bytes >= P.r_total, "mcca_fit result block too small: %zu < %zu", result_bytes, P.r_total);
+  uint8_t* w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  uint8_t* res = static_cast<uint8_t*>(result);
+  CCAB_CHECK_ARG((reinterpret_cast<uintptr_t>(res) & 255) == 0, "mcca_fit: result block must be 256-byte aligned");
+  auto at = [&](size_t off) { return reinterpret_cast<T*>(w + off); };
+  T *C = at(P.oC), *R = at(P.oR), *Linv = at(P.oLinv), *Tmp = at(P.oTmp), *K = at(P.oK), *Z = at(P.oZ), *Z2 = at(P.oZ2),
+    *Y = at(P.oY), *H = at(P.oH), *lam = at(P.oLam), *Vy = at(P.oVy), *Zr = at(P.oZr), *E = at(P.oE);
+  CholQrWs<T> cq;
+  cq.G = at(P.oG);
+  cq.Ginv = at(P.oGinv);
+  cq.pws = w + P.oPws;
+  cq.pws_bytes = P.pws_bytes;
+  cq.ldg = P.ldp;
+  uint8_t* sm = w + P.oSmall;
+  int* flags = reinterpret_cast<int*>(sm);
+  int* infos = flags + 4;                                      // [m + iters + 4]
+  const int n_infos = m + iters + 4;
+  int* rr_info = infos + 100;
+  unsigned* dmax = reinterpret_cast<unsigned*>(sm + 512);
+  double* tol = reinterpret_cast<double*>(sm + 1024);          // [m]
+  double* stats = tol + kMaxViews;                             // [2]
+  CCAB_CUDA(cudaMemsetAsync(sm, 0, 2048, s));
+  CCAB_CUDA(cudaMemsetAsync(K, 0, sizeof(T) * (size_t)D * P.ldC, s));
+  double* hdr = reinterpret_cast<double*>(res);
+  double* mean = reinterpret_cast<double*>(res + P.r_mean);
+  T* vals = reinterpret_cast<T*>(res + P.r_val);
+
+  // ---- covariance + ridge blocks (np.cov always centres: the caller passes center accordingly) ----
+  {
+    CovRidgeParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.n_views = m; cp.D = D; cp.Dp = L.Dp;
+    PivotTolParams q;
+    memset(&q, 0, sizeof(q));
+    q.n_views = m;
+    for (int v = 0; v < m; ++v) {
+      cp.dims[v] = L.dims[v]; cp.c[v] = c[v];
+      cp.R[v] = R + (size_t)v * P.strideR; cp.ldr[v] = P.ldR;
+      q.c[v] = c[v]; q.rank_tol[v] = L.dims[v] * eps_of<T>();
+    }
+    for (int v = 0; v <= m; ++v) { cp.coff[v] = L.coff[v]; cp.poff[v] = L.poff[v]; }
+    q.floor = eps_floor;
+    dim3 block(32, 8), grid((unsigned)ceil_div(D, 32), (unsigned)ceil_div(D, 8));
+    cov_ridge_kernel<T><<<grid, block, 0, s>>>(cp, moments, n_dev, n_host, center, C, P.ldC, mean, dmax, flags);
+    count_launches(1);
+    pivot_tol_kernel<<<1, 32, 0, s>>>(q, dmax, tol);
+    count_launches(1);
+    CCAB_CUDA(cudaGetLastError());
+  }
+  int rc;
+  if (P.equal) {
+    rc = potrf_inv<T>(L.dims[0], m, R, P.ldR, P.strideR, Linv, P.ldR, P.strideR, 0.0, tol, infos, cq.pws, cq.pws_bytes, s);
+    if (rc) return rc;
+  } else {
+    for (int v = 0; v < m; ++v) {
+      rc = potrf_inv<T>(L.dims[v], 1, R + (size_t)v * P.strideR, P.ldR, 0, Linv + (size_t)v * P.strideR, P.ldR, 0, 0.0,
+                        tol + v, infos + v, cq.pws, cq.pws_bytes, s);
+      if (rc) return rc;
+    }
+  }
+  // ---- K_ij = Linv_i C_ij Linv_j^T (and its mirror) ----
+  for (int i = 0; i < m; ++i)
+    for (int j = i + 1; j < m; ++j) {
+      const int di = L.dims[i], dj = L.dims[j];
+      GemmArgs<T> g;
+      g.m = di; g.n = dj; g.k = di;
+      g.A = Linv + (size_t)i * P.strideR; g.lda = P.ldR;
+      g.B = C + (size_t)P.off[i] * P.ldC + P.off[j]; g.ldb = P.ldC; g.C = Tmp; g.ldc = P.ldR;
+      rc = xgemm<T>(g, s);
+      if (rc) return rc;
+      GemmArgs<T> h;
+      h.transb = 1; h.m = di; h.n = dj; h.k = dj;
+      h.A = Tmp; h.lda = P.ldR; h.B = Linv + (size_t)j * P.strideR; h.ldb = P.ldR;
+      h.C = K + (size_t)P.off[i] * P.ldC + P.off[j]; h.ldc = P.ldC;
+      h.Ct = K + (size_t)P.off[j] * P.ldC + P.off[i]; h.ldct = P.ldC;
+      rc = xgemm<T>(h, s);
+      if (rc) return rc;
+    }
+  // ---- subspace iteration on K + shift I ----
+  const double shift = 1.0 / (1.0 - cmax);
+  {
+    const size_t total = (size_t)D * p;
+    randn_kernel<T><<<(unsigned)std::min<size_t>((total + 255) / 256, 592), 256, 0, s>>>(Z2, P.ldp, D, p, 0x4321ull);
+    count_launches(1);
+    CCAB_CUDA(cudaGetLastError());
+  }
+  int slot = m;
+  rc = cholqr<T>(Z2, P.ldp, Z, P.ldp, D, p, cq, infos + slot++, s);
+  if (rc) return rc;
+  for (int it = 0; it < iters; ++it) {
+    CCAB_CUDA(cudaMemcpy2DAsync(Y, P.ldp * sizeof(T), Z, P.ldp * sizeof(T), (size_t)p * sizeof(T), (size_t)D,
+                                cudaMemcpyDeviceToDevice, s));
+    GemmArgs<T> a;   // Y = K Z + shift Z
+    a.m = D; a.n = p; a.k = D; a.beta = (T)shift; a.A = K; a.lda = P.ldC; a.B = Z; a.ldb = P.ldp; a.C = Y; a.ldc = P.ldp;
+    rc = xgemm<T>(a, s);
+    if (rc) return rc;
+    rc = cholqr<T>(Y, P.ldp, Z, P.ldp, D, p, cq, infos + slot++, s);
+    if (rc) return rc;
+    if (it == iters - 1) {
+      rc = cholqr<T>(Z, P.ldp, Z2, P.ldp, D, p, cq, infos + slot++, s);
+      if (rc) return rc;
+      std::swap(Z, Z2);
+    }
+  }
+  // ---- Rayleigh-Ritz: H = Z^T K Z ----
+  {
+    GemmArgs<T> a;
+    a.m = D; a.n = p; a.k = D; a.A = K; a.lda = P.ldC; a.B = Z; a.ldb = P.ldp; a.C = Y; a.ldc = P.ldp;   // Y = K Z
+    rc = xgemm<T>(a, s);
+    if (rc) return rc;
+    GemmArgs<T> h;
+    h.transa = 1; h.m = p; h.n = p; h.k = D; h.A = Z; h.lda = P.ldp; h.B = Y; h.ldb = P.ldp; h.C = H; h.ldc = P.ldp;
+    rc = xgemm<T>(h, s);
+    if (rc) return rc;
+    rc = syevj_small<T>(p, 1, H, P.ldp, 0, lam, p, Vy, P.ldp, 0, rr_info, s);
+    if (rc) return rc;
+    GemmArgs<T> u;   // Ritz vectors Zr = Z Q_k
+    u.transb = 1; u.m = D; u.n = k; u.k = p; u.A = Z; u.lda = P.ldp; u.B = Vy; u.ldb = P.ldp; u.C = Zr; u.ldc = P.ldk;
+    rc = xgemm<T>(u, s);
+    if (rc) return rc;
+    GemmArgs<T> e;   // E = (K Z) Q_k
+    e.transb = 1; e.m = D; e.n = k; e.k = p; e.A = Y; e.lda = P.ldp; e.B = Vy; e.ldb = P.ldp; e.C = E; e.ldc = P.ldk;
+    rc = xgemm<T>(e, s);
+    if (rc) return rc;
+    sym_residual_kernel<T><<<1, 1024, 0, s>>>(E, P.ldk, Zr, P.ldk, D, k, lam, shift, stats);
+    copy_vals_kernel<T><<<(unsigned)ceil_div(k, 128), 128, 0, s>>>(lam, vals, k);
+    count_launches(2);
+    CCAB_CUDA(cudaGetLastError());
+  }
+  // ---- v_i = sqrt(m) Linv_i^T y_i ----
+  for (int v = 0; v < m; ++v) {
+    GemmArgs<T> a;
+    a.transa = 1; a.m = L.dims[v]; a.n = k; a.k = L.dims[v]; a.alpha = (T)std::sqrt((double)m);
+    a.A = Linv + (size_t)v * P.strideR; a.lda = P.ldR; a.B = Zr + (size_t)P.off[v] * P.ldk; a.ldb = P.ldk;
+    a.C = reinterpret_cast<T*>(res + P.r_w[v]); a.ldc = k;
+    rc = xgemm<T>(a, s);
+    if (rc) return rc;
+  }
+  fit_status_kernel<<<1, 32, 0, s>>>(hdr, flags, infos, n_infos, rr_info, stats, n_dev, n_host, 200.0 * eps_of<T>(), k,
+                                    P.dmax);
+  count_launches(1);
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template size_t mcca_fit_workspace_bytes<float>(const ColumnLayout&, int, int);
+template size_t mcca_fit_workspace_bytes<double>(const ColumnLayout&, int, int);
+template void mcca_fit_result_layout<float>(const ColumnLayout&, int, int, int64_t*);
+template void mcca_fit_result_layout<double>(const ColumnLayout&, int, int, int64_t*);
+template int mcca_fit<float>(const ColumnLayout&, const double*, const double*, double, int, const double*, double, int,
+                             int, int, void*, size_t, void*, size_t, cudaStream_t);
+template int mcca_fit<double>(const ColumnLayout&, const double*, const double*, double, int, const double*, double, int,
+                              int, int, void*, size_t, void*, size_t, cudaStream_t);
 
 // =============================================================================================================
 // Deep-CCA objective (cca_zoo/deep/objectives.py:61-102) on the device, any widths, no host read-back.

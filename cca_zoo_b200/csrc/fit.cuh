@@ -25,6 +25,17 @@ int rcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
              const double* c, int k, int p, int iters, void* result, size_t result_bytes, void* ws, size_t ws_bytes,
              cudaStream_t stream);
 
+// MCCA (cca_zoo/linear/_mcca.py:113-173, pca=False form): result block = header | mean | eigenvalues T[k] | W_1 .. W_m
+// (offsets: mean, values, W_1 .. W_m, total = m + 3 entries).  c: host double[m], eps_floor: the reference's eps.
+template <typename T>
+size_t mcca_fit_workspace_bytes(const ColumnLayout& L, int k, int p);
+template <typename T>
+void mcca_fit_result_layout(const ColumnLayout& L, int k, int p, int64_t* offsets);
+template <typename T>
+int mcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, double n_host, int center,
+             const double* c, double eps_floor, int k, int p, int iters, void* result, size_t result_bytes, void* ws,
+             size_t ws_bytes, cudaStream_t stream);
+
 // ---- deep-CCA objective on the device (cca_zoo/deep/objectives.py:61-102), any widths, nothing read back ----
 // saved (T[d1*d1 + d1*d2 + d2*d2]) = G11 | P | G22 for the analytic backward; flags_out (device int[3]) = Cholesky
 // status of S11, S22 (pivot^2 <= eps / 4 counts as failure) and a non-finite-input flag, to be checked lazily.

@@ -802,8 +802,16 @@ int jacobi_solve(const JacobiArgs<T>& a, void* ws, size_t ws_bytes, cudaStream_t
     jacobi_reset_stat_kernel<<<1, 1024, 0, stream>>>(c.stat, batch); count_launches(1);
   }
   if (rc) return rc;
-  if (a.info) { a.info[0] = sweeps_done; }
+  // "no silent fallback": a solve that ran out of sweeps reports it -- info[0] = -sweeps, and the call fails unless the
+  // caller asked for the diagnostics (info != NULL) and therefore handles the sign itself
+  const bool converged = last_ratio >= 0.f && last_ratio <= (float)tol;
+  if (a.info) { a.info[0] = converged ? sweeps_done : -sweeps_done; }
   if (a.final_offdiag) *a.final_offdiag = last_ratio;
+  if (!converged && !a.info) {
+    set_error("Jacobi iteration did not converge in %d sweeps (normalised off-diagonal %.3e > tolerance %.3e)",
+              sweeps_done, (double)last_ratio, (double)tol);
+    return -20;
+  }
 
   jacobi_values_kernel<T><<<dim3((unsigned)ceil_div(P.n_pad, 8), batch), 256, 0, stream>>>(c, n, a.svd_mode, shift, vals, vnorm); count_launches(1);
   jacobi_rank_kernel<T><<<dim3((unsigned)ceil_div(P.n_pad, 256), batch), 256, 0, stream>>>(vals, P.n_pad, rank); count_launches(1);

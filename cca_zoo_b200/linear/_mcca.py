@@ -6,9 +6,10 @@ from typing import Any, ClassVar
 
 from sklearn.utils._param_validation import Interval, StrOptions
 
+from .. import ops
 from .._base import BaseModel
 from .._solvers import mcca_weights
-from .._validation import perview_parameter
+from .._validation import perview_parameter, validate_views
 from ._rcca import RIDGE_PARAMETER
 
 #: cca_zoo/_utils/_param_constraints.py:22 (POSITIVE_EPS)
@@ -47,8 +48,33 @@ class MCCA(BaseModel):
         self.solver = solver
 
     def fit(self, views, y=None):
-        C, dims, n_total = self._fit_device(views)
-        return self._finish(self._solve(C, dims, n_total))
+        self._validate_params()
+        validated = validate_views(views)
+        device = self._device()
+        mom, n_local, dims, in_dtype = self._local_moments(validated, device)
+        self._partial = None
+        return self._fit_moments(mom, n_local, dims, in_dtype)
+
+    def _device_fit_plan(self, dims, n_local, in_dtype):
+        """Device-side fit (csrc/fit.cu: mcca_fit) for plain MCCA on large, well-posed problems; subclasses that
+        rebuild A / B (GRCCA, PartialCCA) assemble on the host and never get here."""
+        if type(self) is not MCCA or self.solver == "eigen":
+            return None
+        D = int(sum(dims))
+        if self.solver == "auto" and not (D >= 512 and n_local > max(dims)):
+            return None
+        k = min(int(self.latent_dimensions), D)
+        p = min(D, max(2 * k, k + 32))
+        c_ = [float(x) for x in perview_parameter("c", self.c, 0.0, len(dims))]
+        if 4 * k > D or p > 128 or max(c_) > 0.9:
+            return None
+        eps = float(self.eps)
+
+        def call(mom, dims_, n_host, n_dev, solve_dtype, iters):
+            # np.cov centres regardless of `center` (cca_zoo/linear/_mcca.py:150,166)
+            return ops.mcca_fit(mom, dims_, n_host, n_dev, True, c_, eps, k, p, iters, solve_dtype)
+
+        return {"call": call, "k": k, "iters": [8, 32]}
 
     def _solve(self, C, dims, n_total):
         c_ = perview_parameter("c", self.c, 0.0, self.n_views_)

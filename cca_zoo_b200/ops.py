@@ -118,6 +118,15 @@ def covariance(mom: torch.Tensor, dims, n_total: float, center: bool = True, dty
 # --------------------------------------------------------------------------------------------------
 # K3 / K4
 # --------------------------------------------------------------------------------------------------
+def _jacobi_converged(what, sweeps, offdiag, caller_checks):
+    """The library reports a solve that ran out of sweeps as a negative sweep count: no silent use of unconverged
+    eigen / singular vectors.  Callers that ask for the diagnostics (return_info=True) decide themselves."""
+    if sweeps < 0 and not caller_checks:
+        raise RuntimeError(f"{what}: the Jacobi iteration did not converge in {-sweeps} sweeps "
+                           f"(normalised off-diagonal {offdiag:.3e}); the matrix may contain NaN / inf or be "
+                           f"pathologically scaled")
+
+
 def syevj(A: torch.Tensor, shift: float = 0.0, return_info: bool = False):
     """Symmetric eigendecomposition.  A: (n,n) or (batch,n,n).  Returns (evals desc, evecs_t) where
     evecs_t[..., j, :] is the j-th eigenvector."""
@@ -138,10 +147,11 @@ def syevj(A: torch.Tensor, shift: float = 0.0, return_info: bool = False):
         rc = lib.ccab_syevj(dt, n, batch, _ptr(Ab), n, n * n, float(shift), _ptr(evals), _ptr(evt), n,
                             C.byref(info), C.byref(off), _ptr(ws), ws.numel(), _stream(Ab))
     _lib.check(rc, "ccab_syevj")
+    _jacobi_converged("ccab_syevj", info.value, off.value, return_info)
     if squeeze:
         evals, evt = evals[0], evt[0]
     if return_info:
-        return evals, evt, {"sweeps": info.value, "offdiag": off.value}
+        return evals, evt, {"sweeps": abs(info.value), "offdiag": off.value, "converged": info.value > 0}
     return evals, evt
 
 
@@ -185,8 +195,9 @@ def gesvj(Gt: torch.Tensor, return_info: bool = False):
         rc = lib.ccab_gesvj(dt, m, n, _ptr(Gt), m, _ptr(sigma), _ptr(right), n, _ptr(left), m, C.byref(info),
                             C.byref(off), _ptr(ws), ws.numel(), _stream(Gt))
     _lib.check(rc, "ccab_gesvj")
+    _jacobi_converged("ccab_gesvj", info.value, off.value, return_info)
     if return_info:
-        return sigma, right, left, {"sweeps": info.value, "offdiag": off.value}
+        return sigma, right, left, {"sweeps": abs(info.value), "offdiag": off.value, "converged": info.value > 0}
     return sigma, right, left
 
 
@@ -431,6 +442,30 @@ def rcca_fit(mom: torch.Tensor, dims, n_host, n_dev, center: bool, c, k: int, p:
                                1 if center else 0, cc, int(k), int(p), int(iters), _ptr(block), block.numel(), _ptr(ws),
                                ws.numel(), _stream(mom))
     _lib.check(rc, "ccab_rcca_fit")
+    return block, offsets
+
+
+def mcca_fit(mom: torch.Tensor, dims, n_host, n_dev, center: bool, c, eps: float, k: int, p: int, iters: int, dtype):
+    """Device-side MCCA fit (ccab_mcca_fit); same conventions as ``rcca_fit``; offsets = (mean, eigenvalues,
+    W_1 .. W_m, total)."""
+    lib = _lib.load()
+    _require_cuda(mom, "moments")
+    dt = _DT[dtype]
+    m = len(dims)
+    d = _lib.i64_array(dims)
+    offs = (C.c_int64 * (m + 3))()
+    _lib.check(lib.ccab_mcca_fit_result_layout(dt, m, d, int(k), int(p), offs), "ccab_mcca_fit_result_layout")
+    offsets = [int(x) for x in offs]
+    block = torch.empty(offsets[-1] + 256, dtype=torch.uint8, device=mom.device)
+    shift = (-block.data_ptr()) % 256
+    block = block[shift:shift + offsets[-1]]
+    ws = _ws(lib.ccab_mcca_fit_workspace_bytes(dt, m, d, int(k), int(p)), mom.device)
+    cc = (C.c_double * m)(*[float(x) for x in c])
+    with torch.cuda.device(mom.device):
+        rc = lib.ccab_mcca_fit(dt, m, d, _ptr(mom), _ptr(n_dev), float(n_host if n_host is not None else 0.0),
+                               1 if center else 0, cc, float(eps), int(k), int(p), int(iters), _ptr(block),
+                               block.numel(), _ptr(ws), ws.numel(), _stream(mom))
+    _lib.check(rc, "ccab_mcca_fit")
     return block, offsets
 
 

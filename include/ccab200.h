@@ -72,7 +72,8 @@ int ccab_covariance(int out_dtype, int n_views, const int64_t* dims, const doubl
  * evecs_t[b] (n x n, ldv): evecs_t[b][j,:] is the unit eigenvector of the j-th largest eigenvalue.
  * `shift` is added to the diagonal before solving and removed from the eigenvalues afterwards; pass a
  * value >= -lambda_min for indefinite matrices (the one-sided method needs A + shift*I to be PSD to
- * separate +/- pairs).  info[0] (host, may be NULL) = sweeps used, info_offdiag (host, may be NULL) =
+ * separate +/- pairs).  info[0] (host, may be NULL) = sweeps used, NEGATED when the iteration ran out of sweeps before
+ * reaching the tolerance (with info == NULL such a call fails instead), info_offdiag (host, may be NULL) =
  * last normalised off-diagonal.
  * Replaces: scipy.linalg.eigh cca_zoo/_utils/_linalg.py:64-71, np.linalg.eigvalsh
  * cca_zoo/linear/_mcca.py:170,194 cca_zoo/linear/_gcca.py:102, sklearn PCA cca_zoo/linear/_mcca.py:117,
@@ -194,6 +195,21 @@ int ccab_rcca_fit_result_layout(int dtype, const int64_t* dims, int k, int p, in
 int ccab_rcca_fit(int dtype, const int64_t* dims, const double* moments, const double* n_total_dev, double n_total,
                   int center, const double* c, int k, int p, int iters, void* result, size_t result_bytes,
                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the fit behind the ABI: MCCA -------------------------------------------------------------------------------------
+ * Same contract as ccab_rcca_fit for m >= 2 views: B_i = (1-c_i) C_ii + c_i I = L_i L_i^T (batched Cholesky + inverse
+ * when the views share one width), K_ij = L_i^-1 C_ij L_j^-T, the k largest eigenpairs of K by blocked subspace
+ * iteration on K + I / (1 - max c) with a Rayleigh-Ritz step, v_i = sqrt(m) L_i^-T y_i (v^T (B/m) v = 1 as scipy).
+ * Result block: double header[32] | double mean[D] | T eigenvalues[k] | T W_1[d_1 x k] | .. | T W_m; offsets has m + 3
+ * entries (mean, eigenvalues, W_1 .. W_m, total).  `eps` is the reference's floor on lambda_min(B): a block whose pivots
+ * fall below it fails the factorisation (status bit 1) and the caller takes the eigen route, which applies the floor.
+ * Needs max c <= 0.9 and k <= p <= 128.
+ * Replaces cca_zoo/linear/_mcca.py:113-173 (_build_A, _build_B, gevp of cca_zoo/_utils/_linalg.py:44-73). */
+size_t ccab_mcca_fit_workspace_bytes(int dtype, int n_views, const int64_t* dims, int k, int p);
+int ccab_mcca_fit_result_layout(int dtype, int n_views, const int64_t* dims, int k, int p, int64_t* offsets);
+int ccab_mcca_fit(int dtype, int n_views, const int64_t* dims, const double* moments, const double* n_total_dev,
+                  double n_total, int center, const double* c, double eps, int k, int p, int iters, void* result,
+                  size_t result_bytes, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- the deep-CCA objective behind the ABI (any widths) ---------------------------------------------------------
  * ccab_ccaloss_fwd: loss[0] = -|| S11^-1/2 S12 S22^-1/2 ||_F^2 with S_ii = cov(z_i) + eps I, from the moment pass over

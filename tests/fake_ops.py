@@ -284,6 +284,56 @@ def rcca_fit(mom, dims, n_host, n_dev, center, c, k, p, iters, dtype):
     return block, offsets
 
 
+def mcca_fit(mom, dims, n_host, n_dev, center, c, eps, k, p, iters, dtype):
+    item = 4 if dtype == torch.float32 else 8
+    m, D = len(dims), int(sum(dims))
+    offsets = [8 * FIT_HEADER_DOUBLES]
+    offsets.append(offsets[-1] + _al256(8 * D))
+    offsets.append(offsets[-1] + _al256(item * k))
+    for d in dims:
+        offsets.append(offsets[-1] + _al256(item * d * k))
+    block = torch.zeros(offsets[-1], dtype=torch.uint8)
+    buf = block.numpy()
+    hdr = buf[:8 * FIT_HEADER_DOUBLES].view(np.float64)
+    n = float(n_host) if n_host is not None else float(n_dev[0])
+    status = 0
+    if not bool(torch.isfinite(mom).all()):
+        status |= FIT_NON_FINITE
+    if not n > max(dims):
+        status |= FIT_TOO_FEW_SAMPLES
+    hdr[1] = n
+    if status == 0:
+        C, mean = covariance(mom, dims, n, center, torch.float64)
+        off = np.concatenate([[0], np.cumsum(dims)]).astype(int)
+        Linv = []
+        for i in range(m):
+            sl = slice(off[i], off[i + 1])
+            R = (1.0 - c[i]) * C[sl, sl] + c[i] * torch.eye(dims[i], dtype=torch.float64)
+            L, info = torch.linalg.cholesky_ex(R)
+            tol = max(eps, dims[i] * float(torch.finfo(dtype).eps) * ((1.0 - c[i]) * float(C[sl, sl].diagonal().max()) + c[i]))
+            if int(info) != 0 or bool((L.diagonal() ** 2 <= tol).any()):
+                status |= FIT_NOT_POSITIVE_DEFINITE
+                break
+            Linv.append(torch.linalg.inv(L))
+        if status == 0:
+            K = torch.zeros((D, D), dtype=torch.float64)
+            for i in range(m):
+                for j in range(m):
+                    if i != j:
+                        K[off[i]:off[i + 1], off[j]:off[j + 1]] = Linv[i] @ C[off[i]:off[i + 1], off[j]:off[j + 1]] @ Linv[j].T
+            w, V = torch.linalg.eigh(K)
+            w, V = w.flip(0)[:k], V.flip(1)[:, :k]
+            np_dt = np.float32 if dtype == torch.float32 else np.float64
+            buf[offsets[0]:offsets[0] + 8 * D].view(np.float64)[:] = mean.numpy()
+            buf[offsets[1]:offsets[1] + item * k].view(np_dt)[:] = w.numpy()
+            for i in range(m):
+                wi = (m ** 0.5) * Linv[i].T @ V[off[i]:off[i + 1]]
+                buf[offsets[2 + i]:offsets[2 + i] + item * dims[i] * k].view(np_dt)[:] = wi.numpy().reshape(-1)
+            hdr[3] = float(w[0])
+    hdr[0] = status
+    return block, offsets
+
+
 def decode_fit_block(host, offsets, dims, k, dtype):
     from cca_zoo_b200.ops import decode_fit_block as real
 
@@ -301,12 +351,12 @@ def install(monkeypatch):
 
     import cca_zoo_b200
     from cca_zoo_b200 import _base, _solvers
-    from cca_zoo_b200.linear import _grcca, _partialcca, _rcca
+    from cca_zoo_b200.linear import _grcca, _mcca, _partialcca, _rcca
 
     from cca_zoo_b200.deep import objectives
 
     me = sys.modules[__name__]
-    for mod in (_base, _solvers, _partialcca, _grcca, _rcca, objectives):
+    for mod in (_base, _solvers, _partialcca, _grcca, _rcca, _mcca, objectives):
         monkeypatch.setattr(mod, "ops", me)
     monkeypatch.setattr(objectives, "_require_cuda", lambda name, *tensors: None)
     monkeypatch.setattr(cca_zoo_b200, "ops", me, raising=False)
