@@ -169,6 +169,13 @@ template <typename T>
 double eps_of() {
   return std::is_same<T, float>::value ? 1.1920928955078125e-7 : 2.220446049250313e-16;
 }
+// residual tolerance of the subspace iteration relative to sigma_1 sqrt(k): 200 eps in float, and no tighter than 1e-10
+// in double -- the vectors are then accurate to 1e-10 / gap, far inside the 1e-5 parity bar, while 200 eps (4e-14) would
+// cost twice the iterations for nothing
+template <typename T>
+double resid_tol_of() {
+  return std::max(200.0 * eps_of<T>(), 1e-10);
+}
 
 // ---------------------------------------------------------------------------------------------
 // CholQR: Zout (rows x p) = Zin * chol(Zin^T Zin)^-T ; info slot must be zero on entry
@@ -432,7 +439,7 @@ int rcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
     rc = xgemm<T>(b, s);
     if (rc) return rc;
   }
-  fit_status_kernel<<<1, 32, 0, s>>>(hdr, flags, infos, n_infos, rr_info, stats, n_dev, n_host, 200.0 * eps_of<T>(), k,
+  fit_status_kernel<<<1, 32, 0, s>>>(hdr, flags, infos, n_infos, rr_info, stats, n_dev, n_host, resid_tol_of<T>(), k,
                                     std::max(d1, d2));
   count_launches(1);
   CCAB_CUDA(cudaGetLastError());
@@ -701,7 +708,7 @@ int mcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
     rc = xgemm<T>(a, s);
     if (rc) return rc;
   }
-  fit_status_kernel<<<1, 32, 0, s>>>(hdr, flags, infos, n_infos, rr_info, stats, n_dev, n_host, 200.0 * eps_of<T>(), k,
+  fit_status_kernel<<<1, 32, 0, s>>>(hdr, flags, infos, n_infos, rr_info, stats, n_dev, n_host, resid_tol_of<T>(), k,
                                     P.dmax);
   count_launches(1);
   CCAB_CUDA(cudaGetLastError());

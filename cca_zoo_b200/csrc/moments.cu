@@ -927,6 +927,11 @@ size_t moments_workspace_bytes(int dtype, int precision, const ColumnLayout& L, 
 int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t* lds, int64_t n_rows, bool x3,
                  double* moments_out, void* ws, size_t ws_bytes, cudaStream_t stream) {
   CCAB_CHECK_ARG(n_rows >= 1 && n_rows < (int64_t)1 << 31, "n_rows out of range");
+  {
+    int dev = 0;   // bind the primary context to this thread before the driver-API tensor-map encoder (see tgemm.cu)
+    CCAB_CUDA(cudaGetDevice(&dev));
+    CCAB_CUDA(cudaSetDevice(dev));
+  }
   TcPlan P = plan_tc(L, n_rows, x3);
   const size_t need = align256(P.partial_bytes) + align256(P.sum_bytes) + align256(P.split_bytes) + 256;
   CCAB_CHECK_ARG(ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);

@@ -171,6 +171,7 @@ struct JacobiCtx {
   T* Qm;         // [batch][npairs][kS*kS]        row-major Q
   int* skip;     // [batch][npairs]
   unsigned* stat;  // [batch] max off-diagonal ratio of the sweep (float bits)
+  float* null2;    // [batch] squared column norm below which a column is numerical noise: (n eps)^2 ||G||_F^2
   int m, n_pad, nb, npairs, R;
   int64_t ldg;
   int rows_per_part;
@@ -265,13 +266,17 @@ __global__ void __launch_bounds__(256) jacobi_solve_kernel(const JacobiCtx<T> c,
   }
   __syncthreads();
   // convergence statistic: max_{i<j} |w_ij| / sqrt(w_ii w_jj)
+  const float null2_b = c.null2[b];
   float myr = 0.f;
   for (int e = threadIdx.x; e < kS * kS; e += blockDim.x) {
     const int i = e / kS, j = e % kS;
     if (i < j) {
-      const T d = Wa[i * kSP + i] * Wa[j * kSP + j];
+      // columns at the rounding-noise level of the matrix (rank-deficient input) have no direction: the cosine
+      // between them and anything else is noise and must not keep the iteration "unconverged" forever
+      const T wi = Wa[i * kSP + i], wj = Wa[j * kSP + j];
+      const T d = wi * wj;
       const T w = fabs(Wa[i * kSP + j]);
-      if (d > T(0) && w > T(0)) myr = fmaxf(myr, (float)(w / sqrt(d)));
+      if (d > T(0) && w > T(0) && (float)wi > null2_b && (float)wj > null2_b) myr = fmaxf(myr, (float)(w / sqrt(d)));
     }
   }
   for (int o = 16; o > 0; o >>= 1) myr = fmaxf(myr, __shfl_xor_sync(0xffffffffu, myr, o));
@@ -440,13 +445,17 @@ __global__ void __launch_bounds__(256) jacobi_round_fused_kernel(const JacobiCtx
   }
   cluster.sync();  // all remote reads done: CTAs are independent from here on
   // ---- convergence statistic of this panel ----
+  const float null2_b = c.null2[b];
   float myr = 0.f;
   for (int e = threadIdx.x; e < kS * kS; e += blockDim.x) {
     const int i = e / kS, j = e % kS;
     if (i < j) {
-      const T d = Wa[i * kSP + i] * Wa[j * kSP + j];
+      // columns at the rounding-noise level of the matrix (rank-deficient input) have no direction: the cosine
+      // between them and anything else is noise and must not keep the iteration "unconverged" forever
+      const T wi = Wa[i * kSP + i], wj = Wa[j * kSP + j];
+      const T d = wi * wj;
       const T w = fabs(Wa[i * kSP + j]);
-      if (d > T(0) && w > T(0)) myr = fmaxf(myr, (float)(w / sqrt(d)));
+      if (d > T(0) && w > T(0) && (float)wi > null2_b && (float)wj > null2_b) myr = fmaxf(myr, (float)(w / sqrt(d)));
     }
   }
   for (int o = 16; o > 0; o >>= 1) myr = fmaxf(myr, __shfl_xor_sync(0xffffffffu, myr, o));
@@ -535,6 +544,29 @@ __global__ void jacobi_init_kernel(const T* __restrict__ in, int64_t ld_in, int6
     if (row < c.n_pad) V[(size_t)col * c.n_pad + row] = (row == col) ? T(1) : T(0);
   }
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) c.stat[b] = 0u;
+}
+
+// null2[b] = (10 n eps)^2 ||G_b||_F^2 (one block per matrix, fixed-order reduction: deterministic)
+template <typename T>
+__global__ void jacobi_scale_kernel(const JacobiCtx<T> c, int n, float* __restrict__ null2) {
+  __shared__ double red[32];
+  const int b = blockIdx.x;
+  const T* G = c.G + (size_t)b * c.n_pad * c.ldg;
+  double acc = 0.0;
+  const size_t total = (size_t)n * c.m;
+  for (size_t e = threadIdx.x; e < total; e += blockDim.x) {
+    const double v = (double)G[(e / c.m) * c.ldg + (e % c.m)];
+    acc += v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    const double ne = (double)n * (double)Eps<T>::v;
+    null2[b] = (float)fmin(100.0 * ne * ne * t, 3.0e38);   // norm threshold 10 n eps ||G||_F
+  }
 }
 
 __global__ void jacobi_reset_stat_kernel(unsigned* stat, int batch) {
@@ -658,7 +690,7 @@ template <typename T>
 struct Plan {
   int n_pad, nb, npairs, R, rows_per_part;
   int64_t ldg;
-  size_t oG, oV, oW, oQ, oSkip, oStat, oVals, oNorm, oRank, total;
+  size_t oG, oV, oW, oQ, oSkip, oStat, oNull, oVals, oNorm, oRank, total;
 };
 
 template <typename T>
@@ -680,6 +712,7 @@ Plan<T> make_plan(int m, int n, int batch) {
   P.oQ = o; o += al((size_t)batch * P.npairs * kS * kS * sizeof(T));
   P.oSkip = o; o += al((size_t)batch * P.npairs * sizeof(int));
   P.oStat = o; o += al((size_t)batch * sizeof(unsigned));
+  P.oNull = o; o += al((size_t)batch * sizeof(float));
   P.oVals = o; o += al((size_t)batch * P.n_pad * sizeof(T));
   P.oNorm = o; o += al((size_t)batch * P.n_pad * sizeof(T));
   P.oRank = o; o += al((size_t)batch * P.n_pad * sizeof(int));
@@ -709,6 +742,7 @@ int jacobi_solve(const JacobiArgs<T>& a, void* ws, size_t ws_bytes, cudaStream_t
   c.Qm = reinterpret_cast<T*>(w + P.oQ);
   c.skip = reinterpret_cast<int*>(w + P.oSkip);
   c.stat = reinterpret_cast<unsigned*>(w + P.oStat);
+  c.null2 = reinterpret_cast<float*>(w + P.oNull);
   T* vals = reinterpret_cast<T*>(w + P.oVals);
   T* vnorm = reinterpret_cast<T*>(w + P.oNorm);
   int* rank = reinterpret_cast<int*>(w + P.oRank);
@@ -725,6 +759,7 @@ int jacobi_solve(const JacobiArgs<T>& a, void* ws, size_t ws_bytes, cudaStream_t
     const int rows = std::max(m, P.n_pad);
     dim3 grid((unsigned)std::min<int64_t>(ceil_div(rows, 256), 64), P.n_pad, batch);
     jacobi_init_kernel<T><<<grid, 256, 0, stream>>>(a.in, a.ld_in, a.batch_stride_in, a.colmajor_in, m, n, c, shift); count_launches(1);
+    jacobi_scale_kernel<T><<<batch, 1024, 0, stream>>>(c, n, c.null2); count_launches(1);
     CCAB_CUDA(cudaGetLastError());
   }
   const T tol = a.tol > 0 ? (T)a.tol : (T)(4.0 * (double)Eps<T>::v * std::sqrt((double)m));

@@ -325,6 +325,14 @@ bool tgemm_supported(const TgemmArgs& a) {
 }
 
 int tgemm(const TgemmArgs& a, cudaStream_t stream) {
+  {
+    // cuTensorMapEncodeTiled is a driver entry point and needs a current context on the CALLING thread; a thread that
+    // has only inherited the device ordinal (torch's autograd worker) has none until a runtime call binds the primary
+    // context -- cudaSetDevice does (CUDA 12)
+    int dev = 0;
+    CCAB_CUDA(cudaGetDevice(&dev));
+    CCAB_CUDA(cudaSetDevice(dev));
+  }
   CCAB_CHECK_ARG(tgemm_supported(a), "tgemm: operands must be 16-byte aligned with leading dimensions % 4 == 0");
   CCAB_CHECK_ARG(a.C || a.Ct, "tgemm: no output");
   CCAB_CHECK_ARG(a.C || a.beta == 0.f, "tgemm: beta != 0 needs C");

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 def _views(n, dims, k=6, seed=0, dtype=np.float32):
     rng = np.random.default_rng(seed)
-    z = rng.standard_normal((n, k))
+    z = rng.standard_normal((n, k)) * np.linspace(1.0, 0.45, k)      # distinct signal strengths: separated correlations
     return [(z @ rng.standard_normal((k, d)) * 0.5 + rng.standard_normal((n, d)) + 0.3).astype(dtype) for d in dims]
 
 
@@ -83,7 +83,7 @@ def test_fit_config1_through_ctypes_only():
     block = block[(-block.data_ptr()) % 256:][:offs[4]]
     fws = torch.empty(lib.ccab_rcca_fit_workspace_bytes(_lib.F64, d, k, p) + 256, dtype=torch.uint8, device="cuda")
     cc = (C.c_double * 2)(0.0, 0.0)
-    rc = lib.ccab_rcca_fit(_lib.F64, d, mom.data_ptr(), None, float(n), 1, cc, k, p, 8, block.data_ptr(), block.numel(),
+    rc = lib.ccab_rcca_fit(_lib.F64, d, mom.data_ptr(), None, float(n), 1, cc, k, p, 16, block.data_ptr(), block.numel(),
                            fws.data_ptr(), fws.numel(), stream)
     assert rc == 0, _lib.last_error()
     host = block.cpu().numpy()
@@ -93,3 +93,59 @@ def test_fit_config1_through_ctypes_only():
     mean = host[offs[0]:offs[0] + 8 * sum(dims)].view(np.float64)
     assert R.max_rel_err_per_vector(w, ws_ref) < 1e-6
     np.testing.assert_allclose(mean[:dims[0]], mus_ref[0], rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-3), (np.float64, 1e-5)])
+@pytest.mark.parametrize("dims,k,c", [([256, 256, 256], 4, 0.1), ([320, 260, 200, 128], 5, [0.0, 0.05, 0.1, 0.2])])
+def test_mcca_device_fit_matches_the_oracle(dtype, tol, dims, k, c):
+    from cca_zoo_b200.linear import MCCA
+
+    views = _views(7000, dims, seed=11 + len(dims), dtype=dtype)
+    est = MCCA(latent_dimensions=k, c=c).fit(views)
+    assert est._fit_info["route"] == "device", est._fit_info
+    w_ref, mu_ref = R.ref_mcca_fit([v.astype(np.float64) for v in views], k, c)
+    assert R.max_rel_err_per_vector([w.astype(np.float64) for w in est.weights_], w_ref) < tol
+    assert est.weights_[0].dtype == np.float64          # np.cov upcasts in the reference: float64 weights
+    np.testing.assert_allclose(est.score(views), R.score(views, mu_ref, w_ref), rtol=10 * tol)
+    eig = MCCA(latent_dimensions=k, c=c, solver="eigen").fit(views)
+    assert R.max_rel_err_per_vector(eig.weights_, w_ref) < tol
+
+
+def test_loss_lazy_status_and_sync_mode_agree():
+    from cca_zoo_b200.deep import CCALoss, MCCALoss
+
+    g = torch.Generator().manual_seed(11)
+    lat = torch.randn(2048, 8, generator=g)
+    zs = [(lat @ torch.randn(8, w, generator=g) + torch.randn(2048, w, generator=g)).cuda() for w in (96, 72, 40)]
+    out = {}
+    for mode in ("lazy", "sync"):
+        z = [t.clone().requires_grad_(True) for t in zs[:2]]
+        fn = CCALoss(verify=mode)
+        loss = fn(z)
+        loss.backward()
+        fn.check()
+        out[mode] = (loss.item(), z[0].grad.clone())
+    assert out["lazy"][0] == out["sync"][0] and torch.equal(out["lazy"][1], out["sync"][1])
+    res = {}
+    for mode in ("lazy", "sync"):                      # one moment pass + shared factorisations vs the pairwise loop
+        z = [t.clone().requires_grad_(True) for t in zs]
+        fn = MCCALoss(verify=mode)
+        loss = fn(z)
+        loss.backward()
+        fn.check()
+        res[mode] = (loss.item(), [t.grad.clone() for t in z])
+    assert abs(res["lazy"][0] - res["sync"][0]) < 1e-4 * abs(res["sync"][0])
+    for a, b in zip(res["lazy"][1], res["sync"][1]):
+        assert float((a - b).abs().max() / b.abs().max()) < 1e-3
+
+
+def test_loss_lazy_status_reports_a_broken_batch_at_the_next_call():
+    from cca_zoo_b200.deep import CCALoss
+
+    z1 = torch.randn(512, 16, device="cuda")
+    z2 = torch.randn(512, 16, device="cuda")
+    z2[5, 3] = float("inf")
+    fn = CCALoss()
+    fn([z1, z2])                                       # asynchronous: nothing is read back here
+    with pytest.raises(ValueError, match="NaN or infinity"):
+        fn.check()
