@@ -164,7 +164,7 @@ class BaseModel(BaseEstimator, ABC):
         if reduced:
             n_total = int(n_local)
         else:
-            mom, n_total = parallel.allreduce_moments(mom, n_local)
+            mom, n_total = parallel.allreduce_moments(mom, n_local, dims=dims)
         # NaN / inf anywhere in the inputs poisons the moments: one tiny device-side check replaces the
         # reference's host scan (check_array) for tensors that never visit the host
         if check_finite and not bool(torch.isfinite(mom).all()):
@@ -211,7 +211,7 @@ class BaseModel(BaseEstimator, ABC):
         if plan is None:
             C, dims, n_total = self._covariance_stage(mom, n_local, dims, in_dtype, True)
             return self._finish(self._solve(C, dims, n_total))
-        mom, n_host, n_dev = parallel.allreduce_moments_lazy(mom, n_local)
+        mom, n_host, n_dev = parallel.allreduce_moments_lazy(mom, n_local, dims=dims)
         solve_dtype = torch.float64 if (self._solve_in_float64 or in_dtype == torch.float64) else torch.float32
         attempts = plan.pop("iters")
         hdr = None
@@ -324,7 +324,7 @@ class BaseModel(BaseEstimator, ABC):
         if dims != list(self.n_features_in_):
             raise ValueError(f"views have {dims} features, the model was fitted on {self.n_features_in_}")
         mom = ops.moments(dev_views, precision=self.precision)
-        mom, n_total = parallel.allreduce_moments(mom, int(dev_views[0].shape[0]))
+        mom, n_total = parallel.allreduce_moments(mom, int(dev_views[0].shape[0]), dims=dims)
         C, _ = ops.covariance(mom, dims, n_total, center=True, dtype=torch.float64)
         off = np.concatenate([[0], np.cumsum(dims)]).astype(int)
         sl = [slice(int(off[i]), int(off[i + 1])) for i in range(len(dims))]

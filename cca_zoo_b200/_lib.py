@@ -29,6 +29,9 @@ SIGNATURES = {
     "ccab_moments_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, _i64p, C.c_int64]),
     "ccab_moments": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_vp), _i64p, _i64p, C.c_int64, _vp, _vp,
                                C.c_size_t, _vp]),
+    "ccab_moments_packed_size": (C.c_int64, [C.c_int, _i64p]),
+    "ccab_moments_pack": (C.c_int, [C.c_int, _i64p, _vp, C.c_double, _vp, _vp]),
+    "ccab_moments_unpack": (C.c_int, [C.c_int, _i64p, _vp, _vp, _vp]),
     "ccab_covariance": (C.c_int, [C.c_int, C.c_int, _i64p, _vp, C.c_double, C.c_int, _vp, C.c_int64, _vp, _vp]),
     "ccab_syevj_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "ccab_syevj": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, C.c_int64, C.c_double, _vp, _vp, C.c_int64,

@@ -112,6 +112,37 @@ int ccab_moments(int dtype, int precision, int n_views, const void* const* views
   CCAB_CATCH
 }
 
+int64_t ccab_moments_packed_size(int n_views, const int64_t* dims) {
+  ColumnLayout L;
+  if (make_layout(n_views, dims, &L)) return -1;
+  return moments_packed_size(L);
+}
+
+int ccab_moments_pack(int n_views, const int64_t* dims, const double* moments, double n_local, double* packed,
+                      void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dims && moments && packed, "null pointer argument");
+  ColumnLayout L;
+  int rc = make_layout(n_views, dims, &L);
+  if (rc) return rc;
+  rc = require_device();
+  if (rc) return rc;
+  return moments_pack(L, moments, n_local, packed, static_cast<cudaStream_t>(stream));
+  CCAB_CATCH
+}
+
+int ccab_moments_unpack(int n_views, const int64_t* dims, const double* packed, double* moments, void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dims && moments && packed, "null pointer argument");
+  ColumnLayout L;
+  int rc = make_layout(n_views, dims, &L);
+  if (rc) return rc;
+  rc = require_device();
+  if (rc) return rc;
+  return moments_unpack(L, packed, moments, static_cast<cudaStream_t>(stream));
+  CCAB_CATCH
+}
+
 int ccab_covariance(int out_dtype, int n_views, const int64_t* dims, const double* moments, double n_total,
                     int center, void* C, int64_t ldc, void* mean, void* stream) {
   CCAB_TRY
@@ -267,8 +298,11 @@ int ccab_gemm(int dtype, int transa, int transb, int m, int n, int k, double alp
     g.C = static_cast<float*>(C); g.ldc = ldc;
     return xgemm<float>(g, s);
   }
-  return gemm<double>(transa, transb, m, n, k, alpha, static_cast<const double*>(A), lda,
-                      static_cast<const double*>(B), ldb, beta, static_cast<double*>(C), ldc, s);
+  GemmArgs<double> g;   // fp64 tensor pipe (mma.sync m8n8k4.f64)
+  g.transa = transa; g.transb = transb; g.m = m; g.n = n; g.k = k; g.alpha = alpha; g.beta = beta;
+  g.A = static_cast<const double*>(A); g.lda = lda; g.B = static_cast<const double*>(B); g.ldb = ldb;
+  g.C = static_cast<double*>(C); g.ldc = ldc;
+  return xgemm<double>(g, s);
   CCAB_CATCH
 }
 

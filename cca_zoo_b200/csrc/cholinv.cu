@@ -401,7 +401,7 @@ int potrf_panel_gemm(const GemmArgs<T>& g, T* scratch, int64_t strideScratch, cu
     a.force_bn = 128;   // ONE column tile per row block: the in-place condition
     if (tgemm_supported(a)) return tgemm(a, stream);
   }
-  if (g.n <= 64) return gemm_fma<T>(g, stream);   // the FMA kernel's 64-column tile covers the panel: same argument
+  if (g.n <= 64) return xgemm<T>(g, stream);      // one 64-column tile covers the panel in every kernel: same argument
   GemmArgs<T> t = g;
   t.C = scratch; t.ldc = g.n; t.strideC = strideScratch;
   int rc = gemm_fma<T>(t, stream);

@@ -1,5 +1,7 @@
 #include "dense.cuh"
 
+#include <algorithm>
+
 #include "tgemm.cuh"
 
 namespace ccab {
@@ -122,6 +124,213 @@ template int gemm<float>(int, int, int, int, int, float, const float*, int64_t, 
 template int gemm<double>(int, int, int, int, int, double, const double*, int64_t, const double*, int64_t, double,
                           double*, int64_t, cudaStream_t);
 
+// ---------------------------------------------------------------------------------------------------------------
+// float64 GEMM on the fp64 tensor pipe: mma.sync.aligned.m8n8k4.f64 (DMMA; tcgen05 has no f64 kind).  64 x 64 output
+// tile, 8 warps x (4 x 2) m8n8 fragments, 16-deep k chunks staged through skewed shared tiles ([k][64 + 8] doubles:
+// conflict-free 64-bit fragment loads) and double-buffered through registers (the global loads of chunk c + 1 are in
+// flight while chunk c is multiplied).  Same GemmArgs contract as the FMA kernel; it carries the float64 solver stage
+// (MCCA / GCCA whitening, K assembly, subspace iteration) that np.cov's upcast imposes
+// (cca_zoo/linear/_mcca.py:150-152).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int TA, int TB>
+__global__ void __launch_bounds__(256) dgemm_mma_kernel(const GemmArgs<double> g, int nsplit, int kchunk,
+                                                        double* __restrict__ partial) {
+  constexpr int KC = 16, LDS = 64 + 8;
+  __shared__ double As[2][KC][LDS];
+  __shared__ double Bs[2][KC][LDS];
+  const int m = g.m, n = g.n;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  if (g.lower_only && n0 >= m0 + 64) return;
+  const int split = (int)blockIdx.z % nsplit, bz = (int)blockIdx.z / nsplit;
+  const int kbeg = split * kchunk;
+  const int k = min(g.k, kbeg + kchunk);        // this CTA reduces over [kbeg, k)
+  const int b1 = bz % g.batch, b2 = bz / g.batch;
+  const double* __restrict__ A = g.A + (size_t)b1 * g.strideA + (size_t)b2 * g.strideA2;
+  const double* __restrict__ B = g.B + (size_t)b1 * g.strideB + (size_t)b2 * g.strideB2;
+  const int64_t lda = g.lda, ldb = g.ldb;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
+  const int gq = lane >> 2, tq = lane & 3;
+
+  double ra[4], rb[4];
+  auto load_regs = [&](int k0) {
+    if (TA) {  // stored k x m
+      const int mm = tid & 63, kk0 = tid >> 6;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kk = kk0 + 4 * i;
+        ra[i] = (k0 + kk < k && m0 + mm < m) ? A[(size_t)(k0 + kk) * lda + m0 + mm] : 0.0;
+      }
+    } else {   // stored m x k
+      const int kk = tid & 15, mm0 = tid >> 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int mm = mm0 + 16 * i;
+        ra[i] = (k0 + kk < k && m0 + mm < m) ? A[(size_t)(m0 + mm) * lda + k0 + kk] : 0.0;
+      }
+    }
+    if (TB) {  // stored n x k
+      const int kk = tid & 15, nn0 = tid >> 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int nn = nn0 + 16 * i;
+        rb[i] = (k0 + kk < k && n0 + nn < n) ? B[(size_t)(n0 + nn) * ldb + k0 + kk] : 0.0;
+      }
+    } else {   // stored k x n
+      const int nn = tid & 63, kk0 = tid >> 6;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kk = kk0 + 4 * i;
+        rb[i] = (k0 + kk < k && n0 + nn < n) ? B[(size_t)(k0 + kk) * ldb + n0 + nn] : 0.0;
+      }
+    }
+  };
+  auto store_regs = [&](int buf) {
+    if (TA) {
+      const int mm = tid & 63, kk0 = tid >> 6;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) As[buf][kk0 + 4 * i][mm] = ra[i];
+    } else {
+      const int kk = tid & 15, mm0 = tid >> 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) As[buf][kk][mm0 + 16 * i] = ra[i];
+    }
+    if (TB) {
+      const int kk = tid & 15, nn0 = tid >> 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Bs[buf][kk][nn0 + 16 * i] = rb[i];
+    } else {
+      const int nn = tid & 63, kk0 = tid >> 6;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Bs[buf][kk0 + 4 * i][nn] = rb[i];
+    }
+  };
+
+  double acc[4][2][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  load_regs(kbeg);
+  store_regs(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = kbeg; k0 < k; k0 += KC) {
+    const bool more = k0 + KC < k;
+    if (more) load_regs(k0 + KC);
+#pragma unroll
+    for (int kk = 0; kk < KC; kk += 4) {
+      double a[4], b[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[buf][kk + tq][wm + 8 * i + gq];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) b[j] = Bs[buf][kk + tq][wn + 8 * j + gq];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dmma_884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    if (more) {
+      store_regs(buf ^ 1);   // the other buffer was last read one iteration ago (barrier below separates them)
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+  if (nsplit > 1) {   // partial tile of this split: [bz][split][m][n], summed in fixed order by the reduce kernel
+    double* Pp = partial + ((size_t)bz * nsplit + split) * (size_t)m * n;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int r = m0 + wm + 8 * i + gq, c = n0 + wn + 8 * j + 2 * tq + e;
+          if (r < m && c < n) Pp[(size_t)r * n + c] = acc[i][j][e];
+        }
+    return;
+  }
+  double* C = g.C ? g.C + (size_t)b1 * g.strideC + (size_t)b2 * g.strideC2 : nullptr;
+  double* Ct = g.Ct ? g.Ct + (size_t)b1 * g.strideCt + (size_t)b2 * g.strideCt2 : nullptr;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int r = m0 + wm + 8 * i + gq, c = n0 + wn + 8 * j + 2 * tq + e;
+        if (r >= m || c >= n) continue;
+        double v = g.alpha * acc[i][j][e];
+        if (C) {
+          if (g.beta != 0.0) v += g.beta * C[(size_t)r * g.ldc + c];
+          C[(size_t)r * g.ldc + c] = v;
+        }
+        if (Ct) Ct[(size_t)c * g.ldct + r] = v;
+      }
+}
+
+// C (+ Ct) = alpha * sum_s partial[s] + beta * C, splits added in index order
+__global__ void splitk_reduce_kernel(const GemmArgs<double> g, int nsplit, const double* __restrict__ partial) {
+  const size_t mn = (size_t)g.m * g.n;
+  const int bz = blockIdx.y, b1 = bz % g.batch, b2 = bz / g.batch;
+  double* C = g.C ? g.C + (size_t)b1 * g.strideC + (size_t)b2 * g.strideC2 : nullptr;
+  double* Ct = g.Ct ? g.Ct + (size_t)b1 * g.strideCt + (size_t)b2 * g.strideCt2 : nullptr;
+  const double* Pp = partial + (size_t)bz * nsplit * mn;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < mn; e += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / g.n), c = (int)(e % g.n);
+    if (g.lower_only && (c / 64) > (r / 64)) continue;
+    double acc = 0.0;
+    for (int s = 0; s < nsplit; ++s) acc += Pp[(size_t)s * mn + e];
+    double v = g.alpha * acc;
+    if (C) {
+      if (g.beta != 0.0) v += g.beta * C[(size_t)r * g.ldc + c];
+      C[(size_t)r * g.ldc + c] = v;
+    }
+    if (Ct) Ct[(size_t)c * g.ldct + r] = v;
+  }
+}
+
+int gemm_dmma(const GemmArgs<double>& g, cudaStream_t stream) {
+  CCAB_CHECK_ARG(g.m >= 0 && g.n >= 0 && g.k >= 0 && g.batch >= 1 && g.batch2 >= 1, "bad gemm shape");
+  CCAB_CHECK_ARG(g.C || g.Ct, "gemm: no output");
+  CCAB_CHECK_ARG(g.C || g.beta == 0.0, "gemm: beta != 0 needs C");
+  if (g.m == 0 || g.n == 0) return 0;
+  const int64_t tiles = ceil_div(g.n, 64) * ceil_div(g.m, 64) * g.batch * g.batch2;
+  // thin products (few output tiles, long reduction) leave most SMs idle: split the reduction when scratch is given
+  int nsplit = 1;
+  if (g.splitk_ws && tiles < 74 && g.k >= 512) {
+    nsplit = (int)std::min<int64_t>(std::min<int64_t>(8, 148 / tiles), g.k / 256);
+    const size_t need = (size_t)g.batch * g.batch2 * nsplit * (size_t)g.m * g.n * sizeof(double);
+    if (nsplit < 2 || need > g.splitk_ws_bytes) nsplit = 1;
+  }
+  int kchunk = g.k;
+  if (nsplit > 1) {
+    kchunk = (int)(ceil_div(ceil_div(g.k, nsplit), 16) * 16);
+    nsplit = (int)ceil_div(g.k, kchunk);
+  }
+  double* partial = static_cast<double*>(g.splitk_ws);
+  dim3 grid((unsigned)ceil_div(g.n, 64), (unsigned)ceil_div(g.m, 64), (unsigned)(g.batch * g.batch2 * nsplit));
+  if (!g.transa && !g.transb) dgemm_mma_kernel<0, 0><<<grid, 256, 0, stream>>>(g, nsplit, kchunk, partial);
+  else if (g.transa && !g.transb) dgemm_mma_kernel<1, 0><<<grid, 256, 0, stream>>>(g, nsplit, kchunk, partial);
+  else if (!g.transa && g.transb) dgemm_mma_kernel<0, 1><<<grid, 256, 0, stream>>>(g, nsplit, kchunk, partial);
+  else dgemm_mma_kernel<1, 1><<<grid, 256, 0, stream>>>(g, nsplit, kchunk, partial);
+  count_launches(1);
+  if (nsplit > 1) {
+    const size_t mn = (size_t)g.m * g.n;
+    dim3 rgrid((unsigned)std::min<size_t>((mn + 255) / 256, 592), (unsigned)(g.batch * g.batch2));
+    splitk_reduce_kernel<<<rgrid, 256, 0, stream>>>(g, nsplit, partial);
+    count_launches(1);
+  }
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // tensor pipe when the operands are float32 and TMA-addressable and the product is big enough to amortise the
 // pipeline fill; exact FMA tiles otherwise
 template <>
@@ -133,12 +342,13 @@ int xgemm<float>(const GemmArgs<float>& g, cudaStream_t stream) {
   a.C = g.C; a.ldc = g.ldc; a.strideC = g.strideC; a.strideC2 = g.strideC2;
   a.Ct = g.Ct; a.ldct = g.ldct; a.strideCt = g.strideCt; a.strideCt2 = g.strideCt2;
   a.batch = g.batch; a.batch2 = g.batch2; a.lower_only = g.lower_only;
-  const bool big = (int64_t)g.m * g.n >= 64 * 32 && g.k >= 16;
+  const bool big = (int64_t)g.m * g.n * g.k >= ((int64_t)1 << 21) && g.k >= 16;   // >= 128^3: the pipeline fill (~9 us) pays off
   if (big && !xgemm_force_fma() && tgemm_supported(a)) return tgemm(a, stream);
   return gemm_fma<float>(g, stream);
 }
 template <>
 int xgemm<double>(const GemmArgs<double>& g, cudaStream_t stream) {
+  if (!xgemm_force_fma() && g.k >= 8) return gemm_dmma(g, stream);   // fp64 tensor pipe (DMMA)
   return gemm_fma<double>(g, stream);
 }
 int& xgemm_force_fma() {

@@ -23,6 +23,8 @@ struct GemmArgs {
   int64_t ldct = 0, strideCt = 0, strideCt2 = 0;
   int batch = 1, batch2 = 1;
   int lower_only = 0;             // skip output tiles strictly above the diagonal
+  void* splitk_ws = nullptr;      // optional scratch: thin float64 products split their reduction over CTAs and
+  size_t splitk_ws_bytes = 0;     // add the partial tiles in a fixed order (deterministic); unused when too small
 };
 template <typename T>
 int gemm_fma(const GemmArgs<T>& g, cudaStream_t stream);   // exact FMA tiles on the CUDA cores

@@ -187,6 +187,8 @@ struct CholQrWs {
   void* pws;
   size_t pws_bytes;
   int64_t ldg;
+  void* splitk_ws = nullptr;   // scratch for the split reduction of the (single-tile, long-k) Gram product in float64
+  size_t splitk_ws_bytes = 0;
 };
 
 template <typename T>
@@ -195,6 +197,7 @@ int cholqr(const T* Zin, int64_t ldz, T* Zout, int64_t ldo, int rows, int p, con
   GemmArgs<T> g;
   g.transa = 1; g.m = p; g.n = p; g.k = rows;
   g.A = Zin; g.lda = ldz; g.B = Zin; g.ldb = ldz; g.C = w.G; g.ldc = w.ldg;
+  g.splitk_ws = w.splitk_ws; g.splitk_ws_bytes = w.splitk_ws_bytes;
   int rc = xgemm<T>(g, s);
   if (rc) return rc;
   const int NB = potrf_inv_block_size<T>();
@@ -464,8 +467,8 @@ struct MccaPlan {
   bool equal;
   int64_t ldC, ldR, strideR, ldp, ldk;
   int off[kMaxViews + 1];
-  size_t oC, oR, oLinv, oTmp, oK, oZ, oZ2, oY, oG, oGinv, oH, oLam, oVy, oZr, oE, oPws, oSmall, total;
-  size_t pws_bytes;
+  size_t oC, oR, oLinv, oTmp, oK, oZ, oZ2, oY, oG, oGinv, oH, oLam, oVy, oZr, oE, oPws, oSplit, oSmall, total;
+  size_t pws_bytes, split_bytes;
   size_t r_mean, r_val, r_w[kMaxViews], r_total;
 };
 
@@ -502,6 +505,8 @@ MccaPlan make_mcca_plan(const ColumnLayout& L, int k, int p) {
   P.oE = take((size_t)P.D * P.ldk);
   P.pws_bytes = std::max(potrf_inv_workspace_bytes<T>(P.dmax, P.m), potrf_inv_workspace_bytes<T>(p, 1));
   P.oPws = o; o += al256(P.pws_bytes);
+  P.split_bytes = 8 * (size_t)P.D * p * sizeof(T);
+  P.oSplit = o; o += al256(P.split_bytes);
   P.oSmall = o; o += 4096;
   P.total = o + 256;
   size_t r = sizeof(double) * kFitHeaderDoubles;
@@ -583,6 +588,8 @@ int mcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
   cq.pws = w + P.oPws;
   cq.pws_bytes = P.pws_bytes;
   cq.ldg = P.ldp;
+  cq.splitk_ws = w + P.oSplit;
+  cq.splitk_ws_bytes = P.split_bytes;
   uint8_t* sm = w + P.oSmall;
   int* flags = reinterpret_cast<int*>(sm);
   int* infos = flags + 4;                                      // [m + iters + 4]
@@ -649,7 +656,10 @@ int mcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
       if (rc) return rc;
     }
   // ---- subspace iteration on K + shift I ----
-  const double shift = 1.0 / (1.0 - cmax);
+  // K + I / (1 - max c) is positive semi-definite, so lambda_min(K) >= -1 / (1 - max c): half of that bound as the shift
+  // keeps every wanted (positive) eigenvalue ahead of the negative end in magnitude and damps the unwanted middle of
+  // the spectrum twice as fast as the full bound would
+  const double shift = 0.5 / (1.0 - cmax);
   {
     const size_t total = (size_t)D * p;
     randn_kernel<T><<<(unsigned)std::min<size_t>((total + 255) / 256, 592), 256, 0, s>>>(Z2, P.ldp, D, p, 0x4321ull);
@@ -664,8 +674,13 @@ int mcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
                                 cudaMemcpyDeviceToDevice, s));
     GemmArgs<T> a;   // Y = K Z + shift Z
     a.m = D; a.n = p; a.k = D; a.beta = (T)shift; a.A = K; a.lda = P.ldC; a.B = Z; a.ldb = P.ldp; a.C = Y; a.ldc = P.ldp;
+    a.splitk_ws = cq.splitk_ws; a.splitk_ws_bytes = cq.splitk_ws_bytes;
     rc = xgemm<T>(a, s);
     if (rc) return rc;
+    if (it % 2 == 0 && it != iters - 1) {   // orthonormalise every second product: cond grows by (|lam_1|+s)/(lam_p+s)
+      std::swap(Y, Z);                      // per step, far inside what one CholQR pass absorbs
+      continue;
+    }
     rc = cholqr<T>(Y, P.ldp, Z, P.ldp, D, p, cq, infos + slot++, s);
     if (rc) return rc;
     if (it == iters - 1) {
@@ -678,10 +693,12 @@ int mcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
   {
     GemmArgs<T> a;
     a.m = D; a.n = p; a.k = D; a.A = K; a.lda = P.ldC; a.B = Z; a.ldb = P.ldp; a.C = Y; a.ldc = P.ldp;   // Y = K Z
+    a.splitk_ws = cq.splitk_ws; a.splitk_ws_bytes = cq.splitk_ws_bytes;
     rc = xgemm<T>(a, s);
     if (rc) return rc;
     GemmArgs<T> h;
     h.transa = 1; h.m = p; h.n = p; h.k = D; h.A = Z; h.lda = P.ldp; h.B = Y; h.ldb = P.ldp; h.C = H; h.ldc = P.ldp;
+    h.splitk_ws = cq.splitk_ws; h.splitk_ws_bytes = cq.splitk_ws_bytes;
     rc = xgemm<T>(h, s);
     if (rc) return rc;
     rc = syevj_small<T>(p, 1, H, P.ldp, 0, lam, p, Vy, P.ldp, 0, rr_info, s);

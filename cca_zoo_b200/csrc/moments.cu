@@ -1138,6 +1138,70 @@ template int moments_simt<float>(const ColumnLayout&, const void* const*, const 
 template int moments_simt<double>(const ColumnLayout&, const void* const*, const int64_t*, int64_t, double*, void*,
                                   size_t, cudaStream_t);
 
+// =============================================================================================
+// exchange-step packing: only the upper triangle of 128 x 128 blocks of the moment matrix carries
+// information; the all-reduced message is  [ upper blocks (row-major over bi <= bj) | column sums | n | reserved ].
+// For D = 2048 that is 17.9 MB of float64 instead of 33.6 MB.
+// =============================================================================================
+__global__ void pack_moments_kernel(const double* __restrict__ mom, int nblocks, int Dp, double n_local,
+                                    double* __restrict__ packed) {
+  // blockIdx.x walks the upper-triangle blocks, then one extra "block" for the column sums and the tail
+  const int nt = nblocks * (nblocks + 1) / 2;
+  const int t = blockIdx.x;
+  if (t < nt) {
+    int bi = 0, rem = t, rowlen = nblocks;
+    while (rem >= rowlen) { rem -= rowlen; ++bi; --rowlen; }
+    const int bj = bi + rem;
+    const double* src = mom + (size_t)bi * kBlk * Dp + (size_t)bj * kBlk;
+    double* dst = packed + (size_t)t * kBlk * kBlk;
+    for (int e = threadIdx.x; e < kBlk * kBlk; e += blockDim.x) dst[e] = src[(size_t)(e / kBlk) * Dp + (e % kBlk)];
+  } else {
+    double* dst = packed + (size_t)nt * kBlk * kBlk;
+    const double* s = mom + (size_t)Dp * Dp;
+    for (int e = threadIdx.x; e < Dp; e += blockDim.x) dst[e] = s[e];
+    if (threadIdx.x == 0) { dst[Dp] = n_local; dst[Dp + 1] = 0.0; }
+  }
+}
+
+__global__ void unpack_moments_kernel(const double* __restrict__ packed, int nblocks, int Dp, double* __restrict__ mom) {
+  const int nt = nblocks * (nblocks + 1) / 2;
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bi < nblocks) {
+    double* dst = mom + (size_t)bi * kBlk * Dp + (size_t)bj * kBlk;
+    if (bj >= bi) {
+      const int t = bi * nblocks - bi * (bi - 1) / 2 + (bj - bi);
+      const double* src = packed + (size_t)t * kBlk * kBlk;
+      for (int e = threadIdx.x; e < kBlk * kBlk; e += blockDim.x) dst[(size_t)(e / kBlk) * Dp + (e % kBlk)] = src[e];
+    } else {
+      for (int e = threadIdx.x; e < kBlk * kBlk; e += blockDim.x) dst[(size_t)(e / kBlk) * Dp + (e % kBlk)] = 0.0;
+    }
+  } else if (bj == 0) {
+    const double* src = packed + (size_t)nt * kBlk * kBlk;
+    double* s = mom + (size_t)Dp * Dp;
+    for (int e = threadIdx.x; e < Dp; e += blockDim.x) s[e] = src[e];
+  }
+}
+
+int64_t moments_packed_size(const ColumnLayout& L) {
+  const int64_t nt = (int64_t)L.nblocks * (L.nblocks + 1) / 2;
+  return nt * kBlk * kBlk + L.Dp + 2;
+}
+
+int moments_pack(const ColumnLayout& L, const double* mom, double n_local, double* packed, cudaStream_t stream) {
+  const int nt = L.nblocks * (L.nblocks + 1) / 2;
+  pack_moments_kernel<<<nt + 1, 256, 0, stream>>>(mom, L.nblocks, L.Dp, n_local, packed);
+  count_launches(1);
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int moments_unpack(const ColumnLayout& L, const double* packed, double* mom, cudaStream_t stream) {
+  unpack_moments_kernel<<<dim3(L.nblocks, L.nblocks + 1), 256, 0, stream>>>(packed, L.nblocks, L.Dp, mom);
+  count_launches(1);
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <typename Tout>
 int covariance_from_moments(const ColumnLayout& L, const double* moments, double n_total, int center, Tout* C,
                             int64_t ldc, Tout* mean, cudaStream_t stream) {

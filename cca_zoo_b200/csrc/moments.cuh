@@ -39,6 +39,11 @@ template <typename Tout>
 int covariance_from_moments(const ColumnLayout& L, const double* moments, double n_total, int center,
                             Tout* C, int64_t ldc, Tout* mean, cudaStream_t stream);
 
+// exchange-step message: upper triangle of 128 x 128 blocks | column sums | n | reserved (all float64)
+int64_t moments_packed_size(const ColumnLayout& L);
+int moments_pack(const ColumnLayout& L, const double* moments, double n_local, double* packed, cudaStream_t stream);
+int moments_unpack(const ColumnLayout& L, const double* packed, double* moments, cudaStream_t stream);
+
 // debug knobs for the tcgen05 kernel (descriptor strides / TMA data type), see tools/umma_probe.py
 struct TcDebug {
   int lbo_bytes;    // <0: default

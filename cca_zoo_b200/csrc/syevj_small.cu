@@ -147,6 +147,31 @@ syevj_small_kernel(const T* __restrict__ A, int64_t lda, int64_t strideA, int n,
       // all operands are loaded before anything is stored so that the loads overlap (the blocks partition H: no
       // hazard).  Rutishauser's update  x' = x - s (y + tau x),  y' = y + s (x - tau y)  keeps the error
       // proportional to the rotation.
+      if (sizeof(T) == 8) {
+        // float64: 64 registers per thread do not hold the preloaded operands; walk the blocks warp by warp instead
+        for (int i = warp; i < m2; i += kSmallThreads / 32) {
+          const Rot<T> ri = rot[i];
+          T* Hp = H + ri.p * LD;
+          T* Hq = H + ri.q * LD;
+          for (int j = lane; j < m2; j += 32) {
+            const Rot<T> rj = rot[j];
+            const T a = Hp[rj.p], b = Hp[rj.q], c_ = Hq[rj.p], d = Hq[rj.q];
+            const T a1 = a - ri.s * (c_ + ri.tau * a), c1 = c_ + ri.s * (a - ri.tau * c_);
+            const T b1 = b - ri.s * (d + ri.tau * b), d1 = d + ri.s * (b - ri.tau * d);
+            T a2 = a1 - rj.s * (b1 + rj.tau * a1), b2 = b1 + rj.s * (a1 - rj.tau * b1);
+            T c2 = c1 - rj.s * (d1 + rj.tau * c1), d2 = d1 + rj.s * (c1 - rj.tau * d1);
+            if (i == j && ri.s != T(0)) { b2 = T(0); c2 = T(0); }
+            Hp[rj.p] = a2; Hp[rj.q] = b2; Hq[rj.p] = c2; Hq[rj.q] = d2;
+          }
+        }
+        for (int e = tid; e < m2 * ncol; e += kSmallThreads) {
+          const int i = e / ncol, col = e - i * ncol;
+          const Rot<T> ri = rot[i];
+          const T vp = V[ri.p * LDV + col], vq = V[ri.q * LDV + col];
+          V[ri.p * LDV + col] = vp - ri.s * (vq + ri.tau * vp);
+          V[ri.q * LDV + col] = vq + ri.s * (vp - ri.tau * vq);
+        }
+      } else {
 #pragma unroll
       for (int u0 = 0; u0 < kHB; u0 += CH) {
         Rot<T> ri[CH], rj[CH];
@@ -195,6 +220,7 @@ syevj_small_kernel(const T* __restrict__ A, int64_t lda, int64_t strideA, int n,
             V[rv[u].p * LDV + vc[u]] = vp[u] - rv[u].s * (vq[u] + rv[u].tau * vp[u]);
             V[rv[u].q * LDV + vc[u]] = vq[u] + rv[u].s * (vp[u] - rv[u].tau * vq[u]);
           }
+      }
       }
       __syncthreads();
     }

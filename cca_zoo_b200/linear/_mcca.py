@@ -74,7 +74,7 @@ class MCCA(BaseModel):
             # np.cov centres regardless of `center` (cca_zoo/linear/_mcca.py:150,166)
             return ops.mcca_fit(mom, dims_, n_host, n_dev, True, c_, eps, k, p, iters, solve_dtype)
 
-        return {"call": call, "k": k, "iters": [16, 48]}
+        return {"call": call, "k": k, "iters": [32, 60]}
 
     def _solve(self, C, dims, n_total):
         c_ = perview_parameter("c", self.c, 0.0, self.n_views_)

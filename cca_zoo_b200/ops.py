@@ -93,6 +93,34 @@ def moments(views, precision: str = "tf32x3") -> torch.Tensor:
     return out
 
 
+def moments_pack(mom: torch.Tensor, dims, n_local) -> torch.Tensor:
+    """The exchange-step message (ccab_moments_pack): upper block triangle | column sums | n | reserved."""
+    lib = _lib.load()
+    _require_cuda(mom, "moments")
+    d = _lib.i64_array(dims)
+    size = lib.ccab_moments_packed_size(len(dims), d)
+    if size < 0:
+        raise ValueError(_lib.last_error())
+    packed = torch.empty(size, dtype=torch.float64, device=mom.device)
+    with torch.cuda.device(mom.device):
+        rc = lib.ccab_moments_pack(len(dims), d, _ptr(mom), float(n_local), _ptr(packed), _stream(mom))
+    _lib.check(rc, "ccab_moments_pack")
+    return packed
+
+
+def moments_unpack(packed: torch.Tensor, dims, out=None):
+    """(moments buffer, n_total as a 1-element device tensor) from an all-reduced message."""
+    lib = _lib.load()
+    _require_cuda(packed, "packed")
+    d = _lib.i64_array(dims)
+    size = lib.ccab_moments_size(len(dims), d)
+    mom = out if out is not None else torch.empty(size, dtype=torch.float64, device=packed.device)
+    with torch.cuda.device(packed.device):
+        rc = lib.ccab_moments_unpack(len(dims), d, _ptr(packed), _ptr(mom), _stream(packed))
+    _lib.check(rc, "ccab_moments_unpack")
+    return mom, packed[-2:-1]
+
+
 def covariance(mom: torch.Tensor, dims, n_total: float, center: bool = True, dtype=torch.float64):
     """(C [D,D], mean [D]) from an (all-reduced) moments buffer."""
     lib = _lib.load()

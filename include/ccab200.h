@@ -59,6 +59,17 @@ int ccab_moments(int dtype, int precision, int n_views, const void* const* views
                  const int64_t* lds, int64_t n_rows, double* moments, void* workspace, size_t workspace_bytes,
                  void* stream);
 
+/* ---- exchange step of a sample-sharded fit ---------------------------------------------------------
+ * ccab_moments_pack gathers what the all-reduce has to carry into ONE contiguous float64 message of
+ * ccab_moments_packed_size() entries: the upper triangle of 128 x 128 blocks of M (row-major over block pairs),
+ * the column sums, the local sample count n and one reserved slot.  Sum it over the ranks (NCCL all-reduce over
+ * NVLink), then ccab_moments_unpack restores the moment buffer of ccab_moments (zero below the block diagonal);
+ * packed[size - 2] is the total sample count, which ccab_rcca_fit / ccab_mcca_fit read on the device (n_total_dev). */
+int64_t ccab_moments_packed_size(int n_views, const int64_t* dims);
+int ccab_moments_pack(int n_views, const int64_t* dims, const double* moments, double n_local, double* packed,
+                      void* stream);
+int ccab_moments_unpack(int n_views, const int64_t* dims, const double* packed, double* moments, void* stream);
+
 /* ---- K2: covariance from (all-reduced) moments ---------------------------------------------------
  * C = (M - s s^T / n_total) / (n_total - 1) (center != 0) or M / (n_total - 1), compact D x D
  * (D = sum dims, hstack order), full symmetric, in out_dtype; mean = s / n_total (or 0).

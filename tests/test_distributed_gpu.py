@@ -40,6 +40,13 @@ def _worker(rank, world, port, out_dir):
         np.save(os.path.join(out_dir, f"rcca_mean0_rank{rank}.npy"), est.means_[0])
         m = MCCA(latent_dimensions=5, c=0.05).fit(shard)
         np.save(os.path.join(out_dir, f"mcca_w2_rank{rank}.npy"), m.weights_[2])
+        # wide views: the device-side fit, which reads the all-reduced sample count on the device (no read-back)
+        wide = joint_data(n_views=2, n_samples=5003, n_features=[256, 320], latent_dimensions=4,
+                          signal_to_noise=0.02, random_state=10, dtype=np.float32)
+        lo, hi = parallel.shard_rows(5003, rank, world)
+        dev = rCCA(latent_dimensions=4, c=0.1).fit([torch.from_numpy(v[lo:hi]).cuda() for v in wide])
+        assert dev._fit_info["route"] == "device" and dev.n_samples_ == 5003
+        np.save(os.path.join(out_dir, f"wide_w1_rank{rank}.npy"), dev.weights_[1])
     finally:
         dist.destroy_process_group()
 
@@ -63,3 +70,23 @@ def test_two_rank_fit_matches_single_gpu(tmp_path):
     ms = MCCA(latent_dimensions=5, c=0.05).fit(views)
     w2 = np.load(tmp_path / "mcca_w2_rank1.npy")
     assert R.max_rel_err_per_vector([w2], [ms.weights_[2]]) < 1e-9
+    wide = joint_data(n_views=2, n_samples=5003, n_features=[256, 320], latent_dimensions=4,
+                      signal_to_noise=0.02, random_state=10, dtype=np.float32)
+    one = rCCA(latent_dimensions=4, c=0.1).fit(wide)
+    ww = [np.load(tmp_path / f"wide_w1_rank{r}.npy") for r in range(2)]
+    assert np.array_equal(ww[0], ww[1])
+    assert R.max_rel_err_per_vector([ww[0].astype(np.float64)], [one.weights_[1].astype(np.float64)]) < 2e-4
+
+
+def test_exchange_message_round_trip():
+    """pack -> unpack restores the moment buffer (upper block triangle, column sums) and carries n."""
+    from cca_zoo_b200 import ops
+
+    views = [torch.randn(700, d, device="cuda", dtype=torch.float64) for d in (130, 64, 300)]
+    dims = [130, 64, 300]
+    mom = ops.moments(views)
+    packed = ops.moments_pack(mom, dims, 700)
+    assert packed.numel() < mom.numel() * 0.62
+    back, n_dev = ops.moments_unpack(packed, dims)
+    assert float(n_dev.item()) == 700.0
+    assert torch.equal(back, mom)
