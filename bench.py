@@ -370,9 +370,12 @@ def run_ours(args):
     value = world / (ms_per_step * 1e-3)
 
     # ---- end-to-end arm: pinned host inputs -> public API -> result on the host ----
-    for _ in range(min(args.warmup, 2)):
-        step_e2e()
-    e2e_ms = timed(step_e2e, args.steps) / args.steps
+    if args.no_e2e:            # profiling runs (ncu launch lists): the device-resident step only
+        e2e_ms = float("nan")
+    else:
+        for _ in range(min(args.warmup, 2)):
+            step_e2e()
+        e2e_ms = timed(step_e2e, args.steps) / args.steps
     if est is not None:
         d2h = sum(w.nbytes for w in est.weights_) + sum(m.nbytes for m in est.means_)
     else:
@@ -457,6 +460,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="tf32x3", choices=["tf32", "tf32x3", "exact"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling only: skip the end-to-end leg (the line is then "
+                                                          "not a valid bench line)")
     ap.add_argument("--workload", default="rcca", choices=sorted(WORKLOADS),
                     help="rcca = BASELINE configs[1] (the headline); mcca4 = configs[3] shard; ccaloss64 / "
                          "ccaloss512 = configs[2] at the two readings of its width")

@@ -18,6 +18,7 @@
 #include <cmath>
 #include <type_traits>
 
+#include "ccaloss.cuh"
 #include "cholinv.cuh"
 #include "dense.cuh"
 #include "moments.cuh"
@@ -755,14 +756,16 @@ template int mcca_fit<double>(const ColumnLayout&, const double*, const double*,
 // =============================================================================================================
 namespace {
 
-// loss[0] = -sum_ij P[i][j] * S12[i][j]   (one block, fixed order)
+// loss[0] = -sum_ij P[i][j] * S12[i][j]: per-block partial sums (fixed assignment of elements to blocks), then one
+// warp adds the partials in index order -- deterministic
 template <typename T>
-__global__ void loss_dot_kernel(const T* __restrict__ P, int64_t ldp, const T* __restrict__ S, int64_t lds, int d1, int d2,
-                                T* __restrict__ loss) {
+__global__ void loss_dot_partial_kernel(const T* __restrict__ P, int64_t ldp, const T* __restrict__ S, int64_t lds, int d1,
+                                        int d2, double* __restrict__ partial) {
   __shared__ double red[32];
   double acc = 0.0;
-  for (int e = threadIdx.x; e < d1 * d2; e += blockDim.x) {
-    const int i = e / d2, j = e % d2;
+  const int total = d1 * d2;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int i = e / d2, j = e - i * d2;
     acc += (double)P[(size_t)i * ldp + j] * (double)S[(size_t)i * lds + j];
   }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -771,8 +774,50 @@ __global__ void loss_dot_kernel(const T* __restrict__ P, int64_t ldp, const T* _
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+}
+template <typename T>
+__global__ void loss_dot_final_kernel(const double* __restrict__ partial, int nparts, T* __restrict__ loss) {
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < nparts; ++i) t += partial[i];
     loss[0] = (T)(-t);
   }
+}
+
+// column sums of A (m x n) over row slabs: part[slab][j] (fixed order inside a slab)
+template <typename T>
+__global__ void colsum_partial_kernel(int m, int n, const T* __restrict__ A, int64_t lda, int rows_per_slab,
+                                      double* __restrict__ part) {
+  __shared__ double sh[8][33];
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rg = threadIdx.x >> 5;   // 8 row groups
+  const int r0 = blockIdx.y * rows_per_slab, r1 = min(m, r0 + rows_per_slab);
+  double acc = 0.0;
+  if (j < n)
+    for (int i = r0 + rg; i < r1; i += 8) acc += (double)A[(size_t)i * lda + j];
+  sh[rg][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (rg == 0 && j < n) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x & 31];
+    part[(size_t)blockIdx.y * n + j] = t;
+  }
+}
+// A[i][j] = (A[i][j] - mean_j) * scale[0], mean_j from the slab partials (added in slab order)
+template <typename T>
+__global__ void center_apply_kernel(int m, int n, T* __restrict__ A, int64_t lda, const double* __restrict__ part,
+                                    int nslabs, const T* __restrict__ scale) {
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  if (j >= n) return;
+  double t = 0.0;
+  for (int k = 0; k < nslabs; ++k) t += part[(size_t)k * n + j];
+  const T mu = (T)(t / (double)m);
+  const T sc = scale ? scale[0] : T(1);
+  const int rows_per_block = (m + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(m, r0 + rows_per_block);
+  for (int i = r0 + (threadIdx.x >> 5); i < r1; i += blockDim.x >> 5) A[(size_t)i * lda + j] = (A[(size_t)i * lda + j] - mu) * sc;
 }
 
 // A[:, j] = (A[:, j] - mean_i A[i, j]) * scale[0]   (one block per 32 columns; fixed-order reduction)
@@ -798,6 +843,21 @@ __global__ void center_scale_kernel(int m, int n, T* __restrict__ A, int64_t lda
     for (int i = rg; i < m; i += 32) A[(size_t)i * lda + j] = (A[(size_t)i * lda + j] - mu) * sc;
 }
 
+// Per-device scratch of the backward's centring (2 x 32 slabs x up to 4096 columns of partial sums, 2 MB), allocated
+// once with the stream-ordered allocator: the backward entry point takes no workspace argument.
+double* center_scratch(cudaStream_t) {
+  static double* buf[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!buf[dev]) {
+    if (cudaMalloc(reinterpret_cast<void**>(&buf[dev]), sizeof(double) * 2 * 32 * 4096) != cudaSuccess) {
+      set_error("could not allocate the 2 MB centring scratch");
+      return nullptr;
+    }
+  }
+  return buf[dev];
+}
+
 struct LossPlan {
   int d1, d2, D, Dp;
   int64_t ldC, ldR, strideR;
@@ -819,7 +879,8 @@ LossPlan make_loss_plan(const ColumnLayout& L, int64_t n, int precision) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o += al256(bytes); return at; };
   P.oMom = take(sizeof(double) * ((size_t)P.Dp * P.Dp + P.Dp));
-  P.mom_ws_bytes = moments_workspace_bytes(std::is_same<T, float>::value ? 0 : 1, precision, L, n) + 512;
+  P.mom_ws_bytes = std::max(moments_workspace_bytes(std::is_same<T, float>::value ? 0 : 1, precision, L, n),
+                            moments_workspace_bytes(std::is_same<T, float>::value ? 0 : 1, 2, L, n)) + 512;
   P.oMomWs = take(P.mom_ws_bytes);
   P.oC = take(sizeof(T) * (size_t)P.D * P.ldC);
   P.oR = take(sizeof(T) * 2 * (size_t)P.strideR);
@@ -876,6 +937,13 @@ int ccaloss_forward(const ColumnLayout& L, int precision, const void* z1, int64_
   const void* views[2] = {z1, z2};
   const int64_t lds[2] = {ld1, ld2};
   int rc;
+  if (std::max(d1, d2) <= 64) {
+    // narrow representations (config 3's k = 64): the moment pass (exact FMA, HBM / latency bound) and ONE single-CTA
+    // launch for everything else
+    rc = moments_simt<T>(L, views, lds, n, mom, w + P.oMomWs, P.mom_ws_bytes, s);
+    if (rc) return rc;
+    return ccaloss_small_forward<T>(mom, L.Dp, (double)n, d1, d2, eps, loss, saved, flags_out, s);
+  }
   if (std::is_same<T, float>::value && precision != 2)
     rc = moments_tf32(L, views, lds, n, precision == 1, mom, w + P.oMomWs, P.mom_ws_bytes, s);
   else
@@ -946,8 +1014,12 @@ int ccaloss_forward(const ColumnLayout& L, int precision, const void* z1, int64_
     rc = xgemm<T>(b, s);
     if (rc) return rc;
   }
-  loss_dot_kernel<T><<<1, 1024, 0, s>>>(Pm, d2, S12, P.ldC, d1, d2, loss);
-  count_launches(1);
+  {
+    double* partial = reinterpret_cast<double*>(sm + 2048);   // [64]
+    loss_dot_partial_kernel<T><<<64, 256, 0, s>>>(Pm, d2, S12, P.ldC, d1, d2, partial);
+    loss_dot_final_kernel<T><<<1, 32, 0, s>>>(partial, 64, loss);
+    count_launches(2);
+  }
   CCAB_CUDA(cudaGetLastError());
   // flags_out[0..1] = Cholesky status, [2] = non-finite moments
   CCAB_CUDA(cudaMemcpyAsync(flags_out, flags, 2 * sizeof(int), cudaMemcpyDeviceToDevice, s));
@@ -959,6 +1031,8 @@ template <typename T>
 int ccaloss_backward(int d1, int d2, const T* z1, int64_t ld1, const T* z2, int64_t ld2, int64_t n, const T* saved,
                      const T* grad_out, T* g1, int64_t ldg1, T* g2, int64_t ldg2, cudaStream_t s) {
   CCAB_CHECK_ARG(n >= 2 && d1 >= 1 && d2 >= 1, "ccaloss_backward: bad shape");
+  if (std::max(d1, d2) <= 64)
+    return ccaloss_small_backward<T>(d1, d2, z1, ld1, z2, ld2, n, saved, grad_out, g1, ldg1, g2, ldg2, s);
   const T* G11 = saved;
   const T* Pm = saved + (size_t)d1 * d1;
   const T* G22 = Pm + (size_t)d1 * d2;
@@ -981,9 +1055,30 @@ int ccaloss_backward(int d1, int d2, const T* z1, int64_t ld1, const T* z2, int6
   v.A = z1; v.lda = ld1; v.B = Pm; v.ldb = d2; v.C = g2; v.ldc = ldg2;
   rc = xgemm<T>(v, s);
   if (rc) return rc;
-  center_scale_kernel<T><<<(unsigned)ceil_div(d1, 32), 1024, 0, s>>>((int)n, d1, g1, ldg1, grad_out);
-  center_scale_kernel<T><<<(unsigned)ceil_div(d2, 32), 1024, 0, s>>>((int)n, d2, g2, ldg2, grad_out);
-  count_launches(2);
+  // centring: slab partial sums, then subtract and scale (the scratch lives behind the gradients' own columns: none is
+  // available here, so the caller-provided `part` buffer is carved from g-independent static device scratch)
+  {
+    const int nslabs = (int)std::min<int64_t>(32, ceil_div(n, 128));
+    const int rows_per_slab = (int)ceil_div(n, nslabs);
+    double* part = std::max(d1, d2) <= 4096 ? center_scratch(s) : nullptr;
+    if (!part) {   // wider than the scratch (or no scratch): the single-pass kernel
+      center_scale_kernel<T><<<(unsigned)ceil_div(d1, 32), 1024, 0, s>>>((int)n, d1, g1, ldg1, grad_out);
+      center_scale_kernel<T><<<(unsigned)ceil_div(d2, 32), 1024, 0, s>>>((int)n, d2, g2, ldg2, grad_out);
+      count_launches(2);
+      CCAB_CUDA(cudaGetLastError());
+      return 0;
+    }
+    for (int v = 0; v < 2; ++v) {
+      T* g = v ? g2 : g1;
+      const int d = v ? d2 : d1;
+      const int64_t ldg = v ? ldg2 : ldg1;
+      double* pv = part + (size_t)v * 32 * 4096;
+      colsum_partial_kernel<T><<<dim3((unsigned)ceil_div(d, 32), (unsigned)nslabs), 256, 0, s>>>((int)n, d, g, ldg,
+                                                                                                 rows_per_slab, pv);
+      center_apply_kernel<T><<<dim3((unsigned)ceil_div(d, 32), 32), 256, 0, s>>>((int)n, d, g, ldg, pv, nslabs, grad_out);
+    }
+    count_launches(4);
+  }
   CCAB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -37,7 +37,7 @@ int mcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
              size_t ws_bytes, cudaStream_t stream);
 
 // ---- deep-CCA objective on the device (cca_zoo/deep/objectives.py:61-102), any widths, nothing read back ----
-// saved (T[d1*d1 + d1*d2 + d2*d2]) = G11 | P | G22 for the analytic backward; flags_out (device int[3]) = Cholesky
+// saved (T[d1*d1 + d1*d2 + d2*d2 + d1 + d2]) = G11 | P | G22 | means for the analytic backward; flags_out (device int[3]) = Cholesky
 // status of S11, S22 (pivot^2 <= eps / 4 counts as failure) and a non-finite-input flag, to be checked lazily.
 template <typename T>
 size_t ccaloss_workspace_bytes(const ColumnLayout& L, int64_t n, int precision);

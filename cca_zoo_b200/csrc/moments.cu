@@ -905,7 +905,7 @@ SimtPlan plan_simt(const ColumnLayout& L, int64_t n_rows) {
   P.ntiles = P.nb64 * (P.nb64 + 1) / 2;
   int S = 1;
   if (P.ntiles < 2 * sm_count()) S = (2 * sm_count()) / P.ntiles;
-  S = (int)std::min<int64_t>(S, std::max<int64_t>(1, n_rows / 256));
+  S = (int)std::min<int64_t>(S, std::max<int64_t>(1, n_rows / 64));   // mini-batches: fill the machine with short slabs
   S = std::max(1, std::min(S, 64));
   P.rows_per_split = ceil_div(ceil_div(n_rows, S), 16) * 16;
   P.num_splits = (int)ceil_div(n_rows, P.rows_per_split);

@@ -21,10 +21,10 @@ namespace ccab {
 
 namespace {
 
-constexpr int kSmallThreads = 1024;
+constexpr int kSmallThreads = 512;
 constexpr int kSmallMaxN = 128;                      // (n/2)^2 2 x 2 blocks over 1024 threads: 4 per thread
-constexpr int kHB = (kSmallMaxN / 2) * (kSmallMaxN / 2) / kSmallThreads;   // H blocks per thread
-constexpr int kVB = 2;                                // V items per thread: (n/2) * ceil(n/4) <= 2048
+constexpr int kHB = ((kSmallMaxN / 2) * (kSmallMaxN / 2 + 1) / 2 + kSmallThreads - 1) / kSmallThreads;   // upper-triangle pair blocks per thread
+constexpr int kVB = (kSmallMaxN / 2) * (kSmallMaxN / 4) / kSmallThreads;   // V items per thread: (n/2) * ceil(n/4) <= 2048
 
 template <typename T>
 struct SmallEps;
@@ -37,17 +37,30 @@ struct SmallEps<double> {
   static constexpr double v = 2.220446049250313e-16;
 };
 
-// rotation of one index pair, as every thread needs it: the indices and Rutishauser's (s, tau = s / (1 + c))
+// Position bookkeeping of the tournament: the matrix is PHYSICALLY permuted after every step so that the rotation
+// pairs are always the adjacent positions (2i, 2i+1) -- all addresses are affine in the block indices, no index
+// tables.  Brent-Luk movement on the 2 x (N/2) array top[i] = position 2i, bot[i] = position 2i+1: top[0] stays,
+// bot[0] -> top[1], top[i] -> top[i+1], top[last] -> bot[last], bot[i] -> bot[i-1].
+__device__ __forceinline__ int rr_dest(int r, int N) {
+  if (r == 0 || N == 2) return r;
+  if (r == 1) return 2;
+  if (r & 1) return r - 2;                 // bot[i] -> bot[i-1]
+  return r + 2 < N ? r + 2 : N - 1;        // top[i] -> top[i+1], the last one drops to the bottom row
+}
+
+__device__ __forceinline__ float fast_sqrt(float x) { return __fsqrt_rn(x); }
+__device__ __forceinline__ double fast_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float fast_rsqrt(float x) {
+  const float r = rsqrtf(x);
+  return r * fmaf(-0.5f * x * r, r, 1.5f);
+}
+__device__ __forceinline__ double fast_rsqrt(double x) { return 1.0 / sqrt(x); }
+__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double fast_div(double a, double b) { return a / b; }
+
 template <typename T>
-struct alignas(16) Rot {
-  int p, q;
-  T s, tau;
-};
-template <>
-struct alignas(32) Rot<double> {
-  int p, q;
-  double s, tau;
-  double pad;
+struct alignas(2 * sizeof(T)) Rot2 {
+  T s, tau;   // Rutishauser: x' = x - s (y + tau x), y' = y + s (x - tau y)
 };
 
 template <typename T>
@@ -59,8 +72,8 @@ syevj_small_kernel(const T* __restrict__ A, int64_t lda, int64_t strideA, int n,
   // arithmetic, hence identical bits) and accumulates the eigenvector columns [c0, c1) only -- the V update is
   // as large as the H update and splits without any communication.
   extern __shared__ __align__(16) unsigned char sv_smem[];
-  const int N = (n + 1) & ~1;      // even number of players; index n (if any) is a bye
-  const int LD = N + 1;
+  const int N = (n + 1) & ~1;      // even number of positions; for odd n one of them is a bye (zero row / column)
+  const int LD = N + 2;            // even: the two columns of a pair sit in one aligned 2-vector
   const int m2 = N / 2;
   const int nsplit = gridDim.x;
   const int cw = (n + nsplit - 1) / nsplit;              // eigenvector columns of this CTA
@@ -68,11 +81,14 @@ syevj_small_kernel(const T* __restrict__ A, int64_t lda, int64_t strideA, int n,
   const int c1 = min(n, c0 + cw);
   const int ncol = max(0, c1 - c0);
   const int LDV = cw + 1;
-  T* H = reinterpret_cast<T*>(sv_smem);
-  T* V = H + (size_t)N * LD;                             // [N][LDV]
-  T* red = V + (size_t)N * LDV;                          // [32]
-  Rot<T>* rot = reinterpret_cast<Rot<T>*>((reinterpret_cast<uintptr_t>(red + 32) + 31) & ~uintptr_t(31));   // [m2]
-  int* rank = reinterpret_cast<int*>(rot + m2);          // [N]
+  T* const H0 = reinterpret_cast<T*>(sv_smem);
+  T* const H1 = H0 + (size_t)N * LD;
+  T* const V0 = H1 + (size_t)N * LD;
+  T* const V1 = V0 + (size_t)N * LDV;
+  T* red = V1 + (size_t)N * LDV;                         // [32]
+  Rot2<T>* rot = reinterpret_cast<Rot2<T>*>((reinterpret_cast<uintptr_t>(red + 32) + 15) & ~uintptr_t(15));   // [m2]
+  int* label = reinterpret_cast<int*>(rot + m2);         // [2][N] original index held by a position (-1: the bye)
+  int* rank = label + 2 * N;                             // [N]
   __shared__ int done;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -84,13 +100,14 @@ syevj_small_kernel(const T* __restrict__ A, int64_t lda, int64_t strideA, int n,
     const int r = e / N, c = e % N;
     T v = T(0);
     if (r < n && c < n) v = T(0.5) * (Ab[(size_t)r * lda + c] + Ab[(size_t)c * lda + r]);
-    H[r * LD + c] = v;
+    H0[r * LD + c] = v;
     fro_local = fma(v, v, fro_local);
   }
   for (int e = tid; e < N * cw; e += kSmallThreads) {
     const int r = e / cw, c = e % cw;
-    V[r * LDV + c] = (r == c0 + c) ? T(1) : T(0);
+    V0[r * LDV + c] = (r == c0 + c && r < n) ? T(1) : T(0);
   }
+  if (tid < N) label[tid] = tid < n ? tid : -1;
   for (int o = 16; o > 0; o >>= 1) fro_local += __shfl_xor_sync(0xffffffffu, fro_local, o);
   if (lane == 0) red[warp] = fro_local;
   if (tid == 0) done = 0;
@@ -99,15 +116,20 @@ syevj_small_kernel(const T* __restrict__ A, int64_t lda, int64_t strideA, int n,
   for (int w = 0; w < kSmallThreads / 32; ++w) fro2 += red[w];
   __syncthreads();
 
-  // static work assignment: H blocks (i, j) = blk / m2, blk % m2 for blk = tid + u * threads; V items likewise
-  constexpr int CH = sizeof(T) == 4 ? 2 : 1;   // blocks in flight per thread (64 registers at 1024 threads)
-  int hi[kHB], hj[kHB], vi[kVB], vc[kVB];
+  // static work assignment: upper-triangle pair blocks (i <= j), V items (pair, column)
+  const int nt = m2 * (m2 + 1) / 2;
+  int bi[kHB], bj[kHB];
 #pragma unroll
   for (int u = 0; u < kHB; ++u) {
-    const int blk = tid + u * kSmallThreads;
-    hi[u] = blk < m2 * m2 ? blk / m2 : -1;
-    hj[u] = blk < m2 * m2 ? blk % m2 : 0;
+    int t = tid + u * kSmallThreads;
+    bi[u] = -1; bj[u] = 0;
+    if (t < nt) {
+      int i = 0, rowlen = m2;
+      while (t >= rowlen) { t -= rowlen; ++i; --rowlen; }
+      bi[u] = i; bj[u] = i + t;
+    }
   }
+  int vi[kVB], vc[kVB];
 #pragma unroll
   for (int u = 0; u < kVB; ++u) {
     const int e = tid + u * kSmallThreads;
@@ -115,117 +137,71 @@ syevj_small_kernel(const T* __restrict__ A, int64_t lda, int64_t strideA, int n,
     vc[u] = (ncol > 0 && e < m2 * ncol) ? e % ncol : 0;
   }
 
-  int sweeps = 0;
+  int cur = 0, sweeps = 0;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     T off_local = T(0);
     for (int t = 0; t < N - 1; ++t) {
+      const T* H = cur ? H1 : H0;
+      T* Hn = cur ? H0 : H1;
+      const T* V = cur ? V1 : V0;
+      T* Vn = cur ? V0 : V1;
       if (tid < m2) {
-        int p, q;
-        if (tid == 0) { p = N - 1; q = t; }
-        else {
-          p = t + tid; if (p >= N - 1) p -= N - 1;
-          q = t - tid; if (q < 0) q += N - 1;
-        }
+        const int p = 2 * tid, q = p + 1;
+        const T hpp = H[p * LD + p], hqq = H[q * LD + q], hpq = H[p * LD + q];
         T s = T(0), tau = T(0);
-        if (p < n && q < n) {
-          const T hpp = H[p * LD + p], hqq = H[q * LD + q], hpq = H[p * LD + q];
-          off_local = fma(T(2) * hpq, hpq, off_local);
-          if (fabs(hpq) > SmallEps<T>::v * T(0.01) * sqrt(fabs(hpp * hqq)) && hpq != T(0)) {
-            const T th = (hqq - hpp) / (T(2) * hpq);
-            const T tt = (th >= T(0) ? T(1) : T(-1)) / (fabs(th) + sqrt(T(1) + th * th));
-            const T c = T(1) / sqrt(T(1) + tt * tt);
-            s = tt * c;
-            tau = s / (T(1) + c);
-          }
+        off_local = fma(T(2) * hpq, hpq, off_local);
+        // the whole CTA waits for these few threads: keep the dependent chain short (4 special-function ops).
+        // With z = (hqq - hpp) / 2 and r = hypot(z, hpq):  tan = hpq / (z + sign(z) r)  (the smaller root),
+        // c = 1 / sqrt(1 + tan^2), s = tan c, tau = s / (1 + c).  The rotation only has to be orthogonal to
+        // rounding (it is, by construction of the update from s and tau) and ANNIHILATE approximately: a pivot left
+        // at 1e-7 of its size is finished off by the next sweep, so fast reciprocals are good enough in float.
+        if (hpq * hpq > SmallEps<T>::v * SmallEps<T>::v * T(1e-4) * fabs(hpp * hqq) && hpq != T(0)) {
+          const T z = T(0.5) * (hqq - hpp);
+          const T r = fast_sqrt(fma(z, z, hpq * hpq));
+          const T tt = fast_div(hpq, z + (z >= T(0) ? r : -r));
+          const T c = fast_rsqrt(fma(tt, tt, T(1)));
+          s = tt * c;
+          tau = fast_div(s, T(1) + c);
         }
-        Rot<T> r;
-        r.p = p; r.q = q; r.s = s; r.tau = tau;
+        Rot2<T> r;
+        r.s = s; r.tau = tau;
         rot[tid] = r;
       }
+      if (tid < N) label[(cur ^ 1) * N + rr_dest(tid, N)] = label[cur * N + tid];
       __syncthreads();
-      // H <- J^T H J : a thread owns the SAME 2 x 2 blocks (rows {p_i, q_i} x columns {p_j, q_j}) in every step;
-      // all operands are loaded before anything is stored so that the loads overlap (the blocks partition H: no
-      // hazard).  Rutishauser's update  x' = x - s (y + tau x),  y' = y + s (x - tau y)  keeps the error
-      // proportional to the rotation.
-      if (sizeof(T) == 8) {
-        // float64: 64 registers per thread do not hold the preloaded operands; walk the blocks warp by warp instead
-        for (int i = warp; i < m2; i += kSmallThreads / 32) {
-          const Rot<T> ri = rot[i];
-          T* Hp = H + ri.p * LD;
-          T* Hq = H + ri.q * LD;
-          for (int j = lane; j < m2; j += 32) {
-            const Rot<T> rj = rot[j];
-            const T a = Hp[rj.p], b = Hp[rj.q], c_ = Hq[rj.p], d = Hq[rj.q];
-            const T a1 = a - ri.s * (c_ + ri.tau * a), c1 = c_ + ri.s * (a - ri.tau * c_);
-            const T b1 = b - ri.s * (d + ri.tau * b), d1 = d + ri.s * (b - ri.tau * d);
-            T a2 = a1 - rj.s * (b1 + rj.tau * a1), b2 = b1 + rj.s * (a1 - rj.tau * b1);
-            T c2 = c1 - rj.s * (d1 + rj.tau * c1), d2 = d1 + rj.s * (c1 - rj.tau * d1);
-            if (i == j && ri.s != T(0)) { b2 = T(0); c2 = T(0); }
-            Hp[rj.p] = a2; Hp[rj.q] = b2; Hq[rj.p] = c2; Hq[rj.q] = d2;
-          }
-        }
-        for (int e = tid; e < m2 * ncol; e += kSmallThreads) {
-          const int i = e / ncol, col = e - i * ncol;
-          const Rot<T> ri = rot[i];
-          const T vp = V[ri.p * LDV + col], vq = V[ri.q * LDV + col];
-          V[ri.p * LDV + col] = vp - ri.s * (vq + ri.tau * vp);
-          V[ri.q * LDV + col] = vq + ri.s * (vp - ri.tau * vq);
-        }
-      } else {
+      // H <- J^T H J on the upper-triangle pair blocks, written (with their mirror images) to the NEXT buffer at the
+      // positions the tournament moves them to: reads and writes never touch the same buffer, one barrier per phase
 #pragma unroll
-      for (int u0 = 0; u0 < kHB; u0 += CH) {
-        Rot<T> ri[CH], rj[CH];
-        T a[CH], b[CH], c_[CH], d[CH];
-#pragma unroll
-        for (int u = 0; u < CH; ++u) {
-          if (hi[u0 + u] >= 0) {
-            ri[u] = rot[hi[u0 + u]];
-            rj[u] = rot[hj[u0 + u]];
-          }
+      for (int u = 0; u < kHB; ++u) {
+        if (bi[u] < 0) continue;
+        const int i = bi[u], j = bj[u];
+        const Rot2<T> ri = rot[i], rj = rot[j];
+        const T* h0 = H + (2 * i) * LD + 2 * j;
+        const T a = h0[0], b = h0[1], c_ = h0[LD], d = h0[LD + 1];
+        const T a1 = a - ri.s * (c_ + ri.tau * a), c1 = c_ + ri.s * (a - ri.tau * c_);
+        const T b1 = b - ri.s * (d + ri.tau * b), d1 = d + ri.s * (b - ri.tau * d);
+        T a2 = a1 - rj.s * (b1 + rj.tau * a1), b2 = b1 + rj.s * (a1 - rj.tau * b1);
+        T c2 = c1 - rj.s * (d1 + rj.tau * c1), d2 = d1 + rj.s * (c1 - rj.tau * d1);
+        if (i == j) {                               // pivot block: annihilated exactly, kept symmetric
+          if (ri.s != T(0)) { b2 = T(0); c2 = T(0); } else { c2 = b2; }
         }
-#pragma unroll
-        for (int u = 0; u < CH; ++u) {
-          if (hi[u0 + u] >= 0) {
-            a[u] = H[ri[u].p * LD + rj[u].p]; b[u] = H[ri[u].p * LD + rj[u].q];
-            c_[u] = H[ri[u].q * LD + rj[u].p]; d[u] = H[ri[u].q * LD + rj[u].q];
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < CH; ++u) {
-          if (hi[u0 + u] >= 0) {
-            const T si = ri[u].s, ti = ri[u].tau, sj = rj[u].s, tj = rj[u].tau;
-            const T a1 = a[u] - si * (c_[u] + ti * a[u]), c1 = c_[u] + si * (a[u] - ti * c_[u]);
-            const T b1 = b[u] - si * (d[u] + ti * b[u]), d1 = d[u] + si * (b[u] - ti * d[u]);
-            T a2 = a1 - sj * (b1 + tj * a1), b2 = b1 + sj * (a1 - tj * b1);
-            T c2 = c1 - sj * (d1 + tj * c1), d2 = d1 + sj * (c1 - tj * d1);
-            if (hi[u0 + u] == hj[u0 + u] && si != T(0)) { b2 = T(0); c2 = T(0); }   // the annihilated pivot, exactly
-            H[ri[u].p * LD + rj[u].p] = a2; H[ri[u].p * LD + rj[u].q] = b2;
-            H[ri[u].q * LD + rj[u].p] = c2; H[ri[u].q * LD + rj[u].q] = d2;
-          }
-        }
+        const int rp = rr_dest(2 * i, N), rq = rr_dest(2 * i + 1, N), cp = rr_dest(2 * j, N), cq = rr_dest(2 * j + 1, N);
+        Hn[rp * LD + cp] = a2; Hn[rp * LD + cq] = b2; Hn[rq * LD + cp] = c2; Hn[rq * LD + cq] = d2;
+        if (i != j) { Hn[cp * LD + rp] = a2; Hn[cq * LD + rp] = b2; Hn[cp * LD + rq] = c2; Hn[cq * LD + rq] = d2; }
       }
-      // eigenvector rows p_i, q_i (own columns), same static assignment
-      {
-        Rot<T> rv[kVB];
-        T vp[kVB], vq[kVB];
 #pragma unroll
-        for (int u = 0; u < kVB; ++u)
-          if (vi[u] >= 0) rv[u] = rot[vi[u]];
-#pragma unroll
-        for (int u = 0; u < kVB; ++u)
-          if (vi[u] >= 0) { vp[u] = V[rv[u].p * LDV + vc[u]]; vq[u] = V[rv[u].q * LDV + vc[u]]; }
-#pragma unroll
-        for (int u = 0; u < kVB; ++u)
-          if (vi[u] >= 0) {
-            V[rv[u].p * LDV + vc[u]] = vp[u] - rv[u].s * (vq[u] + rv[u].tau * vp[u]);
-            V[rv[u].q * LDV + vc[u]] = vq[u] + rv[u].s * (vp[u] - rv[u].tau * vq[u]);
-          }
-      }
+      for (int u = 0; u < kVB; ++u) {
+        if (vi[u] < 0) continue;
+        const Rot2<T> r = rot[vi[u]];
+        const int p = 2 * vi[u];
+        const T vp = V[p * LDV + vc[u]], vq = V[(p + 1) * LDV + vc[u]];
+        Vn[rr_dest(p, N) * LDV + vc[u]] = vp - r.s * (vq + r.tau * vp);
+        Vn[rr_dest(p + 1, N) * LDV + vc[u]] = vq + r.s * (vp - r.tau * vq);
       }
       __syncthreads();
+      cur ^= 1;
     }
     ++sweeps;
-    // off-diagonal mass met during this sweep (threads >= m2 contribute 0)
     for (int o = 16; o > 0; o >>= 1) off_local += __shfl_xor_sync(0xffffffffu, off_local, o);
     if (lane == 0) red[warp] = off_local;
     __syncthreads();
@@ -238,23 +214,30 @@ syevj_small_kernel(const T* __restrict__ A, int64_t lda, int64_t strideA, int n,
     if (done) break;
   }
 
-  // ---- sort (rank by counting, descending; ties by index) and write ----
-  if (tid < n) {
-    const T li = H[tid * LD + tid];
-    int rk = 0;
-    for (int j = 0; j < n; ++j) {
-      const T lj = H[j * LD + j];
-      rk += (lj > li || (lj == li && j < tid)) ? 1 : 0;
+  // ---- sort (rank by counting, descending; ties by position) and write ----
+  const T* H = cur ? H1 : H0;
+  const T* V = cur ? V1 : V0;
+  const int* lab = label + cur * N;
+  if (tid < N) {
+    int rk = -1;
+    if (lab[tid] >= 0) {
+      const T li = H[tid * LD + tid];
+      rk = 0;
+      for (int j = 0; j < N; ++j) {
+        if (lab[j] < 0) continue;
+        const T lj = H[j * LD + j];
+        rk += (lj > li || (lj == li && j < tid)) ? 1 : 0;
+      }
+      if (evals && blockIdx.x == 0) evals[(size_t)blockIdx.y * strideE + rk] = li;
     }
     rank[tid] = rk;
-    if (evals && blockIdx.x == 0) evals[(size_t)blockIdx.y * strideE + rk] = li;
   }
   __syncthreads();
   if (evt) {
     T* Eb = evt + (size_t)blockIdx.y * strideV;
-    for (int e = tid; e < n * ncol; e += kSmallThreads) {
+    for (int e = tid; e < N * ncol; e += kSmallThreads) {
       const int r = e / ncol, c = e - r * ncol;
-      Eb[(size_t)rank[r] * ldv + c0 + c] = V[r * LDV + c];
+      if (rank[r] >= 0) Eb[(size_t)rank[r] * ldv + c0 + c] = V[r * LDV + c];
     }
   }
   if (tid == 0 && info && blockIdx.x == 0) info[blockIdx.y] = done ? sweeps : -sweeps;
@@ -266,8 +249,8 @@ template <typename T>
 size_t small_smem_bytes(int n) {
   const int N = (n + 1) & ~1;
   const int cw = (n + small_nsplit(n) - 1) / small_nsplit(n);
-  return sizeof(T) * ((size_t)N * (N + 1) + (size_t)N * (cw + 1) + 32) + sizeof(Rot<T>) * (size_t)(N / 2) +
-         sizeof(int) * (size_t)N + 128;
+  return sizeof(T) * (2 * (size_t)N * (N + 2) + 2 * (size_t)N * (cw + 1) + 32) + sizeof(Rot2<T>) * (size_t)(N / 2) +
+         sizeof(int) * 3 * (size_t)N + 128;
 }
 
 }  // namespace

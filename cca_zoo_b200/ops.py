@@ -369,7 +369,7 @@ def ccaloss_fwd(z1, z2, eps, precision="exact"):
     if z1.dtype == torch.float64:
         prec = _lib.PREC_EXACT
     loss = torch.empty(1, dtype=z1.dtype, device=z1.device)
-    saved = torch.empty(d1 * d1 + d1 * d2 + d2 * d2, dtype=z1.dtype, device=z1.device)
+    saved = torch.empty(d1 * d1 + d1 * d2 + d2 * d2 + d1 + d2, dtype=z1.dtype, device=z1.device)
     flags = torch.empty(3, dtype=torch.int32, device=z1.device)
     ws = _ws(lib.ccab_ccaloss_workspace_bytes(dt, prec, d1, d2, n), z1.device)
     with torch.cuda.device(z1.device):

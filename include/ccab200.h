@@ -225,12 +225,15 @@ int ccab_mcca_fit(int dtype, int n_views, const int64_t* dims, const double* mom
 /* ---- the deep-CCA objective behind the ABI (any widths) ---------------------------------------------------------
  * ccab_ccaloss_fwd: loss[0] = -|| S11^-1/2 S12 S22^-1/2 ||_F^2 with S_ii = cov(z_i) + eps I, from the moment pass over
  * [z1 z2] (precision as in ccab_moments), a batched Cholesky + inverse and 7 GEMMs; `saved`
- * (T[d1*d1 + d1*d2 + d2*d2]) receives G11 = P S21 S11^-1 | P = S11^-1 S12 S22^-1 | G22 = S22^-1 S21 P for the backward.
+ * (T[d1*d1 + d1*d2 + d2*d2 + d1 + d2]) receives G11 = P S21 S11^-1 | P = S11^-1 S12 S22^-1 | G22 = S22^-1 S21 P | the
+ * column means of z1, z2 (written by the fused path for widths <= 64) for the backward.
  * Nothing is read back: flags_dev (device int[3]) = Cholesky status of S11, S22 (a pivot^2 <= eps / 4 counts as a failure:
  * rounding destroyed the ridge; the caller re-runs through the eigen route, which clamps like the reference) and a
  * non-finite-input flag -- check lazily.
  * ccab_ccaloss_bwd: g1 = 2/(n-1) center(z1 G11 - z2 P^T) * grad_out[0], g2 = 2/(n-1) center(z2 G22 - z1 P) * grad_out[0]
- * (grad_out: device scalar, may be NULL = 1).  4 tall GEMMs (tcgen05 for float) + 2 centring passes.
+ * (grad_out: device scalar, may be NULL = 1).  4 tall GEMMs (tcgen05 for float) + the centring (slab partial sums in a
+ * 2 MB per-device scratch that this entry point allocates on first use -- the one exception to "the library never
+ * allocates": it takes no workspace argument); widths <= 64 run as ONE fused launch instead.
  * Replaces cca_zoo/deep/objectives.py:9-21,79-102 and torch autograd through two eigh + eigvalsh. */
 size_t ccab_ccaloss_workspace_bytes(int dtype, int precision, int d1, int d2, int64_t n);
 int ccab_ccaloss_fwd(int dtype, int precision, const void* z1, int64_t ld1, const void* z2, int64_t ld2, int64_t n,

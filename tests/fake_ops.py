@@ -205,7 +205,8 @@ def ccaloss_fwd(z1, z2, eps, precision="exact"):
     G11 = P @ S12.T @ A1
     G22 = A2 @ S12.T @ P
     loss = -(P * S12).sum()
-    saved = torch.cat([G11.reshape(-1), P.reshape(-1), G22.reshape(-1)]).to(dt)
+    means = torch.cat([z1.to(torch.float64).mean(dim=0), z2.to(torch.float64).mean(dim=0)])
+    saved = torch.cat([G11.reshape(-1), P.reshape(-1), G22.reshape(-1), means]).to(dt)
     return loss.reshape(1).to(dt), saved, flags
 
 
@@ -214,7 +215,7 @@ def ccaloss_bwd(z1, z2, saved, grad_out):
     s64 = saved.to(torch.float64)
     G11 = s64[:d1 * d1].reshape(d1, d1)
     P = s64[d1 * d1:d1 * d1 + d1 * d2].reshape(d1, d2)
-    G22 = s64[d1 * d1 + d1 * d2:].reshape(d2, d2)
+    G22 = s64[d1 * d1 + d1 * d2:d1 * d1 + d1 * d2 + d2 * d2].reshape(d2, d2)
     a = 2.0 / (n - 1)
     x1, x2 = z1.to(torch.float64), z2.to(torch.float64)
     g1 = a * (x1 @ G11 - x2 @ P.T)

