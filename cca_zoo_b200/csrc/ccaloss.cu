@@ -13,6 +13,8 @@
 // elimination step.
 #include "ccaloss.cuh"
 
+#include "chol_device.cuh"
+
 namespace ccab {
 
 constexpr int kLD = 64;
@@ -213,6 +215,84 @@ __device__ void smem_matmul4(const T* A, const T* B, T* Cm, int m, int n, int k)
   __syncthreads();
 }
 
+// S_h^-1 for the two (<= 64 x 64, identity-padded) SPD matrices side by side: threads [0, 512) work on A1, the rest on
+// A2, both halves in lockstep (the barriers are common).  Cholesky by one warp per 32 x 32 block (chol_device.cuh),
+// panel by row-wise forward substitution, inverse of the factor by one warp per diagonal block plus one
+// recursive-doubling step, then A <- X^T X with X = L^-1.  X1 / X2 / tmp are scratch (64 x 65, 64 x 65, 64 x 65).
+// notpd[h] != 0 when a pivot of matrix h is <= piv_tol.
+template <typename T>
+__device__ void chol_inverse_pair(T* A1, int d1, T* A2, int d2, T* X1, T* X2, T* tmp, T* dinv, T piv_tol, int* notpd) {
+  const int half = threadIdx.x >> 9, t = threadIdx.x & 511, hw = t >> 5, lane = t & 31;
+  T* A = half ? A2 : A1;
+  T* X = half ? X2 : X1;
+  T* tm = tmp + half * 32 * kLP;
+  T* dv = dinv + half * kLD;
+  const int d = half ? d2 : d1;
+  const bool two = d > 32;                         // this half has a second 32-block with data
+  const bool any_two = d1 > 32 || d2 > 32;         // uniform over the CTA
+  for (int e = t; e < kLD * kLD; e += 512) X[(e / kLD) * kLP + e % kLD] = T(0);
+  if (t < kLD) dv[t] = T(1);
+  __syncthreads();
+  if (hw == 0) warp_chol_32<T, kLP>(A, dv, 0, d, 0, piv_tol, notpd + half);
+  __syncthreads();
+  if (any_two) {
+    if (two && t < 32) {                           // panel row 32 + t <- a L_00^-T
+      T* row = A + (32 + t) * kLP;
+      T a[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) a[c] = row[c];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        T v = a[c];
+#pragma unroll
+        for (int k = 0; k < c; ++k) v = fma(-a[k], A[c * kLP + k], v);
+        a[c] = v * dv[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) row[c] = a[c];
+    }
+    __syncthreads();
+    if (two)
+      for (int e = t; e < 32 * 32; e += 512) {     // trailing update, lower part
+        const int r = 32 + e / 32, c = 32 + e % 32;
+        if (c > r) continue;
+        T acc = T(0);
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) acc = fma(A[r * kLP + k], A[c * kLP + k], acc);
+        A[r * kLP + c] -= acc;
+      }
+    __syncthreads();
+    if (two && hw == 0) warp_chol_32<T, kLP>(A, dv, 32, d, 0, piv_tol, notpd + half);
+    __syncthreads();
+  }
+  if (hw == 0) warp_trinv_32<T, kLP>(A, dv, X, 0);
+  if (hw == 1) {
+    if (two) warp_trinv_32<T, kLP>(A, dv, X, 32);
+    else X[(32 + lane) * kLP + 32 + lane] = T(1);   // padding block: identity
+  }
+  __syncthreads();
+  if (any_two) {                                   // X_10 = -X_11 (L_10 X_00)
+    if (two)
+      for (int e = t; e < 32 * 32; e += 512) {
+        const int rr = e / 32, cc = e % 32;
+        T acc = T(0);
+        for (int k = cc; k < 32; ++k) acc = fma(A[(32 + rr) * kLP + k], X[k * kLP + cc], acc);
+        tm[rr * kLP + cc] = acc;
+      }
+    __syncthreads();
+    if (two)
+      for (int e = t; e < 32 * 32; e += 512) {
+        const int rr = e / 32, cc = e % 32;
+        T acc = T(0);
+        for (int k = 0; k <= rr; ++k) acc = fma(X[(32 + rr) * kLP + 32 + k], tm[k * kLP + cc], acc);
+        X[(32 + rr) * kLP + cc] = -acc;
+      }
+    __syncthreads();
+  }
+  smem_matmul4<T, 1, 0>(X1, X1, A1, kLD, kLD, kLD);   // S^-1 = X^T X (all threads, one matrix after the other)
+  smem_matmul4<T, 1, 0>(X2, X2, A2, kLD, kLD, kLD);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(1024) ccaloss_small_fwd_kernel(const double* __restrict__ mom, int Dp, double n, int d1,
                                                                  int d2, T eps, T* __restrict__ loss,
@@ -229,10 +309,15 @@ __global__ void __launch_bounds__(1024) ccaloss_small_fwd_kernel(const double* _
   T* red = colk + 2 * kLD;                   // [32]
   T* minpiv = red + 32;                      // [2]
   __shared__ int bad;
+  __shared__ int notpd[2];
   const double* M = mom;
   const double* s = mom + (size_t)Dp * Dp;
   const int o2 = 128;                        // padded offset of view 2 (each view occupies one 128-column block)
-  if (threadIdx.x == 0) { minpiv[0] = T(3.0e38); minpiv[1] = T(3.0e38); bad = 0; }
+  if (threadIdx.x == 0) { minpiv[0] = T(3.0e38); minpiv[1] = T(3.0e38); bad = 0; notpd[0] = notpd[1] = 0; }
+  for (int e = threadIdx.x; e < kLD * kLD; e += blockDim.x) {   // identity padding up to 64 x 64
+    const int i = e / kLD, j = e % kLD;
+    I1[i * kLP + j] = I2[i * kLP + j] = (i == j) ? T(1) : T(0);
+  }
   __syncthreads();
   const double inv = 1.0 / (n - 1.0);
   int notfinite = 0;
@@ -261,7 +346,7 @@ __global__ void __launch_bounds__(1024) ccaloss_small_fwd_kernel(const double* _
   T* mean = G22 + (size_t)d2 * d2;
   for (int i = threadIdx.x; i < d1 + d2; i += blockDim.x) mean[i] = (T)(s[i < d1 ? i : o2 + i - d1] / n);
   __syncthreads();
-  spd_inverse_pair(I1, d1, I2, d2, rowk, colk, minpiv);
+  chol_inverse_pair(I1, d1, I2, d2, Tm, Tm2, Pm, rowk, T(0.25) * eps, notpd);
   smem_matmul4<T, 0, 0>(I1, S12, Tm, d1, d2, d1);      // Tm  = A1 S12          (Q)
   smem_matmul4<T, 0, 0>(S12, I2, Tm2, d1, d2, d2);     // Tm2 = S12 A2          (Q2)
   smem_matmul4<T, 0, 0>(Tm, I2, Pm, d1, d2, d2);       // P   = A1 S12 A2
@@ -279,9 +364,8 @@ __global__ void __launch_bounds__(1024) ccaloss_small_fwd_kernel(const double* _
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (threadIdx.x == 0) {
       loss[0] = -acc;
-      const T floor = T(0.25) * eps;
-      flags[0] = !(minpiv[0] > floor);
-      flags[1] = !(minpiv[1] > floor);
+      flags[0] = notpd[0] != 0;
+      flags[1] = notpd[1] != 0;
       flags[2] = bad;
     }
   }
