@@ -396,7 +396,7 @@ def run_ours(args):
         peak_src = "MEASURED_PEAKS.json bf16_tflops/2 (TF32 runs at half the dense bf16 rate)" if peaks else \
             "fallback 1590/2 TFLOP/s (B200_PROFILING.md)"
         flops = n * D * (D + 1)  # algorithmic: symmetric product, SURVEY.md §8d (per rank)
-        passes = 3 if args.precision == "tf32x3" else 1
+        passes = {"tf32x3": 3, "tf32x3b": 2}.get(args.precision, 1)
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
@@ -426,7 +426,7 @@ def run_ours(args):
         "metric": W["metric"], "value": value, "unit": W["unit"], "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": ("tf32x3+f32" if args.precision == "tf32x3" else args.precision + "+f32") if est is not None else "f32",
+        "dtype": (args.precision + "+f32") if est is not None else "f32",
         "data": "synthetic",
         "config": {"workload": W["text"], "rows_per_gpu": n, "total_rows": n * world,
                    "parallelism": (f"sample-sharded x{world}, one all-reduce of the moment buffer" if est is not None
@@ -458,7 +458,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="tf32x3", choices=["tf32", "tf32x3", "exact"])
+    ap.add_argument("--precision", default="tf32x3b", choices=["tf32", "tf32x3", "tf32x3b", "exact"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs")
     ap.add_argument("--no-e2e", action="store_true", help="profiling only: skip the end-to-end leg (the line is then "
                                                           "not a valid bench line)")

@@ -49,7 +49,7 @@ class BaseModel(BaseEstimator, ABC):
     _parameter_constraints: ClassVar[dict[str, list[Any]]] = {
         "latent_dimensions": [Interval(Integral, 1, None, closed="left")],
         "center": ["boolean"],
-        "precision": [StrOptions({"tf32", "tf32x3", "exact"})],
+        "precision": [StrOptions({"tf32", "tf32x3", "tf32x3b", "exact"})],
         "device": [None, str, int, torch.device],
     }
 
@@ -64,7 +64,7 @@ class BaseModel(BaseEstimator, ABC):
     #: GCCA with ``center=False`` needs both: np.cov for the regularised blocks, raw products for the rest
     _wants_second_moment: ClassVar[bool] = False
 
-    def __init__(self, latent_dimensions: int = 1, center: bool = True, precision: str = "tf32x3",
+    def __init__(self, latent_dimensions: int = 1, center: bool = True, precision: str = "tf32x3b",
                  device=None) -> None:
         self.latent_dimensions = latent_dimensions
         self.center = center

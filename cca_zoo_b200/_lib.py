@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libccab200.so")
 
 F32, F64 = 0, 1
-PREC_TF32, PREC_TF32X3, PREC_EXACT = 0, 1, 2
+PREC_TF32, PREC_TF32X3, PREC_EXACT, PREC_TF32X3B = 0, 1, 2, 3
 MAX_VIEWS = 8
 
 _i64p = C.POINTER(C.c_int64)

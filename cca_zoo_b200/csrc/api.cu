@@ -90,7 +90,7 @@ int ccab_moments(int dtype, int precision, int n_views, const void* const* views
                  void* stream) {
   CCAB_TRY
   CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
-  CCAB_CHECK_ARG(precision >= 0 && precision <= 2, "bad precision %d", precision);
+  CCAB_CHECK_ARG(precision >= 0 && precision <= 3, "bad precision %d", precision);
   CCAB_CHECK_ARG(!(dtype == CCAB_F64 && precision != CCAB_PREC_EXACT),
                  "float64 inputs support CCAB_PREC_EXACT only (tcgen05 has no f64 kind)");
   CCAB_CHECK_ARG(views && dims && lds && moments && workspace, "null pointer argument");
@@ -108,7 +108,7 @@ int ccab_moments(int dtype, int precision, int n_views, const void* const* views
     if (dtype == CCAB_F32) return moments_simt<float>(L, views, lds, n_rows, moments, workspace, workspace_bytes, s);
     return moments_simt<double>(L, views, lds, n_rows, moments, workspace, workspace_bytes, s);
   }
-  return moments_tf32(L, views, lds, n_rows, precision == CCAB_PREC_TF32X3, moments, workspace, workspace_bytes, s);
+  return moments_tf32(L, views, lds, n_rows, precision, moments, workspace, workspace_bytes, s);
   CCAB_CATCH
 }
 
@@ -483,7 +483,7 @@ int ccab_ccaloss_fwd(int dtype, int precision, const void* z1, int64_t ld1, cons
                      size_t workspace_bytes, void* stream) {
   CCAB_TRY
   CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
-  CCAB_CHECK_ARG(precision >= 0 && precision <= 2, "bad precision %d", precision);
+  CCAB_CHECK_ARG(precision >= 0 && precision <= 3, "bad precision %d", precision);
   CCAB_CHECK_ARG(z1 && z2 && loss && saved && flags_dev && workspace, "null pointer argument");
   CCAB_CHECK_ARG(ld1 >= d1 && ld2 >= d2, "leading dimension too small");
   int64_t dims[2] = {d1, d2};

@@ -945,7 +945,7 @@ int ccaloss_forward(const ColumnLayout& L, int precision, const void* z1, int64_
     return ccaloss_small_forward<T>(mom, L.Dp, (double)n, d1, d2, eps, loss, saved, flags_out, s);
   }
   if (std::is_same<T, float>::value && precision != 2)
-    rc = moments_tf32(L, views, lds, n, precision == 1, mom, w + P.oMomWs, P.mom_ws_bytes, s);
+    rc = moments_tf32(L, views, lds, n, precision, mom, w + P.oMomWs, P.mom_ws_bytes, s);
   else
     rc = moments_simt<T>(L, views, lds, n, mom, w + P.oMomWs, P.mom_ws_bytes, s);
   if (rc) return rc;

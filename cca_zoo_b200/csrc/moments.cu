@@ -488,6 +488,247 @@ moments_tf32_2cta_kernel(const __grid_constant__ TcParams2 p) {
   }
 }
 
+// =============================================================================================
+// 3xTF32 with the two CROSS TERMS on the bf16 pipe ("tf32x3b"): x = hi + lo with hi = trunc_tf32(x); the leading term
+// hi*hi runs as kind::tf32 from the raw array (the hardware truncates), the cross terms lo*hi + hi*lo as kind::f16
+// MMAs on bf16 copies bhi = bf16(hi), blo = bf16(lo) (K = 16 per instruction at twice the TF32 rate: 2 instead of 3
+// units of tensor work per sample, and half the shared-memory bytes for the cross operands).  Error of one accumulator
+// run: 3e-7 relative (3xTF32: 1.3e-7, single pass: 7.5e-4; tools/next/emulate_x3_bf16_cross.py) -- still fp32 grade.
+// bf16 MN-major operands: 64-column TMA boxes (SWIZZLE_128B), descriptor layout SWIZZLE_128B, LBO = KC*128 between
+// 64-column atoms, SBO = 1024 between 8-row groups, 2048 B per K = 16 step (probed on hardware:
+// tools/next/umma_bf16_mn_probe.cu, profiles/r2_bf16_mn_probe.txt).
+// =============================================================================================
+struct alignas(64) TcParams3 {
+  CUtensorMap maps[3 * kMaxViews];   // [v] raw fp32, [8+v] bhi (bf16), [16+v] blo (bf16)
+  float* partial;
+  float* partial_sum;
+  int total_chunks, chunks_per_split, num_splits;
+  int nblocks, nb2, Dp2;
+  int blk_col0[kMaxBlocks + 2];
+  uint8_t blk_view[kMaxBlocks + 2];
+};
+static_assert(sizeof(TcParams3) <= 4096, "kernel parameter space");
+
+template <int NS>
+struct Tc3Cfg {
+  static constexpr int KC = 16;
+  static constexpr int kAtom = KC * 128;        // 32 fp32 columns x 16 rows  ==  64 bf16 columns x 16 rows
+  static constexpr int kRaw = 8 * kAtom;        // A (4 atoms) + B half (4 atoms), fp32
+  static constexpr int kBf = 2 * kAtom;         // one bf16 operand of 128 columns
+  static constexpr int kStage = kRaw + 4 * kBf; // + A.bhi, A.blo, B.bhi, B.blo
+  static constexpr int kSmem = NS * kStage + 3072 + 1024 + 256;
+};
+
+template <int NS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+moments_x3b_2cta_kernel(const __grid_constant__ TcParams3 p) {
+  using Cfg = Tc3Cfg<NS>;
+  constexpr int KC = Cfg::KC;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ones = smem + NS * Cfg::kStage;          // 1024 B of 1.0f, then 2048 B of bf16 1.0 (two 8-row groups)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ones + 3072);
+  uint64_t* empty_bar = full_bar + NS;
+  uint64_t* tmem_full_bar = empty_bar + NS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  int t = blockIdx.x >> 1, I = 0, rowlen = p.nb2;
+  while (t >= rowlen) { t -= rowlen; ++I; --rowlen; }
+  const int J = I + t;
+  const bool do_sum = (I == J);
+  const int blkA = min(2 * I + (int)rank, p.nblocks);
+  const int blkB = min(2 * J + (int)rank, p.nblocks);
+  const int split = blockIdx.y;
+  const int c0 = split * p.chunks_per_split;
+  const int c1 = min(c0 + p.chunks_per_split, p.total_chunks);
+  const bool has_work = c1 > c0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int v = 0; v < 3 * kMaxViews; ++v) tma_prefetch_desc(&p.maps[v]);
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
+  if (warp >= 2) {
+    float* o = reinterpret_cast<float*>(ones);
+    uint32_t* ob = reinterpret_cast<uint32_t*>(ones + 1024);
+    for (int i = threadIdx.x - 64; i < 512; i += 128) {
+      if (i < 256) o[i] = 1.0f;
+      ob[i] = 0x3F803F80u;   // two bf16 ones
+    }
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs, each loads its own halves) =================
+    if (has_work && elect_one()) {
+      const int vA = p.blk_view[blkA], colA = p.blk_col0[blkA];
+      const int vB = p.blk_view[blkB], colB = p.blk_col0[blkB];
+      const uint32_t bytes_pair = 2u * Cfg::kStage;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = c0; c < c1; ++c) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], bytes_pair);
+        uint8_t* st = smem + stage * Cfg::kStage;
+        const int row = c * KC;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) tma_load_2d_2sm(st + a * Cfg::kAtom, &p.maps[vA], &full_bar[stage], colA + 32 * a, row);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          tma_load_2d_2sm(st + (4 + a) * Cfg::kAtom, &p.maps[vB], &full_bar[stage], colB + 32 * a, row);
+        uint8_t* bf = st + Cfg::kRaw;
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {      // 0: bhi, 1: blo
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            tma_load_2d_2sm(bf + (o * 2 + a) * Cfg::kAtom, &p.maps[(1 + o) * kMaxViews + vA], &full_bar[stage],
+                            colA + 64 * a, row);
+            tma_load_2d_2sm(bf + (4 + o * 2 + a) * Cfg::kAtom, &p.maps[(1 + o) * kMaxViews + vB], &full_bar[stage],
+                            colB + 64 * a, row);
+          }
+        }
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: one thread of the LEADER CTA drives both SMs =================
+    if (leader && has_work) {
+      const uint32_t idesc_tf = umma_idesc_tf32_mn(256, 256), idesc_tf_sum = umma_idesc_tf32_mn(256, 16);
+      const uint32_t idesc_bf = umma_idesc_bf16_mn(256, 256), idesc_bf_sum = umma_idesc_bf16_mn(256, 16);
+      const uint32_t sb = smem_u32(smem);
+      const uint64_t ones_tf = umma_smem_desc(smem_u32(ones), KC * 128, 512, kUmmaLayout);
+      const uint64_t ones_bf = umma_smem_desc(smem_u32(ones) + 1024, KC * 128, 1024, 2);
+      const uint64_t dA_tf = umma_smem_desc(sb, KC * 128, 512, kUmmaLayout);
+      const uint64_t dB_tf = umma_smem_desc(sb + 4 * Cfg::kAtom, KC * 128, 512, kUmmaLayout);
+      const uint64_t dA_bhi = umma_smem_desc(sb + Cfg::kRaw, KC * 128, 1024, 2);
+      const uint64_t dA_blo = umma_smem_desc(sb + Cfg::kRaw + Cfg::kBf, KC * 128, 1024, 2);
+      const uint64_t dB_bhi = umma_smem_desc(sb + Cfg::kRaw + 2 * Cfg::kBf, KC * 128, 1024, 2);
+      const uint64_t dB_blo = umma_smem_desc(sb + Cfg::kRaw + 3 * Cfg::kBf, KC * 128, 1024, 2);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t acc = 0u;
+      for (int c = c0; c < c1; ++c) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t so = (uint64_t)((stage * Cfg::kStage) >> 4);
+          // small cross terms first (one K = 16 bf16 MMA each), then the leading term (two K = 8 tf32 MMAs)
+          umma_f16_2sm(tmem_base, dA_blo + so, dB_bhi + so, idesc_bf, acc);
+          umma_f16_2sm(tmem_base, dA_bhi + so, dB_blo + so, idesc_bf, 1u);
+          umma_tf32_2sm(tmem_base, dA_tf + so, dB_tf + so, idesc_tf, 1u);
+          umma_tf32_2sm(tmem_base, dA_tf + so + 64, dB_tf + so + 64, idesc_tf, 1u);
+          if (do_sum) {
+            umma_f16_2sm(tmem_base + kSumCol, dA_blo + so, ones_bf, idesc_bf_sum, acc);
+            umma_tf32_2sm(tmem_base + kSumCol, dA_tf + so, ones_tf, idesc_tf_sum, 1u);
+            umma_tf32_2sm(tmem_base + kSumCol, dA_tf + so + 64, ones_tf, idesc_tf_sum, 1u);
+          }
+          umma_commit_2sm(&empty_bar[stage], 3);
+        }
+        acc = 1u;
+        __syncwarp();
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit_2sm(tmem_full_bar, 3);
+      __syncwarp();
+    }
+  } else {
+    // ================= epilogue (both CTAs): own 128 accumulator rows x 256 columns =================
+    const int g = warp & 3;
+    const int m = g * 32 + lane;
+    const size_t prow_idx = (size_t)(2 * I + rank) * 128 + m;
+    float* prow = p.partial + ((size_t)split * p.Dp2 + prow_idx) * p.Dp2;
+    if (has_work) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    for (int cc = 0; cc < 8; ++cc) {
+      uint32_t r[32];
+      if (has_work) {
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + cc * 32, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = 0u;
+      }
+      float4* dst = reinterpret_cast<float4*>(prow + (size_t)(2 * J + (cc >> 2)) * 128 + (cc & 3) * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                             __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+    }
+    if (do_sum) {
+      uint32_t sv = 0u;
+      if (has_work) {
+        sv = tmem_ld_32x32b_x1(tmem_base + ((uint32_t)(g * 32) << 16) + kSumCol);
+        tmem_ld_wait();
+      }
+      p.partial_sum[(size_t)split * p.Dp2 + prow_idx] = __uint_as_float(sv);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+// pre-pass of the tf32x3b mode: bhi = bf16(trunc_tf32(x)), blo = bf16(x - trunc_tf32(x)); reads n*d*4 B, writes n*d*4 B
+__device__ __forceinline__ uint32_t bf16_rn_bits(float v) {
+  uint32_t u = __float_as_uint(v);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return u >> 16;
+}
+__global__ void tf32_bf16_split_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx,
+                                       uint16_t* __restrict__ bhi, uint16_t* __restrict__ blo, int64_t ldo, int vec4) {
+  if (vec4) {
+    const int d4 = d >> 2;
+    const int64_t total = n * (int64_t)d4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = i / d4;
+      const int c = (int)(i - r * d4) << 2;
+      const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float hi = __uint_as_float(__float_as_uint(vv[q]) & 0xFFFFE000u);
+        h[q] = bf16_rn_bits(hi);
+        l[q] = bf16_rn_bits(vv[q] - hi);
+      }
+      *reinterpret_cast<uint2*>(bhi + r * ldo + c) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+      *reinterpret_cast<uint2*>(blo + r * ldo + c) = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
+    }
+  } else {
+    const int64_t total = n * (int64_t)d;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = i / d;
+      const int c = (int)(i - r * d);
+      const float v = x[r * ldx + c];
+      const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+      bhi[r * ldo + c] = (uint16_t)bf16_rn_bits(hi);
+      blo[r * ldo + c] = (uint16_t)bf16_rn_bits(v - hi);
+    }
+  }
+}
+
 // 3xTF32 operand split.  The tensor core TRUNCATES its fp32 operands to TF32 (measured: tools/probe_trunc.py),
 // so the raw array itself serves as the "hi" operand (hi = x with the low 13 mantissa bits cleared) and only
 // the residual lo = rna_tf32(x - hi) is materialised (exact subtraction, then 11 significant bits: the
@@ -823,6 +1064,27 @@ int encode_view_map(CUtensorMap* map, const void* ptr, int64_t n_rows, int64_t d
   return 0;
 }
 
+int encode_bf16_map(CUtensorMap* map, const void* ptr, int64_t n_rows, int64_t d, int64_t ld, int kc) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
+    return -2;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)n_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)kc};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (bf16) failed with CUresult %d (d=%lld n=%lld ld=%lld)", (int)r, (long long)d,
+              (long long)n_rows, (long long)ld);
+    return -3;
+  }
+  return 0;
+}
+
 int sm_count() {
   static int n = 0;
   if (!n) {
@@ -840,12 +1102,13 @@ struct TcPlan {
   size_t partial_bytes, sum_bytes, split_bytes;  // split_bytes: hi/lo operand copies (3xTF32)
 };
 
-TcPlan plan_tc(const ColumnLayout& L, int64_t n_rows, bool x3) {
+TcPlan plan_tc(const ColumnLayout& L, int64_t n_rows, int mode) {
+  const bool x3 = mode != 0;   // 0: one TF32 pass, 1: 3xTF32, 3: 3xTF32 with bf16 cross terms
   TcPlan P;
   P.kc = x3 ? 16 : 32;
   if (!x3 && tc_debug().variant != 1 && (tc_debug().kc == 16 || tc_debug().kc == 64)) P.kc = tc_debug().kc;
   P.total_chunks = (int)ceil_div(n_rows, P.kc);
-  P.two_cta = tc_debug().variant != 1;
+  P.two_cta = tc_debug().variant != 1 || mode == 3;
   P.nb2 = (L.nblocks + 1) / 2;
   int nt = 0;
   if (P.two_cta) {
@@ -883,10 +1146,16 @@ TcPlan plan_tc(const ColumnLayout& L, int64_t n_rows, bool x3) {
   P.partial_bytes = (size_t)P.num_splits * P.ldp * P.ldp * sizeof(float);
   P.sum_bytes = (size_t)P.num_splits * P.ldp * sizeof(float);
   P.split_bytes = 0;
-  if (x3) {
+  if (mode == 3) {
+    for (int v = 0; v < L.n_views; ++v) {
+      int64_t ldo = ceil_div(L.dims[v], 8) * 8;
+      P.split_bytes += 2 * (size_t)n_rows * ldo * sizeof(uint16_t) + 512;   // bhi + blo
+    }
+  } else if (x3) {
     for (int v = 0; v < L.n_views; ++v) {
       int64_t ldo = ceil_div(L.dims[v], 4) * 4;
-      P.split_bytes += 2 * (size_t)n_rows * ldo * sizeof(float);   // lo (and hi for the round-to-nearest split)
+      // lo only; hi as well for the round-to-nearest split (debug)
+      P.split_bytes += (tc_debug().x3_split == 1 ? 2 : 1) * (size_t)n_rows * ldo * sizeof(float);
     }
   }
   return P;
@@ -920,19 +1189,20 @@ size_t moments_workspace_bytes(int dtype, int precision, const ColumnLayout& L, 
     size_t el = dtype == 1 ? 8 : 4;
     return align256((size_t)P.num_splits * L.Dp * L.Dp * el) + align256((size_t)P.num_splits * L.Dp * el);
   }
-  TcPlan P = plan_tc(L, n_rows, precision == 1);
+  TcPlan P = plan_tc(L, n_rows, precision);
   return align256(P.partial_bytes) + align256(P.sum_bytes) + align256(P.split_bytes) + 256;
 }
 
-int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t* lds, int64_t n_rows, bool x3,
+int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t* lds, int64_t n_rows, int mode,
                  double* moments_out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  const bool x3 = mode == 1;
   CCAB_CHECK_ARG(n_rows >= 1 && n_rows < (int64_t)1 << 31, "n_rows out of range");
   {
     int dev = 0;   // bind the primary context to this thread before the driver-API tensor-map encoder (see tgemm.cu)
     CCAB_CUDA(cudaGetDevice(&dev));
     CCAB_CUDA(cudaSetDevice(dev));
   }
-  TcPlan P = plan_tc(L, n_rows, x3);
+  TcPlan P = plan_tc(L, n_rows, mode);
   const size_t need = align256(P.partial_bytes) + align256(P.sum_bytes) + align256(P.split_bytes) + 256;
   CCAB_CHECK_ARG(ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
   uint8_t* w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
@@ -940,6 +1210,77 @@ int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t*
   float* d_partial = reinterpret_cast<float*>(w);
   float* d_partial_sum = reinterpret_cast<float*>(w + align256(P.partial_bytes));
   uint8_t* splitbuf = w + align256(P.partial_bytes) + align256(P.sum_bytes);
+
+  if (mode == 3) {
+    // ---- 3xTF32 with bf16 cross terms: raw view (tf32 hi by truncation) + bf16 copies of hi and lo ----
+    TcParams3 prm;
+    memset(&prm, 0, sizeof(prm));
+    for (int v = 0; v < L.n_views; ++v) {
+      const float* x = static_cast<const float*>(views[v]);
+      const int64_t ldo = ceil_div(L.dims[v], 8) * 8;
+      uint16_t* bhi = reinterpret_cast<uint16_t*>(splitbuf);
+      uint16_t* blo = bhi + (size_t)n_rows * ldo;
+      splitbuf += align256(2 * (size_t)n_rows * ldo * sizeof(uint16_t));
+      const int vec4 = (L.dims[v] % 4 == 0) && (lds[v] % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+      const int64_t total = n_rows * (int64_t)L.dims[v] / (vec4 ? 4 : 1);
+      int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
+      tf32_bf16_split_kernel<<<blocks, 256, 0, stream>>>(x, n_rows, L.dims[v], lds[v], bhi, blo, ldo, vec4);
+      count_launches(1);
+      CCAB_CUDA(cudaGetLastError());
+      int rc = encode_view_map(&prm.maps[v], x, n_rows, L.dims[v], lds[v], P.kc);
+      if (rc) return rc;
+      rc = encode_bf16_map(&prm.maps[kMaxViews + v], bhi, n_rows, L.dims[v], ldo, P.kc);
+      if (rc) return rc;
+      rc = encode_bf16_map(&prm.maps[2 * kMaxViews + v], blo, n_rows, L.dims[v], ldo, P.kc);
+      if (rc) return rc;
+    }
+    for (int v = L.n_views; v < kMaxViews; ++v) {
+      prm.maps[v] = prm.maps[0];
+      prm.maps[kMaxViews + v] = prm.maps[kMaxViews];
+      prm.maps[2 * kMaxViews + v] = prm.maps[2 * kMaxViews];
+    }
+    prm.partial = d_partial;
+    prm.partial_sum = d_partial_sum;
+    prm.total_chunks = P.total_chunks;
+    prm.chunks_per_split = P.chunks_per_split;
+    prm.num_splits = P.num_splits;
+    prm.nblocks = L.nblocks;
+    prm.nb2 = P.nb2;
+    prm.Dp2 = P.ldp;
+    int b = 0;
+    for (int v = 0; v < L.n_views; ++v)
+      for (int c = 0; c < L.dims[v]; c += kBlk, ++b) {
+        prm.blk_view[b] = (uint8_t)v;
+        prm.blk_col0[b] = c;
+      }
+    for (; b < kMaxBlocks + 2; ++b) {
+      prm.blk_view[b] = 0;
+      prm.blk_col0[b] = 1 << 30;
+    }
+    using Cfg = Tc3Cfg<6>;
+    static bool attr_done[64] = {};
+    int dev = 0;
+    CCAB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+      CCAB_CUDA(cudaFuncSetAttribute(moments_x3b_2cta_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+      if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    if (g_prof_on) cudaEventRecord(g_prof_e0, stream);
+    moments_x3b_2cta_kernel<6><<<dim3(2 * P.ntiles, P.num_splits), kTcThreads, Cfg::kSmem, stream>>>(prm);
+    count_launches(1);
+    CCAB_CUDA(cudaGetLastError());
+    if (g_prof_on) {
+      cudaEventRecord(g_prof_e1, stream);
+      g_prof_valid = true;
+    }
+    const size_t total = (size_t)L.Dp * L.Dp + L.Dp;
+    int rblocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
+    reduce_partials_kernel<float><<<rblocks, 256, 0, stream>>>(d_partial, d_partial_sum, P.num_splits, L.Dp, P.ldp, kBlk,
+                                                              moments_out);
+    count_launches(1);
+    CCAB_CUDA(cudaGetLastError());
+    return 0;
+  }
 
   // operands (raw, or hi/lo copies for 3xTF32) and their tensor maps
   CUtensorMap maps[2 * kMaxViews];

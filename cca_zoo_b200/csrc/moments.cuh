@@ -24,11 +24,12 @@ struct ColumnLayout {
 int make_layout(int n_views, const int64_t* dims, ColumnLayout* out);
 
 // --- launchers (all asynchronous on `stream`) -------------------------------------------------
-// precision: 0 = TF32 single pass (tcgen05), 1 = 3xTF32 split (tcgen05), 2 = exact SIMT FMA.
+// precision: 0 = TF32 single pass (tcgen05), 1 = 3xTF32 split (tcgen05), 2 = exact SIMT FMA,
+//            3 = 3xTF32 with the two cross terms as bf16 MMAs (tcgen05 kind::f16).
 size_t moments_workspace_bytes(int dtype, int precision, const ColumnLayout& L, int64_t n_rows);
 
 int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t* lds, int64_t n_rows,
-                 bool x3, double* moments_out, void* ws, size_t ws_bytes, cudaStream_t stream);
+                 int mode /* 0, 1 or 3 */, double* moments_out, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 template <typename T>
 int moments_simt(const ColumnLayout& L, const void* const* views, const int64_t* lds, int64_t n_rows,

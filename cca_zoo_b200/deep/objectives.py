@@ -40,7 +40,7 @@ def _resolve_precision(precision, zs):
     if zs[0].dtype == torch.float64:
         return "exact"
     if precision == "auto":
-        precision = "tf32x3" if sum(z.shape[1] for z in zs) > 256 else "exact"
+        precision = "tf32x3b" if sum(z.shape[1] for z in zs) > 256 else "exact"
     if precision != "exact" and not all(z.data_ptr() % 16 == 0 and z.stride(0) % 4 == 0 for z in zs):
         return "exact"
     return precision

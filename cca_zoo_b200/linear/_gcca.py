@@ -33,7 +33,7 @@ class GCCA(BaseModel):
     }
 
     def __init__(self, latent_dimensions: int = 1, center: bool = True, c=0.0, view_weights=None,
-                 eps: float = 1e-6, precision: str = "tf32x3", device=None, solver: str = "auto") -> None:
+                 eps: float = 1e-6, precision: str = "tf32x3b", device=None, solver: str = "auto") -> None:
         super().__init__(latent_dimensions=latent_dimensions, center=center, precision=precision, device=device)
         self.c = c
         self.view_weights = view_weights

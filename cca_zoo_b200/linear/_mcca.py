@@ -40,7 +40,7 @@ class MCCA(BaseModel):
     }
 
     def __init__(self, latent_dimensions: int = 1, center: bool = True, c=0.0, pca: bool = True,
-                 eps: float = 1e-6, precision: str = "tf32x3", device=None, solver: str = "auto") -> None:
+                 eps: float = 1e-6, precision: str = "tf32x3b", device=None, solver: str = "auto") -> None:
         super().__init__(latent_dimensions=latent_dimensions, center=center, precision=precision, device=device)
         self.c = c
         self.pca = pca

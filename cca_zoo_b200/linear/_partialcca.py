@@ -48,7 +48,7 @@ class PartialCCA(MCCA):
     """
 
     def __init__(self, latent_dimensions: int = 1, center: bool = True, c=0.0, eps: float = 1e-6,
-                 precision: str = "tf32x3", device=None, solver: str = "auto") -> None:
+                 precision: str = "tf32x3b", device=None, solver: str = "auto") -> None:
         super().__init__(latent_dimensions=latent_dimensions, center=center, c=c, pca=False, eps=eps,
                          precision=precision, device=device, solver=solver)
 

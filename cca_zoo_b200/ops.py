@@ -54,11 +54,11 @@ def _row_major(t: torch.Tensor, tma: bool) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------
 # K1 / K2
 # --------------------------------------------------------------------------------------------------
-def moments(views, precision: str = "tf32x3") -> torch.Tensor:
+def moments(views, precision: str = "tf32x3b") -> torch.Tensor:
     """Block moments of the row shard held in ``views`` (list of (n, d_i) CUDA tensors, same dtype).
 
     Returns the additive double buffer ``[Dp*Dp + Dp]`` (see ccab_moments in include/ccab200.h).
-    precision: "tf32" | "tf32x3" | "exact" (float64 views always use "exact").
+    precision: "tf32" | "tf32x3" | "tf32x3b" (3xTF32 with bf16 cross terms) | "exact" (float64 views always use "exact").
     """
     lib = _lib.load()
     if not (1 <= len(views) <= _lib.MAX_VIEWS):
@@ -72,7 +72,8 @@ def moments(views, precision: str = "tf32x3") -> torch.Tensor:
             raise ValueError("All views must have the same number of samples.")
         if v.device != views[0].device:
             raise ValueError(f"views live on different devices: {v.device} vs {views[0].device}")
-    prec = {"tf32": _lib.PREC_TF32, "tf32x3": _lib.PREC_TF32X3, "exact": _lib.PREC_EXACT}[precision]
+    prec = {"tf32": _lib.PREC_TF32, "tf32x3": _lib.PREC_TF32X3, "exact": _lib.PREC_EXACT,
+            "tf32x3b": _lib.PREC_TF32X3B}[precision]
     if dt == torch.float64:
         prec = _lib.PREC_EXACT
     vs = [_row_major(v, tma=prec != _lib.PREC_EXACT) for v in views]
@@ -365,7 +366,8 @@ def ccaloss_fwd(z1, z2, eps, precision="exact"):
     _require_cuda(z2, "z2")
     n, d1, d2 = z1.shape[0], z1.shape[1], z2.shape[1]
     dt = _DT[z1.dtype]
-    prec = {"tf32": _lib.PREC_TF32, "tf32x3": _lib.PREC_TF32X3, "exact": _lib.PREC_EXACT}[precision]
+    prec = {"tf32": _lib.PREC_TF32, "tf32x3": _lib.PREC_TF32X3, "exact": _lib.PREC_EXACT,
+            "tf32x3b": _lib.PREC_TF32X3B}[precision]
     if z1.dtype == torch.float64:
         prec = _lib.PREC_EXACT
     loss = torch.empty(1, dtype=z1.dtype, device=z1.device)

@@ -32,6 +32,7 @@ def _ref_cov(views, center=True):
     ("exact", torch.float64, 1e-12),
     ("exact", torch.float32, 2e-5),
     ("tf32x3", torch.float32, 2e-5),
+    ("tf32x3b", torch.float32, 2e-5),     # 3xTF32 with the two cross terms as bf16 MMAs
     ("tf32", torch.float32, 3e-3),
 ])
 @pytest.mark.parametrize("n,dims", [
