@@ -143,6 +143,21 @@ int ccab_moments_unpack(int n_views, const int64_t* dims, const double* packed, 
   CCAB_CATCH
 }
 
+int ccab_moments_exchange_nvls(int n_views, const int64_t* dims, double* moments, double n_local, double* sym_local,
+                               double* sym_multicast, void* const* signal_pads_dev, int rank, int world,
+                               int pad_slots, int64_t sym_doubles, unsigned epoch, double* n_total_out, void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dims && moments, "null pointer argument");
+  ColumnLayout L;
+  int rc = make_layout(n_views, dims, &L);
+  if (rc) return rc;
+  rc = require_device();
+  if (rc) return rc;
+  return moments_exchange_nvls(L, moments, n_local, sym_local, sym_multicast, signal_pads_dev, rank, world, pad_slots,
+                               sym_doubles, epoch, n_total_out, static_cast<cudaStream_t>(stream));
+  CCAB_CATCH
+}
+
 int ccab_covariance(int out_dtype, int n_views, const int64_t* dims, const double* moments, double n_total,
                     int center, void* C, int64_t ldc, void* mean, void* stream) {
   CCAB_TRY

@@ -1523,6 +1523,144 @@ __global__ void unpack_moments_kernel(const double* __restrict__ packed, int nbl
   }
 }
 
+// =============================================================================================
+// Fused exchange step over NVLink / NVSwitch (SURVEY.md §8e "v2"): ONE kernel packs the upper block triangle of the
+// local moments into a symmetric-memory buffer, meets the other ranks on per-CTA flags in their signal pads, reduces
+// its slice of the message INSIDE THE SWITCH (multimem.ld_reduce on the multicast address: one load returns the sum
+// over all ranks), broadcasts the sums with multimem.st, meets the ranks again and scatters the totals back into the
+// moment buffer.  No NCCL call, no intermediate launch; every element is reduced exactly once, so all ranks receive
+// bit-identical totals.  CTA c of every rank owns the same column of regions {(owner rho, c)}: it needs no grid-wide
+// synchronisation, only its own flag row.  The buffers / flags come from torch's symmetric memory (parallel.py).
+// =============================================================================================
+__device__ __forceinline__ double multimem_ld_reduce_add_f64(const double* mc_addr) {
+  double v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(v) : "l"(mc_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_f64(double* mc_addr, double v) {
+  asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc_addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+struct ExchangeParams {
+  double* mom;            // local moment buffer [Dp*Dp + Dp]
+  double* sym;            // this rank's symmetric buffer (local address), >= world * chunk doubles
+  double* mc;             // multicast address of the same buffer
+  uint32_t* const* pads;  // device array [world]: signal pad of every rank (peer-mapped)
+  double* n_total_out;    // device scalar (may be NULL)
+  double n_local;
+  long long packed;       // doubles in the message (upper blocks | column sums | n | reserved)
+  long long chunk;        // doubles per owner rank (world * chunk >= packed)
+  int rank, world, nblocks, Dp;
+  unsigned epoch;         // 2 flag values per call: epoch, epoch + 1 (monotonic; compared with >=)
+};
+
+__device__ __forceinline__ const double* packed_src(const ExchangeParams& p, long long e, int nt) {
+  // element e of the message -> its home in the moment buffer
+  const long long blk = e / (kBlk * kBlk);
+  if (blk < nt) {
+    int bi = 0, rem = (int)blk, rowlen = p.nblocks;
+    while (rem >= rowlen) { rem -= rowlen; ++bi; --rowlen; }
+    const int bj = bi + rem;
+    const int off = (int)(e - blk * (kBlk * kBlk));
+    return p.mom + ((size_t)bi * kBlk + off / kBlk) * p.Dp + (size_t)bj * kBlk + (off % kBlk);
+  }
+  const long long t = e - (long long)nt * kBlk * kBlk;
+  return t < p.Dp ? p.mom + (size_t)p.Dp * p.Dp + t : nullptr;   // tail: n, reserved
+}
+
+__device__ __forceinline__ void exchange_barrier(const ExchangeParams& p, unsigned value) {
+  // all threads of the CTA have finished their writes to symmetric / peer memory
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < p.world)
+    st_release_sys_u32(p.pads[threadIdx.x] + (size_t)blockIdx.x * p.world + p.rank, value);
+  if ((int)threadIdx.x < p.world) {
+    const uint32_t* slot = p.pads[p.rank] + (size_t)blockIdx.x * p.world + threadIdx.x;
+    unsigned spins = 0;
+    while ((int)(ld_acquire_sys_u32(slot) - value) < 0) {
+      if (++spins > (1u << 26)) {   // ~ seconds: a lost peer must not hang the box
+        printf("ccab: exchange barrier timed out (rank %d cta %d peer %d)\n", p.rank, blockIdx.x, threadIdx.x);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(512) exchange_nvls_kernel(const ExchangeParams p) {
+  const int nt = p.nblocks * (p.nblocks + 1) / 2;
+  const long long sub = (p.chunk + gridDim.x - 1) / gridDim.x;   // doubles per (owner, CTA) region
+  const long long r0 = (long long)blockIdx.x * sub;
+  const long long r1 = r0 + sub < p.chunk ? r0 + sub : p.chunk;
+  // ---- pack this CTA's column of regions ----
+  for (int rho = 0; rho < p.world; ++rho) {
+    const long long base = (long long)rho * p.chunk;
+    for (long long i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+      const long long e = base + i;
+      double v = 0.0;
+      if (e < p.packed) {
+        const double* src = packed_src(p, e, nt);
+        v = src ? *src : (e == (long long)nt * kBlk * kBlk + p.Dp ? p.n_local : 0.0);
+      }
+      p.sym[e] = v;
+    }
+  }
+  exchange_barrier(p, p.epoch);
+  // ---- reduce the own region in the switch and broadcast it ----
+  {
+    const long long base = (long long)p.rank * p.chunk;
+    for (long long i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+      const double v = multimem_ld_reduce_add_f64(p.mc + base + i);
+      multimem_st_f64(p.mc + base + i, v);
+    }
+  }
+  exchange_barrier(p, p.epoch + 1);
+  // ---- scatter the totals back ----
+  for (int rho = 0; rho < p.world; ++rho) {
+    const long long base = (long long)rho * p.chunk;
+    for (long long i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+      const long long e = base + i;
+      if (e >= p.packed) continue;
+      const double v = p.sym[e];
+      const double* dst = packed_src(p, e, nt);
+      if (dst) *const_cast<double*>(dst) = v;
+      else if (e == (long long)nt * kBlk * kBlk + p.Dp && p.n_total_out) *p.n_total_out = v;
+    }
+  }
+}
+
+int moments_exchange_nvls(const ColumnLayout& L, double* mom, double n_local, double* sym_local, double* sym_multicast,
+                          void* const* pads_dev, int rank, int world, int pad_slots, int64_t sym_doubles,
+                          unsigned epoch, double* n_total_out, cudaStream_t stream) {
+  CCAB_CHECK_ARG(world >= 2 && world <= 64 && rank >= 0 && rank < world, "bad rank / world %d / %d", rank, world);
+  CCAB_CHECK_ARG(mom && sym_local && sym_multicast && pads_dev, "null pointer argument");
+  ExchangeParams p;
+  memset(&p, 0, sizeof(p));
+  p.mom = mom; p.sym = sym_local; p.mc = sym_multicast;
+  p.pads = reinterpret_cast<uint32_t* const*>(pads_dev);
+  p.n_total_out = n_total_out; p.n_local = n_local;
+  p.packed = moments_packed_size(L);
+  p.chunk = ceil_div(ceil_div(p.packed, world), 2) * 2;
+  CCAB_CHECK_ARG(sym_doubles >= p.chunk * world, "symmetric buffer too small: %lld < %lld doubles", (long long)sym_doubles,
+                 (long long)(p.chunk * world));
+  p.rank = rank; p.world = world; p.nblocks = L.nblocks; p.Dp = L.Dp; p.epoch = epoch;
+  int grid = std::min(64, pad_slots / world);
+  CCAB_CHECK_ARG(grid >= 1, "signal pad too small for %d ranks", world);
+  grid = (int)std::min<int64_t>(grid, std::max<int64_t>(1, p.chunk / 512));
+  exchange_nvls_kernel<<<grid, 512, 0, stream>>>(p);
+  count_launches(1);
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int64_t moments_packed_size(const ColumnLayout& L) {
   const int64_t nt = (int64_t)L.nblocks * (L.nblocks + 1) / 2;
   return nt * kBlk * kBlk + L.Dp + 2;

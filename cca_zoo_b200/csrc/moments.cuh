@@ -45,6 +45,14 @@ int64_t moments_packed_size(const ColumnLayout& L);
 int moments_pack(const ColumnLayout& L, const double* moments, double n_local, double* packed, cudaStream_t stream);
 int moments_unpack(const ColumnLayout& L, const double* packed, double* moments, cudaStream_t stream);
 
+// Fused exchange step on symmetric memory (pack + in-switch reduction with multimem + unpack in ONE kernel).
+// sym_local / sym_multicast: local and multicast address of a symmetric buffer of sym_doubles doubles
+// (>= world * ceil(packed / world)); pads_dev: device array of the world signal-pad pointers (uint32, pad_slots
+// entries each, zero-initialised once); epoch: 2 x the call counter, identical on all ranks, strictly increasing.
+int moments_exchange_nvls(const ColumnLayout& L, double* moments, double n_local, double* sym_local,
+                          double* sym_multicast, void* const* pads_dev, int rank, int world, int pad_slots,
+                          int64_t sym_doubles, unsigned epoch, double* n_total_out, cudaStream_t stream);
+
 // debug knobs for the tcgen05 kernel (descriptor strides / TMA data type), see tools/umma_probe.py
 struct TcDebug {
   int lbo_bytes;    // <0: default

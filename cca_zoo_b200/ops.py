@@ -122,6 +122,22 @@ def moments_unpack(packed: torch.Tensor, dims, out=None):
     return mom, packed[-2:-1]
 
 
+def moments_exchange_nvls(mom: torch.Tensor, dims, n_local, sym: torch.Tensor, multicast_ptr: int, pads_dev_ptr: int,
+                          rank: int, world: int, pad_slots: int, epoch: int):
+    """Fused exchange step (ccab_moments_exchange_nvls): pack, in-switch all-reduce on the multicast address, unpack --
+    one kernel, in place on ``mom``.  Returns the summed sample count as a 1-element device tensor."""
+    lib = _lib.load()
+    _require_cuda(mom, "moments")
+    d = _lib.i64_array(dims)
+    n_dev = torch.empty(1, dtype=torch.float64, device=mom.device)
+    with torch.cuda.device(mom.device):
+        rc = lib.ccab_moments_exchange_nvls(len(dims), d, _ptr(mom), float(n_local), _ptr(sym), C.c_void_p(multicast_ptr),
+                                            C.c_void_p(pads_dev_ptr), int(rank), int(world), int(pad_slots),
+                                            sym.numel(), int(epoch) & 0xFFFFFFFF, _ptr(n_dev), _stream(mom))
+    _lib.check(rc, "ccab_moments_exchange_nvls")
+    return n_dev
+
+
 def covariance(mom: torch.Tensor, dims, n_total: float, center: bool = True, dtype=torch.float64):
     """(C [D,D], mean [D]) from an (all-reduced) moments buffer."""
     lib = _lib.load()

@@ -71,6 +71,19 @@ int ccab_moments_pack(int n_views, const int64_t* dims, const double* moments, d
                       void* stream);
 int ccab_moments_unpack(int n_views, const int64_t* dims, const double* packed, double* moments, void* stream);
 
+/* Fused exchange step over NVLink / NVSwitch: pack -> in-switch all-reduce -> unpack in ONE kernel, no NCCL call.
+ * Needs a symmetric-memory buffer of `sym_doubles` float64 (>= world * ceil(ccab_moments_packed_size / world),
+ * rounded up to even) mapped on every rank with a multicast (NVLS) address, and the ranks' signal pads (uint32 flags,
+ * `pad_slots` entries each, zeroed once) -- torch.distributed._symmetric_memory provides both (cca_zoo_b200/parallel.py).
+ * Each CTA packs its column of the message, meets the peers on its own flag row (st.release.sys / ld.acquire.sys),
+ * reduces this rank's slice with multimem.ld_reduce.add.f64 (the switch adds the ranks' copies), broadcasts it with
+ * multimem.st, meets the peers again and scatters the totals into `moments`; n_total_out (device, may be NULL)
+ * receives the summed sample count.  `epoch` must be the same on every rank and grow by 2 per call.
+ * The result is bit-identical on all ranks (every element is reduced once, in the switch). */
+int ccab_moments_exchange_nvls(int n_views, const int64_t* dims, double* moments, double n_local, double* sym_local,
+                               double* sym_multicast, void* const* signal_pads_dev, int rank, int world,
+                               int pad_slots, int64_t sym_doubles, unsigned epoch, double* n_total_out, void* stream);
+
 /* ---- K2: covariance from (all-reduced) moments ---------------------------------------------------
  * C = (M - s s^T / n_total) / (n_total - 1) (center != 0) or M / (n_total - 1), compact D x D
  * (D = sum dims, hstack order), full symmetric, in out_dtype; mean = s / n_total (or 0).

@@ -47,6 +47,14 @@ def _worker(rank, world, port, out_dir):
         dev = rCCA(latent_dimensions=4, c=0.1).fit([torch.from_numpy(v[lo:hi]).cuda() for v in wide])
         assert dev._fit_info["route"] == "device" and dev.n_samples_ == 5003
         np.save(os.path.join(out_dir, f"wide_w1_rank{rank}.npy"), dev.weights_[1])
+        # which exchange ran?  (fused NVLS kernel on symmetric memory when the box offers multicast, NCCL otherwise)
+        used_nvls = any(v is not None for v in parallel._NvlsExchange._cache.values())
+        os.environ["CCAB_EXCHANGE"] = "nccl"
+        ref = rCCA(latent_dimensions=4, c=0.1).fit([torch.from_numpy(v[lo:hi]).cuda() for v in wide])
+        os.environ.pop("CCAB_EXCHANGE")
+        np.save(os.path.join(out_dir, f"wide_w1_nccl_rank{rank}.npy"), ref.weights_[1])
+        with open(os.path.join(out_dir, f"exchange_rank{rank}.txt"), "w") as f:
+            f.write("nvls" if used_nvls else "nccl")
     finally:
         dist.destroy_process_group()
 
@@ -76,6 +84,10 @@ def test_two_rank_fit_matches_single_gpu(tmp_path):
     ww = [np.load(tmp_path / f"wide_w1_rank{r}.npy") for r in range(2)]
     assert np.array_equal(ww[0], ww[1])
     assert R.max_rel_err_per_vector([ww[0].astype(np.float64)], [one.weights_[1].astype(np.float64)]) < 2e-4
+    # the fused NVLS exchange and the NCCL all-reduce sum the same two shards: identical totals, identical weights
+    wn = np.load(tmp_path / "wide_w1_nccl_rank0.npy")
+    print("exchange path:", open(tmp_path / "exchange_rank0.txt").read())
+    assert R.max_rel_err_per_vector([ww[0].astype(np.float64)], [wn.astype(np.float64)]) < 1e-6
 
 
 def test_exchange_message_round_trip():
