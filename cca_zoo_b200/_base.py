@@ -119,7 +119,10 @@ class BaseModel(BaseEstimator, ABC):
             if len({v.dtype for v in dev_views}) > 1:
                 dev_views = [v.to(torch.float64) for v in dev_views]
             dims = [int(v.shape[1]) for v in dev_views]
-            return ops.moments(dev_views, precision=self.precision), n_rows, dims, dev_views[0].dtype
+            # shifted accumulation when a pilot over the leading rows finds badly centred columns (one-pass covariance
+            # from raw moments would cancel: the reference centres first, cca_zoo/_base.py:96-99)
+            mom, _ = ops.moments_safe(dev_views, precision=self.precision)
+            return mom, n_rows, dims, dev_views[0].dtype
         # ---- streamed: the moments are additive over row chunks (the same identity the multi-GPU path uses) ----
         cpu_views = []
         for v in validated:
@@ -135,6 +138,7 @@ class BaseModel(BaseEstimator, ABC):
         mom = None
         step = self._stream_chunk_rows
         pending = None
+        self._stream_x0 = "undecided"          # pilot origin of the shifted accumulation, fixed by the first chunk
         for lo in range(0, n_rows, step):
             hi = min(lo + step, n_rows)
             with torch.cuda.stream(copy):
@@ -152,7 +156,13 @@ class BaseModel(BaseEstimator, ABC):
         main.wait_event(ready)
         for c in chunk:
             c.record_stream(main)
-        part = ops.moments(chunk, precision=self.precision)
+        if isinstance(self._stream_x0, str):
+            cand, ratio = ops.column_pilot(chunk)
+            self._stream_x0 = cand if ratio > ops.SHIFT_RATIO[chunk[0].dtype] else None
+        if self._stream_x0 is None:
+            part = ops.moments(chunk, precision=self.precision)
+        else:
+            part, _ = ops.moments_safe(chunk, precision=self.precision, x0=self._stream_x0)
         if mom is None:
             return part
         mom.add_(part)
@@ -294,11 +304,35 @@ class BaseModel(BaseEstimator, ABC):
         return out
 
     def transform(self, views):
-        """Project views with the fitted weights (cca_zoo/_base.py:108-123)."""
+        """Project views with the fitted weights: ``(v - mean_) @ weights_`` per view (cca_zoo/_base.py:108-123).
+
+        CUDA tensors, and host inputs above ``_device_score_threshold`` elements, are projected on the device:
+        ``Z_i = X_i W_i - 1 (mean_i^T W_i)`` is one GEMM per view (tcgen05 for float32, DMMA for float64) whose output
+        is pre-loaded with the mean term, so neither a centred copy of the data nor a second pass exists.  Returns
+        numpy arrays like the reference."""
         check_is_fitted(self)
+        on_gpu = any(isinstance(v, torch.Tensor) and v.is_cuda for v in views)
+        big = sum(int(np.prod(getattr(v, "shape", (0,)))) for v in views) >= self._device_score_threshold
+        if on_gpu or (big and torch.cuda.is_available()):
+            return self._transform_device(validate_views(views))
         validated = validate_views(self._as_numpy_views(views))
-        centred = [v - m for v, m in zip(validated, self.means_)]
-        return [v @ w for v, w in zip(centred, self.weights_)]
+        return [(v - m) @ w for v, m, w in zip(validated, self.means_, self.weights_)]
+
+    def _transform_device(self, validated):
+        device = self._device()
+        out = []
+        for v, m, w in zip(validated, self.means_, self.weights_):
+            X = self._to_device(v, device)
+            np_dt = np.result_type(X.cpu().numpy().dtype if False else (np.float32 if X.dtype == torch.float32
+                                                                         else np.float64), w.dtype)
+            dt = torch.float32 if np_dt == np.float32 else torch.float64
+            X = X.to(dt)
+            W = torch.from_numpy(np.ascontiguousarray(w, dtype=np_dt)).to(device)
+            mw = -(np.asarray(m, dtype=np.float64) @ np.asarray(w, dtype=np.float64))          # (k,) on the host: tiny
+            Z = torch.from_numpy(mw.astype(np_dt)).to(device).expand(X.shape[0], -1).contiguous()
+            ops.gemm(X, W, beta=1.0, out=Z)                                                  # Z <- X W + Z
+            out.append(Z.cpu().numpy())
+        return out
 
     def fit_transform(self, views, y=None):
         return self.fit(views, y).transform(views)

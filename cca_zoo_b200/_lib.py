@@ -34,6 +34,9 @@ SIGNATURES = {
     "ccab_moments_unpack": (C.c_int, [C.c_int, _i64p, _vp, _vp, _vp]),
     "ccab_moments_exchange_nvls": (C.c_int, [C.c_int, _i64p, _vp, C.c_double, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int,
                                              C.c_int64, C.c_uint, _vp, _vp]),
+    "ccab_column_pilot": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, C.c_int64, _vp, _vp, _vp]),
+    "ccab_shift_rows": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, C.c_int64, _vp, _vp, C.c_int64, _vp]),
+    "ccab_moments_unshift": (C.c_int, [C.c_int, C.c_int, _i64p, _vp, C.POINTER(_vp), C.c_double, _vp]),
     "ccab_covariance": (C.c_int, [C.c_int, C.c_int, _i64p, _vp, C.c_double, C.c_int, _vp, C.c_int64, _vp, _vp]),
     "ccab_syevj_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "ccab_syevj": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, C.c_int64, C.c_double, _vp, _vp, C.c_int64,

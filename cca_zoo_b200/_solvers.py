@@ -279,11 +279,13 @@ def gcca_weights_cholesky(C, dims, n_samples, latent_dimensions, c, mu, eps, sec
     k = min(latent_dimensions, D, n_samples)
     if 4 * k > D:
         return None
-    Wt = _cholesky_whiteners(C, dims, c, mu, eps)
+    Wt = _cholesky_whiteners(C, dims, c, mu, eps)       # Wt_i = sqrt(mu_i) L_i^-1: a zero view weight zeroes the whitener
     if Wt is None:
         return None
-    # factors of the UNregularised blocks for pinv(X_i) = C_ii^-1 X_i^T/(n-1) (full column rank certified)
-    Lc = _cholesky_whiteners(Cd, dims, [0.0] * m, [1.0] * m, 0.0) if (Cd is not C or any(ci != 0.0 for ci in c)) \
+    # factors of the UNregularised blocks for pinv(X_i) = C_ii^-1 X_i^T/(n-1) (full column rank certified); a view with
+    # mu_i = 0 is ignored by the eigenproblem but still gets weights (the reference: cca_zoo/linear/_gcca.py:105,109)
+    Lc = _cholesky_whiteners(Cd, dims, [0.0] * m, [1.0] * m, 0.0) \
+        if (Cd is not C or any(ci != 0.0 for ci in c) or any(x == 0.0 for x in mu)) \
         else [w / (mu[i] ** 0.5) for i, w in enumerate(Wt)]
     if Lc is None:
         return None
@@ -453,6 +455,9 @@ def gcca_weights(C, dims, n_samples, latent_dimensions, c, mu, eps, solver="auto
     for i in range(m):
         reg_min = float(((1.0 - c[i]) * lams[i][-1] + c[i]).item())
         floor = (eps - reg_min) if reg_min < eps else 0.0
+        if mu[i] == 0.0:                                   # ignored view: zero whitener (no division by mu)
+            wts.append(torch.zeros((dims[i], dims[i]), dtype=C.dtype, device=C.device))
+            continue
         Wt, _, _ = ops.whiten_rows(lams[i], vts[i], c[i], floor_add=floor, scale=1.0 / mu[i], rank_tol=-1.0)
         wts.append(Wt)
     G = torch.empty((D, D), dtype=C.dtype, device=C.device)

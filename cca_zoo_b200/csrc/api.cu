@@ -158,6 +158,50 @@ int ccab_moments_exchange_nvls(int n_views, const int64_t* dims, double* moments
   CCAB_CATCH
 }
 
+int ccab_column_pilot(int dtype, const void* X, int64_t rows, int d, int64_t ld, void* x0, float* ratio_max_dev,
+                      void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(X && x0 && ratio_max_dev, "null pointer argument");
+  int rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CCAB_F32)
+    return column_pilot<float>(static_cast<const float*>(X), rows, d, ld, static_cast<float*>(x0), ratio_max_dev, s);
+  return column_pilot<double>(static_cast<const double*>(X), rows, d, ld, static_cast<double*>(x0), ratio_max_dev, s);
+  CCAB_CATCH
+}
+
+int ccab_shift_rows(int dtype, const void* X, int64_t n, int d, int64_t ldx, const void* x0, void* Xs, int64_t lds,
+                    void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(X && x0 && Xs && ldx >= d && lds >= d, "bad argument");
+  int rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CCAB_F32)
+    return shift_rows<float>(static_cast<const float*>(X), n, d, ldx, static_cast<const float*>(x0),
+                             static_cast<float*>(Xs), lds, s);
+  return shift_rows<double>(static_cast<const double*>(X), n, d, ldx, static_cast<const double*>(x0),
+                            static_cast<double*>(Xs), lds, s);
+  CCAB_CATCH
+}
+
+int ccab_moments_unshift(int dtype, int n_views, const int64_t* dims, double* moments, const void* const* x0,
+                         double n_rows, void* stream) {
+  CCAB_TRY
+  CCAB_CHECK_ARG(dtype == CCAB_F32 || dtype == CCAB_F64, "bad dtype %d", dtype);
+  CCAB_CHECK_ARG(dims && moments && x0, "null pointer argument");
+  ColumnLayout L;
+  int rc = make_layout(n_views, dims, &L);
+  if (rc) return rc;
+  rc = require_device();
+  if (rc) return rc;
+  return moments_unshift(L, moments, x0, dtype == CCAB_F64, n_rows, static_cast<cudaStream_t>(stream));
+  CCAB_CATCH
+}
+
 int ccab_covariance(int out_dtype, int n_views, const int64_t* dims, const double* moments, double n_total,
                     int center, void* C, int64_t ldc, void* mean, void* stream) {
   CCAB_TRY

@@ -127,11 +127,7 @@ int ccaloss_small(const T* C, int64_t ldc, int d1, int d2, double eps, T* loss, 
                  d2);
   CCAB_CHECK_ARG(ldc >= d1 + d2, "ldc too small");
   const size_t smem = sizeof(T) * (6 * kLD * kLP + 2 * kLD + 33);
-  static bool attr = false;
-  if (!attr) {
-    CCAB_CUDA(cudaFuncSetAttribute(ccaloss_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  CCAB_CUDA(cudaFuncSetAttribute(ccaloss_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ccaloss_small_kernel<T><<<1, 1024, smem, stream>>>(C, ldc, d1, d2, (T)eps, loss, G11, P, G22, min_pivot);
   count_launches(1);
   CCAB_CUDA(cudaGetLastError());

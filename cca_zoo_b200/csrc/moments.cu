@@ -1086,14 +1086,15 @@ int encode_bf16_map(CUtensorMap* map, const void* ptr, int64_t n_rows, int64_t d
 }
 
 int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[64] = {};   // per device ordinal (a process may drive several GPUs)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (!n[dev]) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
 struct TcPlan {
@@ -1355,12 +1356,9 @@ int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t*
 #define CCAB_LAUNCH_2CTA(KC_, X3_, NS_)                                                                      \
   do {                                                                                                       \
     using Cfg = Tc2Cfg<KC_, X3_, NS_>;                                                                       \
-    static bool attr = false;                                                                                \
-    if (!attr) {                                                                                             \
-      CCAB_CUDA(cudaFuncSetAttribute(moments_tf32_2cta_kernel<KC_, X3_, NS_>,                                \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));              \
-      attr = true;                                                                                           \
-    }                                                                                                        \
+    /* function attributes are per device / context: set on every call */                       \
+    CCAB_CUDA(cudaFuncSetAttribute(moments_tf32_2cta_kernel<KC_, X3_, NS_>,                                  \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));                \
     moments_tf32_2cta_kernel<KC_, X3_, NS_><<<grid, kTcThreads, Cfg::kSmem, stream>>>(prm);                  \
   } while (0)
     if (x3) {
@@ -1399,21 +1397,13 @@ int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t*
     dim3 grid(P.ntiles, P.num_splits);
     if (x3) {
       using Cfg = TcCfg<16, true>;
-      static bool attr = false;
-      if (!attr) {
-        CCAB_CUDA(cudaFuncSetAttribute(moments_tf32_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::kSmem));
-        attr = true;
-      }
+      CCAB_CUDA(cudaFuncSetAttribute(moments_tf32_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::kSmem));
       moments_tf32_kernel<16, true><<<grid, kTcThreads, Cfg::kSmem, stream>>>(prm);
     } else {
       using Cfg = TcCfg<32, false>;
-      static bool attr = false;
-      if (!attr) {
-        CCAB_CUDA(cudaFuncSetAttribute(moments_tf32_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::kSmem));
-        attr = true;
-      }
+      CCAB_CUDA(cudaFuncSetAttribute(moments_tf32_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::kSmem));
       moments_tf32_kernel<32, false><<<grid, kTcThreads, Cfg::kSmem, stream>>>(prm);
     }
     count_launches(1);
@@ -1657,6 +1647,127 @@ int moments_exchange_nvls(const ColumnLayout& L, double* mom, double n_local, do
   grid = (int)std::min<int64_t>(grid, std::max<int64_t>(1, p.chunk / 512));
   exchange_nvls_kernel<<<grid, 512, 0, stream>>>(p);
   count_launches(1);
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// Shifted accumulation (numerical safety of the one-pass covariance): C = (M - s s^T / n) / (n - 1) cancels
+// catastrophically when a column's mean dominates its spread -- the relative error of C is eps_prod * (mean / std)^2
+// with eps_prod the product / accumulation error of the moment kernel (1e-7 .. 1e-6 for the 3xTF32 modes).  Covariance
+// is shift invariant, so the moments of X - x0 (x0 = pilot mean of the leading rows) are accumulated instead and the
+// raw moments are rebuilt in float64 afterwards, where 53 bits absorb the cancellation:
+//     M = M' + x0 s'^T + s' x0^T + n x0 x0^T,   s = s' + n x0.
+// pilot_kernel : x0 and the ratio mean^2 / var per column from <= 4096 leading rows (one block per 32 columns)
+// shift_kernel : Xs = X - x0
+// unshift_kernel: the float64 correction above on the padded moment buffer (upper block triangle)
+// =============================================================================================
+template <typename T>
+__global__ void pilot_kernel(const T* __restrict__ X, int64_t rows, int d, int64_t ld, T* __restrict__ x0,
+                             float* __restrict__ ratio_max) {
+  __shared__ double s1[32][33], s2[32][33];
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rg = threadIdx.x >> 5;
+  double a = 0.0, b = 0.0;
+  const double ref = j < d ? (double)X[j] : 0.0;     // first row as a provisional origin: the pilot itself must not cancel
+  if (j < d)
+    for (int64_t i = rg; i < rows; i += 32) {
+      const double v = (double)X[i * ld + j] - ref;
+      a += v;
+      b += v * v;
+    }
+  s1[rg][threadIdx.x & 31] = a;
+  s2[rg][threadIdx.x & 31] = b;
+  __syncthreads();
+  if (rg == 0 && j < d) {
+    double sa = 0.0, sb = 0.0;
+    for (int k = 0; k < 32; ++k) { sa += s1[k][threadIdx.x & 31]; sb += s2[k][threadIdx.x & 31]; }
+    const double mean = sa / (double)rows;
+    const double var = fmax(sb / (double)rows - mean * mean, 0.0);
+    const double m0 = ref + mean;
+    x0[j] = (T)m0;
+    const double r = var > 0.0 ? m0 * m0 / var : (m0 != 0.0 ? 1e30 : 0.0);
+    atomicMax(reinterpret_cast<unsigned*>(ratio_max), __float_as_uint((float)fmin(r, 1e30)));
+  }
+}
+
+template <typename T>
+__global__ void shift_kernel(const T* __restrict__ X, int64_t n, int d, int64_t ldx, const T* __restrict__ x0,
+                             T* __restrict__ Xs, int64_t lds) {
+  const int64_t total = n * (int64_t)d;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / d;
+    const int c = (int)(i - r * d);
+    Xs[r * lds + c] = X[r * ldx + c] - x0[c];
+  }
+}
+
+struct UnshiftParams {
+  int n_views, Dp;
+  int dims[kMaxViews];
+  int poff[kMaxViews + 1];
+  const void* x0[kMaxViews];   // per view, in the views' dtype
+  int is_f64;
+};
+__device__ __forceinline__ double unshift_x0(const UnshiftParams& p, int pc) {
+  int v = 0;
+  while (v + 1 < p.n_views && p.poff[v + 1] <= pc) ++v;
+  const int c = pc - p.poff[v];
+  if (c >= p.dims[v] || !p.x0[v]) return 0.0;
+  return p.is_f64 ? static_cast<const double*>(p.x0[v])[c] : (double)static_cast<const float*>(p.x0[v])[c];
+}
+__global__ void unshift_kernel(const UnshiftParams p, double* __restrict__ mom, double n) {
+  double* M = mom;
+  double* s = mom + (size_t)p.Dp * p.Dp;
+  const size_t total = (size_t)p.Dp * p.Dp;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / p.Dp), c = (int)(e % p.Dp);
+    if (r / kBlk > c / kBlk) continue;
+    const double ar = unshift_x0(p, r), ac = unshift_x0(p, c);
+    if (ar == 0.0 && ac == 0.0) continue;
+    M[e] += ar * s[c] + s[r] * ac + n * ar * ac;      // s still holds the shifted sums here
+  }
+}
+__global__ void unshift_sums_kernel(const UnshiftParams p, double* __restrict__ mom, double n) {
+  double* s = mom + (size_t)p.Dp * p.Dp;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < p.Dp) s[c] += n * unshift_x0(p, c);
+}
+
+template <typename T>
+int column_pilot(const T* X, int64_t rows, int d, int64_t ld, T* x0, float* ratio_max, cudaStream_t stream) {
+  CCAB_CHECK_ARG(rows >= 1 && d >= 1 && ld >= d, "bad pilot shape");
+  pilot_kernel<T><<<(unsigned)ceil_div(d, 32), 1024, 0, stream>>>(X, rows, d, ld, x0, ratio_max);
+  count_launches(1);
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+template <typename T>
+int shift_rows(const T* X, int64_t n, int d, int64_t ldx, const T* x0, T* Xs, int64_t lds, cudaStream_t stream) {
+  const int64_t total = n * (int64_t)d;
+  if (total == 0) return 0;
+  shift_kernel<T><<<(unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16), 256, 0, stream>>>(
+      X, n, d, ldx, x0, Xs, lds);
+  count_launches(1);
+  CCAB_CUDA(cudaGetLastError());
+  return 0;
+}
+template int column_pilot<float>(const float*, int64_t, int, int64_t, float*, float*, cudaStream_t);
+template int column_pilot<double>(const double*, int64_t, int, int64_t, double*, float*, cudaStream_t);
+template int shift_rows<float>(const float*, int64_t, int, int64_t, const float*, float*, int64_t, cudaStream_t);
+template int shift_rows<double>(const double*, int64_t, int, int64_t, const double*, double*, int64_t, cudaStream_t);
+
+int moments_unshift(const ColumnLayout& L, double* mom, const void* const* x0, int is_f64, double n,
+                    cudaStream_t stream) {
+  UnshiftParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_views = L.n_views; p.Dp = L.Dp; p.is_f64 = is_f64;
+  for (int v = 0; v < L.n_views; ++v) { p.dims[v] = L.dims[v]; p.x0[v] = x0[v]; }
+  for (int v = 0; v <= L.n_views; ++v) p.poff[v] = L.poff[v];
+  const size_t total = (size_t)L.Dp * L.Dp;
+  unshift_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8), 256, 0, stream>>>(p, mom, n);
+  unshift_sums_kernel<<<(unsigned)ceil_div(L.Dp, 256), 256, 0, stream>>>(p, mom, n);   // after M: M used the shifted s
+  count_launches(2);
   CCAB_CUDA(cudaGetLastError());
   return 0;
 }

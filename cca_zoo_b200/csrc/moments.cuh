@@ -45,6 +45,15 @@ int64_t moments_packed_size(const ColumnLayout& L);
 int moments_pack(const ColumnLayout& L, const double* moments, double n_local, double* packed, cudaStream_t stream);
 int moments_unpack(const ColumnLayout& L, const double* packed, double* moments, cudaStream_t stream);
 
+// Shifted accumulation: pilot statistics of the leading rows, Xs = X - x0, and the float64 correction that turns the
+// moments of the shifted data back into raw moments (see moments.cu).
+template <typename T>
+int column_pilot(const T* X, int64_t rows, int d, int64_t ld, T* x0, float* ratio_max, cudaStream_t stream);
+template <typename T>
+int shift_rows(const T* X, int64_t n, int d, int64_t ldx, const T* x0, T* Xs, int64_t lds, cudaStream_t stream);
+int moments_unshift(const ColumnLayout& L, double* moments, const void* const* x0, int is_f64, double n,
+                    cudaStream_t stream);
+
 // Fused exchange step on symmetric memory (pack + in-switch reduction with multimem + unpack in ONE kernel).
 // sym_local / sym_multicast: local and multicast address of a symmetric buffer of sym_doubles doubles
 // (>= world * ceil(packed / world)); pads_dev: device array of the world signal-pad pointers (uint32, pad_slots

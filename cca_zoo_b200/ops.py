@@ -138,6 +138,71 @@ def moments_exchange_nvls(mom: torch.Tensor, dims, n_local, sym: torch.Tensor, m
     return n_dev
 
 
+#: a column whose pilot mean^2 / variance exceeds this is accumulated shifted (relative covariance error of the float32
+#: moment kernels ~ 1e-6 * ratio; float64 kernels have 9 more digits and never need it below 1e8)
+SHIFT_RATIO = {torch.float32: 16.0, torch.float64: 1e8}
+PILOT_ROWS = 4096
+
+
+def column_pilot(views):
+    """Per view x0 (pilot column means of the leading rows, device tensors in the views' dtype) and the largest
+    mean^2 / variance over all columns (ONE host read-back: it decides whether an extra pass is worth taking)."""
+    lib = _lib.load()
+    ratio = torch.zeros(1, dtype=torch.float32, device=views[0].device)
+    x0 = []
+    for v in views:
+        _require_cuda(v, "view")
+        vv = v if v.stride(1) == 1 else v.contiguous()
+        o = torch.empty(v.shape[1], dtype=v.dtype, device=v.device)
+        with torch.cuda.device(v.device):
+            rc = lib.ccab_column_pilot(_DT[v.dtype], _ptr(vv), min(int(v.shape[0]), PILOT_ROWS), int(v.shape[1]),
+                                       vv.stride(0), _ptr(o), _ptr(ratio), _stream(v))
+        _lib.check(rc, "ccab_column_pilot")
+        x0.append(o)
+    return x0, float(ratio.item())
+
+
+def shift_rows(v, x0):
+    """v - x0 (row-major copy with a TMA-friendly leading dimension)."""
+    lib = _lib.load()
+    vv = v if v.stride(1) == 1 else v.contiguous()
+    per = 16 // v.element_size()
+    ld = (v.shape[1] + per - 1) // per * per
+    out = torch.empty((v.shape[0], ld), dtype=v.dtype, device=v.device)
+    with torch.cuda.device(v.device):
+        rc = lib.ccab_shift_rows(_DT[v.dtype], _ptr(vv), int(v.shape[0]), int(v.shape[1]), vv.stride(0), _ptr(x0),
+                                 _ptr(out), ld, _stream(v))
+    _lib.check(rc, "ccab_shift_rows")
+    return out[:, : v.shape[1]]
+
+
+def moments_unshift_(mom, dims, x0, n_rows):
+    """In place: moments of the shifted views -> raw moments (float64 algebra)."""
+    lib = _lib.load()
+    ptrs = (C.c_void_p * len(x0))(*[0 if t is None else t.data_ptr() for t in x0])
+    dt = next(t.dtype for t in x0 if t is not None)
+    with torch.cuda.device(mom.device):
+        rc = lib.ccab_moments_unshift(_DT[dt], len(dims), _lib.i64_array(dims), _ptr(mom), ptrs, float(n_rows),
+                                      _stream(mom))
+    _lib.check(rc, "ccab_moments_unshift")
+    return mom
+
+
+def moments_safe(views, precision: str = "tf32x3b", x0=None):
+    """``moments`` with the shifted accumulation when it matters: a pilot over the leading rows decides (one tiny
+    kernel per view and one scalar read-back); badly centred views are accumulated as X - x0 and the raw moments are
+    rebuilt in float64.  ``x0`` given = shift by it unconditionally (streamed fits keep one x0 for all chunks).
+    Returns (moments, x0 or None)."""
+    if x0 is None:
+        cand, ratio = column_pilot(views)
+        if not ratio > SHIFT_RATIO[views[0].dtype]:
+            return moments(views, precision=precision), None
+        x0 = cand
+    shifted = [shift_rows(v, o) for v, o in zip(views, x0)]
+    mom = moments(shifted, precision=precision)
+    return moments_unshift_(mom, [int(v.shape[1]) for v in views], x0, views[0].shape[0]), x0
+
+
 def covariance(mom: torch.Tensor, dims, n_total: float, center: bool = True, dtype=torch.float64):
     """(C [D,D], mean [D]) from an (all-reduced) moments buffer."""
     lib = _lib.load()

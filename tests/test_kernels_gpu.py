@@ -71,6 +71,34 @@ def test_moments_uncentred_and_nonzero_mean():
     np.testing.assert_allclose(C1.cpu().numpy(), _ref_cov(views), rtol=1e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize("precision", ["tf32x3b", "tf32x3", "exact"])
+def test_badly_centred_columns_take_the_shifted_accumulation(precision):
+    """Columns with |mean| = 1000 std: raw float32 moments would lose all digits of the covariance
+    (eps * (mean / std)^2 ~ 1e-7 * 1e6); the pilot detects it and the shifted pass keeps float32-grade accuracy."""
+    from cca_zoo_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    n, dims = 6000, [96, 130]
+    base = [torch.randn(n, d, generator=g, dtype=torch.float64) for d in dims]
+    off = [torch.linspace(-1000.0, 1000.0, d, dtype=torch.float64) for d in dims]
+    views64 = [b + o for b, o in zip(base, off)]
+    views = [v.float().cuda() for v in views64]
+    mom, x0 = ops.moments_safe(views, precision=precision)
+    assert x0 is not None, "the pilot must ask for the shifted pass here"
+    Cm, mean = ops.covariance(mom, dims, n, center=True, dtype=torch.float64)
+    X = torch.cat([v.double().cpu() for v in views], dim=1)          # the float32 inputs, exactly
+    ref = torch.cov(X.T)
+    scale = torch.sqrt(torch.outer(ref.diagonal(), ref.diagonal()))
+    assert float(((Cm.cpu() - ref).abs() / scale).max()) < 5e-5
+    assert float((mean.cpu() - X.mean(dim=0)).abs().max()) < 1e-3
+    raw = ops.moments(views, precision=precision)                     # for contrast: the unguarded one-pass form
+    Cr, _ = ops.covariance(raw, dims, n, center=True, dtype=torch.float64)
+    assert float(((Cr.cpu() - ref).abs() / scale).max()) > 1e-3
+    centred = [v.float().cuda() for v in base]                        # well centred data: no extra pass
+    _, x0c = ops.moments_safe(centred, precision=precision)
+    assert x0c is None
+
+
 def test_moments_are_additive_over_row_shards():
     """The multi-GPU contract: moments of row shards sum to the moments of the whole."""
     from cca_zoo_b200 import ops

@@ -297,3 +297,54 @@ def test_fitted_and_partially_fitted_estimators_pickle():
     half = rCCA(latent_dimensions=3, c=0.1).partial_fit([v[:1500] for v in views], solve=False)
     resumed = pickle.loads(pickle.dumps(half)).partial_fit([v[1500:] for v in views])
     assert R.max_rel_err_per_vector(resumed.weights_, est.weights_) < 1e-9
+
+
+def test_large_offsets_do_not_destroy_float32_parity():
+    """float32 views whose means are 300 standard deviations away from zero.  The reference centres the data
+    before anything else; the one-pass moment form needs the shifted accumulation to stay within the 1e-3 bar."""
+    from cca_zoo_b200.linear import MCCA, rCCA
+
+    rng = np.random.default_rng(12)
+    z = rng.standard_normal((5000, 4)) * np.array([1.0, 0.8, 0.6, 0.45])
+    views = [(z @ rng.standard_normal((4, d)) * 0.6 + rng.standard_normal((5000, d)) + 300.0 * (1 + np.arange(d) % 3))
+             .astype(np.float32) for d in (40, 56, 24)]
+    v64 = [v.astype(np.float64) for v in views]
+    est = rCCA(latent_dimensions=3, c=0.05).fit(views[:2])
+    w_ref, _ = R.ref_rcca_fit(v64[:2], 3, 0.05)
+    assert R.max_rel_err_per_vector([w.astype(np.float64) for w in est.weights_], w_ref) < 1e-3
+    m = MCCA(latent_dimensions=3, c=0.1).fit(views)
+    w_ref, _ = R.ref_mcca_fit(v64, 3, 0.1)
+    assert R.max_rel_err_per_vector(m.weights_, w_ref) < 1e-3
+
+
+def test_transform_on_the_device_equals_the_reference_definition():
+    """CUDA inputs (and large host inputs) are projected on the device -- one GEMM per view with the
+    mean term folded in -- and equal (v - mean_) @ weights_ (cca_zoo/_base.py:108-123)."""
+    import torch
+
+    from cca_zoo_b200.linear import MCCA, rCCA
+
+    views = G.dataset("joint3_med", "f32")
+    for est in (rCCA(latent_dimensions=4, c=0.1).fit(views[:2]), MCCA(latent_dimensions=3, c=0.05).fit(views)):
+        vs = views[:len(est.weights_)]
+        host = est.transform(vs)                                        # numpy branch
+        dev = est.transform([torch.from_numpy(v).cuda() for v in vs])   # device branch
+        for h, d, v, m, w in zip(host, dev, vs, est.means_, est.weights_):
+            ref = (v.astype(np.float64) - m.astype(np.float64)) @ w.astype(np.float64)
+            assert isinstance(d, np.ndarray) and d.shape == h.shape and d.dtype == h.dtype
+            scale = np.abs(ref).max()
+            assert np.abs(d - ref).max() < 1e-4 * scale and np.abs(h - ref).max() < 1e-4 * scale
+
+
+def test_gcca_ignores_a_view_with_zero_weight_like_the_reference():
+    """view_weights with a zero entry -- the reference drops that view from the eigenproblem but still
+    returns weights for it (cca_zoo/linear/_gcca.py:105,109); no division by zero on either solver route."""
+    from cca_zoo_b200.linear import GCCA
+
+    views = G.dataset("joint4_gcca", "f64")
+    mu = [1.0, 0.0, 2.0, 1.0]
+    w_ref, _ = R.ref_gcca_fit(views, 3, 0.1, mu)
+    for solver in ("eigen", "cholesky"):
+        est = GCCA(latent_dimensions=3, c=0.1, view_weights=mu, solver=solver).fit(views)
+        assert all(np.isfinite(w).all() for w in est.weights_)
+        assert R.max_rel_err_per_vector(est.weights_, w_ref) < 1e-6
