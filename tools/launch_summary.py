@@ -8,10 +8,11 @@ names = [(r[ki], float(r[vi].replace(",", "")) / 1e3) for r in rows[1:] if len(r
 # the bench runs warm-up fits first: keep the launches after the LAST occurrence of the first kernel of a step
 marker = sys.argv[2] if len(sys.argv) > 2 else None
 if marker:
+    # the list ends with the timed step; it starts at the first kernel of the LAST group of marker launches
     idx = max(i for i, (n, _) in enumerate(names) if marker in n)
-    # a step = from the last marker kernel that still has a full step after it; walk back to the previous marker
-    prev = max([i for i, (n, _) in enumerate(names[:idx]) if marker in n] or [0])
-    names = names[prev:idx]
+    while idx > 0 and marker in names[idx - 1][0]:
+        idx -= 1
+    names = names[idx:]
 agg = collections.OrderedDict()
 for n, t in names:
     k = n.split("(")[0].replace("void ", "").replace("ccab::<unnamed>::", "").replace("ccab::", "")[:70]
