@@ -406,7 +406,10 @@ def run_ours(args):
             pass
         if k1:
             ach = flops / (k1 * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "moments_tf32_2cta_kernel", "achieved": ach, "peak": bf16 / 2,
+            kname = {"tf32x3b": "moments_x3b_2cta_kernel (2 bf16 cross-term + 2 tf32 MMAs per 16 samples)",
+                     "tf32x3": "moments_tf32_2cta_kernel<X3> (3 tf32 MMAs per k-step)"}.get(
+                         args.precision, "moments_tf32_2cta_kernel")
+            roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": bf16 / 2,
                     "unit": "TFLOP/s", "frac": ach / (bf16 / 2), "traffic": traffic, "kernel_ms": k1,
                     "mma_passes": passes, "algorithmic_flops": flops, "algorithmic_bytes": n * D * 4,
                     "frac_of_issued": passes * ach / (bf16 / 2), "peak_source": peak_src,
