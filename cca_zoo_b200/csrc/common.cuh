@@ -190,6 +190,17 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of this cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
 // executed by both CTAs; the transaction bytes are credited to the LEADER CTA's mbarrier
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1) {
   asm volatile(

@@ -67,7 +67,7 @@ float moments_profile_last_ms() {
 }
 
 TcDebug& tc_debug() {
-  static TcDebug d = {-1, -1, -1, 0, 0, 0, 0, 0, 0};
+  static TcDebug d = {-1, -1, -1, 0, 0, 0, 0, 0, 0, 0};
   return d;
 }
 
@@ -504,6 +504,7 @@ struct alignas(64) TcParams3 {
   float* partial_sum;
   int total_chunks, chunks_per_split, num_splits;
   int nblocks, nb2, Dp2;
+  int ntiles, total_units;           // persistent kernel: units = (tile, split) pairs, dealt round-robin to the CTA pairs
   int blk_col0[kMaxBlocks + 2];
   uint8_t blk_view[kMaxBlocks + 2];
 };
@@ -728,6 +729,256 @@ __global__ void tf32_bf16_split_kernel(const float* __restrict__ x, int64_t n, i
     }
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Persistent form of the kernel above (default): one CTA pair per SM pair walks the (tile, split) units
+// u = pair, pair + npairs, ... with ONE continuous TMA / MMA pipeline and TWO 256-column accumulators in TMEM, so the
+// epilogue of unit i (TMEM -> registers -> split partial in HBM) runs under the MMAs of unit i + 1 and the per-unit
+// start-up (barrier init, TMEM allocation, cluster sync, ring fill) is paid once.  Consecutive units of a pair share
+// their sample rows with the units the other pairs are processing (tile index fastest), which keeps the operand
+// re-reads in L2.  The two accumulators leave no room for the 16-column sum accumulator: the column sums come from
+// the pre-pass (tf32_bf16_split_sums_kernel), exactly in fp32.
+//   tmem_full_bar[b]  (each CTA)  : MMA commit, multicast       -> epilogue warps of both CTAs
+//   tmem_empty_bar[b] (leader CTA): 4 epilogue warps x 2 CTAs   -> MMA thread (remote arrive from the peer)
+// ---------------------------------------------------------------------------------------------
+template <int NS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+moments_x3b_persist_kernel(const __grid_constant__ TcParams3 p) {
+  using Cfg = Tc3Cfg<NS>;
+  constexpr int KC = Cfg::KC;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NS * Cfg::kStage);
+  uint64_t* empty_bar = full_bar + NS;
+  uint64_t* tmem_full_bar = empty_bar + NS;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int v = 0; v < 3 * kMaxViews; ++v) tma_prefetch_desc(&p.maps[v]);
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // unit -> (I, J) of the 256-column tile pair, split
+  auto decode = [&](int u, int& I, int& J, int& split) {
+    int t = u % p.ntiles;
+    split = u / p.ntiles;
+    int rowlen = p.nb2;
+    I = 0;
+    while (t >= rowlen) { t -= rowlen; ++I; --rowlen; }
+    J = I + t;
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs, each loads its own halves) =================
+    if (elect_one()) {
+      const uint32_t bytes_pair = 2u * Cfg::kStage;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = pair; u < p.total_units; u += npairs) {
+        int I, J, split;
+        decode(u, I, J, split);
+        const int blkA = min(2 * I + (int)rank, p.nblocks);
+        const int blkB = min(2 * J + (int)rank, p.nblocks);
+        const int vA = p.blk_view[blkA], colA = p.blk_col0[blkA];
+        const int vB = p.blk_view[blkB], colB = p.blk_col0[blkB];
+        const int c0 = split * p.chunks_per_split;
+        const int c1 = min(c0 + p.chunks_per_split, p.total_chunks);
+        for (int c = c0; c < c1; ++c) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], bytes_pair);
+          uint8_t* st = smem + stage * Cfg::kStage;
+          const int row = c * KC;
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            tma_load_2d_2sm(st + a * Cfg::kAtom, &p.maps[vA], &full_bar[stage], colA + 32 * a, row);
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            tma_load_2d_2sm(st + (4 + a) * Cfg::kAtom, &p.maps[vB], &full_bar[stage], colB + 32 * a, row);
+          uint8_t* bf = st + Cfg::kRaw;
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {      // 0: bhi, 1: blo
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+              tma_load_2d_2sm(bf + (o * 2 + a) * Cfg::kAtom, &p.maps[(1 + o) * kMaxViews + vA], &full_bar[stage],
+                              colA + 64 * a, row);
+              tma_load_2d_2sm(bf + (4 + o * 2 + a) * Cfg::kAtom, &p.maps[(1 + o) * kMaxViews + vB], &full_bar[stage],
+                              colB + 64 * a, row);
+            }
+          }
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: one thread of the LEADER CTA drives both SMs =================
+    if (leader) {
+      const uint32_t idesc_tf = umma_idesc_tf32_mn(256, 256);
+      const uint32_t idesc_bf = umma_idesc_bf16_mn(256, 256);
+      const uint32_t sb = smem_u32(smem);
+      const uint64_t dA_tf = umma_smem_desc(sb, KC * 128, 512, kUmmaLayout);
+      const uint64_t dB_tf = umma_smem_desc(sb + 4 * Cfg::kAtom, KC * 128, 512, kUmmaLayout);
+      const uint64_t dA_bhi = umma_smem_desc(sb + Cfg::kRaw, KC * 128, 1024, 2);
+      const uint64_t dA_blo = umma_smem_desc(sb + Cfg::kRaw + Cfg::kBf, KC * 128, 1024, 2);
+      const uint64_t dB_bhi = umma_smem_desc(sb + Cfg::kRaw + 2 * Cfg::kBf, KC * 128, 1024, 2);
+      const uint64_t dB_blo = umma_smem_desc(sb + Cfg::kRaw + 3 * Cfg::kBf, KC * 128, 1024, 2);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int u = pair; u < p.total_units; u += npairs, ++it) {
+        const int split = u / p.ntiles;
+        const int c0 = split * p.chunks_per_split;
+        const int c1 = min(c0 + p.chunks_per_split, p.total_chunks);
+        const uint32_t b = (uint32_t)it & 1u, use = (uint32_t)it >> 1;
+        mbar_wait(&tmem_empty_bar[b], (use & 1u) ^ 1u);   // accumulator b drained by both CTAs' epilogue warps
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + b * 256u;
+        uint32_t acc = 0u;
+        for (int c = c0; c < c1; ++c) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t so = (uint64_t)((stage * Cfg::kStage) >> 4);
+            umma_f16_2sm(tacc, dA_blo + so, dB_bhi + so, idesc_bf, acc);
+            umma_f16_2sm(tacc, dA_bhi + so, dB_blo + so, idesc_bf, 1u);
+            umma_tf32_2sm(tacc, dA_tf + so, dB_tf + so, idesc_tf, 1u);
+            umma_tf32_2sm(tacc, dA_tf + so + 64, dB_tf + so + 64, idesc_tf, 1u);
+            umma_commit_2sm(&empty_bar[stage], 3);
+          }
+          acc = 1u;
+          __syncwarp();
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit_2sm(&tmem_full_bar[b], 3);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================= epilogue (both CTAs): own 128 accumulator rows x 256 columns per unit =================
+    const int g = warp & 3;
+    const int m = g * 32 + lane;
+    int it = 0;
+    for (int u = pair; u < p.total_units; u += npairs, ++it) {
+      int I, J, split;
+      decode(u, I, J, split);
+      const uint32_t b = (uint32_t)it & 1u, use = (uint32_t)it >> 1;
+      const size_t prow_idx = (size_t)(2 * I + rank) * 128 + m;
+      float* prow = p.partial + ((size_t)split * p.Dp2 + prow_idx) * p.Dp2;
+      mbar_wait(&tmem_full_bar[b], use & 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(g * 32) << 16) + b * 256u;
+#pragma unroll 1
+      for (int cc = 0; cc < 8; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tacc + cc * 32, r);
+        tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(prow + (size_t)(2 * J + (cc >> 2)) * 128 + (cc & 3) * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                               __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[b], 0u);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody frees TMEM / exits while the pair is still using either CTA's resources
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+// pre-pass of the persistent kernel: the bf16 copies of tf32_bf16_split_kernel AND the exact fp32 column sums of a slab of
+// rows per block (psum[slab][padded column], pad columns written as zero; summed in fixed order by reduce_colsums_kernel)
+template <int VEC>
+__global__ void __launch_bounds__(256)
+tf32_bf16_split_sums_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx, uint16_t* __restrict__ bhi,
+                            uint16_t* __restrict__ blo, int64_t ldo, int rows_per_slab, float* __restrict__ psum,
+                            int ldps, int pw) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * VEC;
+  if (c >= pw) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_slab;
+  const int64_t r1 = r0 + rows_per_slab < n ? r0 + rows_per_slab : n;
+  float acc[VEC];
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) acc[q] = 0.f;
+  if (c < d) {
+    if (VEC == 4) {
+#pragma unroll 4
+      for (int64_t r = r0; r < r1; ++r) {
+        const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float hi = __uint_as_float(__float_as_uint(vv[q]) & 0xFFFFE000u);
+          h[q] = bf16_rn_bits(hi);
+          l[q] = bf16_rn_bits(vv[q] - hi);
+          acc[q % VEC] += vv[q];
+        }
+        *reinterpret_cast<uint2*>(bhi + r * ldo + c) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+        *reinterpret_cast<uint2*>(blo + r * ldo + c) = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
+      }
+    } else {
+#pragma unroll 4
+      for (int64_t r = r0; r < r1; ++r) {
+        const float v = x[r * ldx + c];
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        bhi[r * ldo + c] = (uint16_t)bf16_rn_bits(hi);
+        blo[r * ldo + c] = (uint16_t)bf16_rn_bits(v - hi);
+        acc[0] += v;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) psum[(size_t)blockIdx.y * ldps + c + q] = acc[q];
+}
+
+// out[col] = sum over the S slabs of psum[s][col] in double, fixed order (32 strided chains, then a 32-term tail)
+__global__ void __launch_bounds__(1024)
+reduce_colsums_kernel(const float* __restrict__ psum, int S, int ldps, int Dp, double* __restrict__ out) {
+  __shared__ double sm[32][33];
+  const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  double acc = 0.0;
+  if (col < Dp)
+    for (int s = g; s < S; s += 32) acc += (double)psum[(size_t)s * ldps + col];
+  sm[g][cx] = acc;
+  __syncthreads();
+  if (g == 0 && col < Dp) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += sm[i][cx];
+    out[col] = t;
+  }
+}
+
 
 // 3xTF32 operand split.  The tensor core TRUNCATES its fp32 operands to TF32 (measured: tools/probe_trunc.py),
 // so the raw array itself serves as the "hi" operand (hi = x with the low 13 mantissa bits cleared) and only
@@ -969,7 +1220,7 @@ __global__ void __launch_bounds__(256) moments_dmma_kernel(const SimtParams p) {
 template <typename T>
 __global__ void reduce_partials_kernel(const T* __restrict__ partial, const T* __restrict__ partial_sum,
                                        int S, int Dp, int ldp, int blk, double* __restrict__ out) {
-  const size_t total = (size_t)Dp * Dp + Dp;
+  const size_t total = (size_t)Dp * Dp + (partial_sum ? Dp : 0);   // partial_sum == NULL: the sums come from elsewhere
   const size_t slab = (size_t)ldp * ldp;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
@@ -1100,6 +1351,7 @@ int sm_count() {
 struct TcPlan {
   int kc, total_chunks, num_splits, chunks_per_split, ntiles;
   int two_cta, nb2, ldp;  // ldp: leading dimension of the partial slabs (Dp, or nb2*256 for the CTA-pair kernel)
+  int sum_rows, sum_slabs;  // tf32x3b: rows per block / number of column-sum slabs of the pre-pass
   size_t partial_bytes, sum_bytes, split_bytes;  // split_bytes: hi/lo operand copies (3xTF32)
 };
 
@@ -1147,7 +1399,11 @@ TcPlan plan_tc(const ColumnLayout& L, int64_t n_rows, int mode) {
   P.partial_bytes = (size_t)P.num_splits * P.ldp * P.ldp * sizeof(float);
   P.sum_bytes = (size_t)P.num_splits * P.ldp * sizeof(float);
   P.split_bytes = 0;
+  P.sum_rows = P.sum_slabs = 0;
   if (mode == 3) {
+    P.sum_rows = (int)std::max<int64_t>(128, ceil_div(ceil_div(n_rows, 1024), 8) * 8);
+    P.sum_slabs = (int)ceil_div(n_rows, P.sum_rows);
+    P.sum_bytes = (size_t)std::max(P.num_splits, P.sum_slabs) * P.ldp * sizeof(float);
     for (int v = 0; v < L.n_views; ++v) {
       int64_t ldo = ceil_div(L.dims[v], 8) * 8;
       P.split_bytes += 2 * (size_t)n_rows * ldo * sizeof(uint16_t) + 512;   // bhi + blo
@@ -1216,6 +1472,7 @@ int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t*
     // ---- 3xTF32 with bf16 cross terms: raw view (tf32 hi by truncation) + bf16 copies of hi and lo ----
     TcParams3 prm;
     memset(&prm, 0, sizeof(prm));
+    const bool persist = tc_debug().x3b_oneshot == 0;
     for (int v = 0; v < L.n_views; ++v) {
       const float* x = static_cast<const float*>(views[v]);
       const int64_t ldo = ceil_div(L.dims[v], 8) * 8;
@@ -1223,9 +1480,23 @@ int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t*
       uint16_t* blo = bhi + (size_t)n_rows * ldo;
       splitbuf += align256(2 * (size_t)n_rows * ldo * sizeof(uint16_t));
       const int vec4 = (L.dims[v] % 4 == 0) && (lds[v] % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-      const int64_t total = n_rows * (int64_t)L.dims[v] / (vec4 ? 4 : 1);
-      int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
-      tf32_bf16_split_kernel<<<blocks, 256, 0, stream>>>(x, n_rows, L.dims[v], lds[v], bhi, blo, ldo, vec4);
+      if (persist) {
+        const int pw = L.poff[v + 1] - L.poff[v];   // padded width of this view (multiple of 128)
+        float* ps = d_partial_sum + L.poff[v];
+        if (vec4) {
+          dim3 grid((unsigned)ceil_div(pw, 1024), (unsigned)P.sum_slabs);
+          tf32_bf16_split_sums_kernel<4><<<grid, 256, 0, stream>>>(x, n_rows, L.dims[v], lds[v], bhi, blo, ldo, P.sum_rows,
+                                                                  ps, P.ldp, pw);
+        } else {
+          dim3 grid((unsigned)ceil_div(pw, 256), (unsigned)P.sum_slabs);
+          tf32_bf16_split_sums_kernel<1><<<grid, 256, 0, stream>>>(x, n_rows, L.dims[v], lds[v], bhi, blo, ldo, P.sum_rows,
+                                                                  ps, P.ldp, pw);
+        }
+      } else {
+        const int64_t total = n_rows * (int64_t)L.dims[v] / (vec4 ? 4 : 1);
+        int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
+        tf32_bf16_split_kernel<<<blocks, 256, 0, stream>>>(x, n_rows, L.dims[v], lds[v], bhi, blo, ldo, vec4);
+      }
       count_launches(1);
       CCAB_CUDA(cudaGetLastError());
       int rc = encode_view_map(&prm.maps[v], x, n_rows, L.dims[v], lds[v], P.kc);
@@ -1258,28 +1529,65 @@ int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t*
       prm.blk_view[b] = 0;
       prm.blk_col0[b] = 1 << 30;
     }
+    prm.ntiles = P.ntiles;
+    prm.total_units = P.ntiles * P.num_splits;
     using Cfg = Tc3Cfg<6>;
     static bool attr_done[64] = {};
+    static int max_pairs[64] = {};
     int dev = 0;
     CCAB_CUDA(cudaGetDevice(&dev));
+    const int di = (dev >= 0 && dev < 64) ? dev : 0;
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
       CCAB_CUDA(cudaFuncSetAttribute(moments_x3b_2cta_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+      CCAB_CUDA(cudaFuncSetAttribute(moments_x3b_persist_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::kSmem));
+      // how many CTA pairs are co-resident (GPCs with an odd number of free SMs cannot host a pair)
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(2 * (unsigned)(sm_count() / 2));
+      cfg.blockDim = dim3(kTcThreads);
+      cfg.dynamicSmemBytes = Cfg::kSmem;
+      cudaLaunchAttribute at;
+      memset(&at, 0, sizeof(at));
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = 2;
+      at.val.clusterDim.y = 1;
+      at.val.clusterDim.z = 1;
+      cfg.attrs = &at;
+      cfg.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, moments_x3b_persist_kernel<6>, &cfg) != cudaSuccess || nc <= 0) {
+        cudaGetLastError();
+        nc = sm_count() / 2;
+      }
+      max_pairs[di] = std::min(nc, sm_count() / 2);
       if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     if (g_prof_on) cudaEventRecord(g_prof_e0, stream);
-    moments_x3b_2cta_kernel<6><<<dim3(2 * P.ntiles, P.num_splits), kTcThreads, Cfg::kSmem, stream>>>(prm);
+    if (persist) {
+      const int npairs = std::max(1, std::min(max_pairs[di], prm.total_units));
+      moments_x3b_persist_kernel<6><<<dim3(2 * npairs), kTcThreads, Cfg::kSmem, stream>>>(prm);
+    } else {
+      moments_x3b_2cta_kernel<6><<<dim3(2 * P.ntiles, P.num_splits), kTcThreads, Cfg::kSmem, stream>>>(prm);
+    }
     count_launches(1);
     CCAB_CUDA(cudaGetLastError());
     if (g_prof_on) {
       cudaEventRecord(g_prof_e1, stream);
       g_prof_valid = true;
     }
-    const size_t total = (size_t)L.Dp * L.Dp + L.Dp;
+    const size_t total = (size_t)L.Dp * L.Dp + (persist ? 0 : L.Dp);
     int rblocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
-    reduce_partials_kernel<float><<<rblocks, 256, 0, stream>>>(d_partial, d_partial_sum, P.num_splits, L.Dp, P.ldp, kBlk,
-                                                              moments_out);
+    reduce_partials_kernel<float><<<rblocks, 256, 0, stream>>>(d_partial, persist ? nullptr : d_partial_sum, P.num_splits,
+                                                              L.Dp, P.ldp, kBlk, moments_out);
     count_launches(1);
     CCAB_CUDA(cudaGetLastError());
+    if (persist) {
+      reduce_colsums_kernel<<<(unsigned)ceil_div(L.Dp, 32), 1024, 0, stream>>>(d_partial_sum, P.sum_slabs, P.ldp, L.Dp,
+                                                                             moments_out + (size_t)L.Dp * L.Dp);
+      count_launches(1);
+      CCAB_CUDA(cudaGetLastError());
+    }
     return 0;
   }
 

@@ -73,6 +73,7 @@ struct TcDebug {
   int dry_run;      // CTA-pair kernel: skip TMA after the first ring fill (MMA-rate experiment; wrong results)
   int x3_split;     // 3xTF32 operand split: 0 = residual only (raw array is hi by truncation), 1 = round-to-nearest hi/lo
   int f64_simt;     // float64 inputs: 0 = DMMA kernel (default), 1 = CUDA-core FMA kernel
+  int x3b_oneshot;  // tf32x3b: 0 = persistent kernel, overlapped epilogue (default), 1 = one (tile, split) unit per CTA pair
 };
 TcDebug& tc_debug();
 

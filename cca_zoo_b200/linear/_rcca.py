@@ -1,6 +1,8 @@
 """rCCA / CCA / PLS on the GPU (mirrors cca_zoo/linear/_rcca.py, _cca.py, _pls.py)."""
 from __future__ import annotations
 
+import os
+
 from numbers import Real
 from typing import Any, ClassVar
 
@@ -77,16 +79,18 @@ class rCCA(BaseModel):
         if self.solver == "auto" and not (min(dims) >= 256 and n_local > max(dims)):
             return None
         k = min(int(self.latent_dimensions), dims[0], dims[1])
-        p = min(min(dims), k + max(32, k // 2))
+        over = int(os.environ.get("CCAB_FIT_OVERSAMPLE", "0")) or max(32, k // 2)
+        p = min(min(dims), k + over)
         if 4 * k > min(dims) or p > 128:
             return None
+        first = int(os.environ.get("CCAB_FIT_ITERS", "0")) or 5
         c_ = [float(x) for x in perview_parameter("c", self.c, 0.0, 2)]
         center = bool(self.center)
 
         def call(mom, dims_, n_host, n_dev, solve_dtype, iters):
             return ops.rcca_fit(mom, dims_, n_host, n_dev, center, c_, k, p, iters, solve_dtype)
 
-        return {"call": call, "k": k, "iters": [5, 20]}
+        return {"call": call, "k": k, "iters": [first, 20]}
 
     def _solve(self, C, dims, n_total):
         c_ = perview_parameter("c", self.c, 0.0, 2)
