@@ -119,14 +119,22 @@ __global__ void ritz_scale_kernel(T* __restrict__ U, int64_t ldu, int rows, int 
   U[(size_t)i * ldu + j] *= s > T(0) ? T(1) / s : T(0);
 }
 
-// stats[0] = || E - V diag(sig) ||_F^2, stats[1] = sig_0 (single block, fixed order: deterministic)
+// stats[0] = || E - V diag(sig) ||_F^2, stats[1] = sig_0 (sym: |sig_0| + shift).  Row slabs over the blocks, partial
+// sums added in block order by the last block to finish (counter zeroed by the caller): deterministic, one launch.
+constexpr int kResidBlocks = 64;
 template <typename T>
-__global__ void residual_kernel(const T* __restrict__ E, int64_t lde, const T* __restrict__ V, int64_t ldv, int rows,
-                                int k, const T* __restrict__ sig, double* __restrict__ stats) {
-  __shared__ double red[32];
+__global__ void __launch_bounds__(256)
+residual_kernel(const T* __restrict__ E, int64_t lde, const T* __restrict__ V, int64_t ldv, int rows, int k,
+                const T* __restrict__ sig, double shift, int sym, double* __restrict__ stats,
+                double* __restrict__ partial, unsigned* __restrict__ counter) {
+  __shared__ double red[8];
+  __shared__ bool last;
+  const int per = (rows + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * per;
+  const int nr = max(0, min(rows, r0 + per) - r0);
   double acc = 0.0;
-  for (int e = threadIdx.x; e < rows * k; e += blockDim.x) {
-    const int i = e / k, j = e % k;
+  for (int e = threadIdx.x; e < nr * k; e += blockDim.x) {
+    const int i = r0 + e / k, j = e % k;
     const double d = (double)E[(size_t)i * lde + j] - (double)V[(size_t)i * ldv + j] * (double)sig[j];
     acc += d * d;
   }
@@ -136,8 +144,17 @@ __global__ void residual_kernel(const T* __restrict__ E, int64_t lde, const T* _
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    stats[0] = t;
-    stats[1] = (double)sig[0];
+    partial[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    if (last) {
+      __threadfence();
+      double tot = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) tot += *reinterpret_cast<volatile double*>(partial + b);
+      stats[0] = tot;
+      stats[1] = sym ? fabs((double)sig[0]) + shift : (double)sig[0];
+      *counter = 0u;
+    }
   }
 }
 
@@ -325,6 +342,8 @@ int rcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
   unsigned* dmax = reinterpret_cast<unsigned*>(sm + 512);      // [2]
   double* tol = reinterpret_cast<double*>(sm + 1024);          // [2]
   double* stats = tol + 8;                                     // [2]
+  double* resid_part = reinterpret_cast<double*>(sm + 1280);   // [kResidBlocks]
+  unsigned* resid_cnt = reinterpret_cast<unsigned*>(sm + 1280 + 8 * kResidBlocks);
 
   CCAB_CUDA(cudaMemsetAsync(sm, 0, 2048, s));
   double* hdr = reinterpret_cast<double*>(res);
@@ -385,15 +404,32 @@ int rcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
     CCAB_CUDA(cudaGetLastError());
   }
   int info_slot = 2;
+  // With d2 <= d1 the Gram matrix A = T^T T fits the (now free) T1 buffer: one product per iteration instead of two.
+  // Only the SUBSPACE is iterated with A (its rounding moves the dominant subspace by ~eps); the Rayleigh-Ritz step
+  // and the residual below use T itself.
+  const bool gram = d2 <= d1 && iters >= 2;
+  if (gram) {
+    GemmArgs<T> g;
+    g.transa = 1; g.m = d2; g.n = d2; g.k = d1; g.A = Tm; g.lda = P.ldT; g.B = Tm; g.ldb = P.ldT; g.C = T1; g.ldc = P.ldT;
+    rc = xgemm<T>(g, s);
+    if (rc) return rc;
+  }
   for (int it = 0; it < iters; ++it) {
-    GemmArgs<T> a;   // Y = T Z
-    a.m = d1; a.n = p; a.k = d2; a.A = Tm; a.lda = P.ldT; a.B = Z; a.ldb = P.ldp; a.C = Y; a.ldc = P.ldp;
-    rc = xgemm<T>(a, s);
-    if (rc) return rc;
-    GemmArgs<T> b;   // Z2 = T^T Y
-    b.transa = 1; b.m = d2; b.n = p; b.k = d1; b.A = Tm; b.lda = P.ldT; b.B = Y; b.ldb = P.ldp; b.C = Z2; b.ldc = P.ldp;
-    rc = xgemm<T>(b, s);
-    if (rc) return rc;
+    if (gram) {
+      GemmArgs<T> a;   // Z2 = (T^T T) Z
+      a.m = d2; a.n = p; a.k = d2; a.A = T1; a.lda = P.ldT; a.B = Z; a.ldb = P.ldp; a.C = Z2; a.ldc = P.ldp;
+      rc = xgemm<T>(a, s);
+      if (rc) return rc;
+    } else {
+      GemmArgs<T> a;   // Y = T Z
+      a.m = d1; a.n = p; a.k = d2; a.A = Tm; a.lda = P.ldT; a.B = Z; a.ldb = P.ldp; a.C = Y; a.ldc = P.ldp;
+      rc = xgemm<T>(a, s);
+      if (rc) return rc;
+      GemmArgs<T> b;   // Z2 = T^T Y
+      b.transa = 1; b.m = d2; b.n = p; b.k = d1; b.A = Tm; b.lda = P.ldT; b.B = Y; b.ldb = P.ldp; b.C = Z2; b.ldc = P.ldp;
+      rc = xgemm<T>(b, s);
+      if (rc) return rc;
+    }
     rc = cholqr<T>(Z2, P.ldp, Z, P.ldp, d2, p, cq, infos + info_slot++, s);
     if (rc) return rc;
     if (it == iters - 1) {   // second pass on the last iterate: orthonormal to working precision
@@ -428,7 +464,7 @@ int rcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
     e.transa = 1; e.m = d2; e.n = k; e.k = d1; e.A = Tm; e.lda = P.ldT; e.B = U; e.ldb = P.ldk; e.C = E; e.ldc = P.ldk;
     rc = xgemm<T>(e, s);
     if (rc) return rc;
-    residual_kernel<T><<<1, 1024, 0, s>>>(E, P.ldk, V, P.ldk, d2, k, sig, stats);
+    residual_kernel<T><<<kResidBlocks, 256, 0, s>>>(E, P.ldk, V, P.ldk, d2, k, sig, 0.0, 0, stats, resid_part, resid_cnt);
     count_launches(1);
     CCAB_CUDA(cudaGetLastError());
   }
@@ -518,28 +554,6 @@ MccaPlan make_mcca_plan(const ColumnLayout& L, int k, int p) {
   return P;
 }
 
-// stats[0] = || E - Zr diag(theta) ||_F^2 over the D x k blocks, stats[1] = |theta_0| + shift
-template <typename T>
-__global__ void sym_residual_kernel(const T* __restrict__ E, int64_t lde, const T* __restrict__ Zr, int64_t ldz, int rows,
-                                    int k, const T* __restrict__ theta, double shift, double* __restrict__ stats) {
-  __shared__ double red[32];
-  double acc = 0.0;
-  for (int e = threadIdx.x; e < rows * k; e += blockDim.x) {
-    const int i = e / k, j = e % k;
-    const double d = (double)E[(size_t)i * lde + j] - (double)Zr[(size_t)i * ldz + j] * (double)theta[j];
-    acc += d * d;
-  }
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    stats[0] = t;
-    stats[1] = fabs((double)theta[0]) + shift;
-  }
-}
-
 template <typename T>
 __global__ void copy_vals_kernel(const T* __restrict__ src, T* __restrict__ dst, int k) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -599,6 +613,8 @@ int mcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
   unsigned* dmax = reinterpret_cast<unsigned*>(sm + 512);
   double* tol = reinterpret_cast<double*>(sm + 1024);          // [m]
   double* stats = tol + kMaxViews;                             // [2]
+  double* resid_part = reinterpret_cast<double*>(sm + 1280);   // [kResidBlocks]
+  unsigned* resid_cnt = reinterpret_cast<unsigned*>(sm + 1280 + 8 * kResidBlocks);
   CCAB_CUDA(cudaMemsetAsync(sm, 0, 2048, s));
   CCAB_CUDA(cudaMemsetAsync(K, 0, sizeof(T) * (size_t)D * P.ldC, s));
   double* hdr = reinterpret_cast<double*>(res);
@@ -712,7 +728,7 @@ int mcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
     e.transb = 1; e.m = D; e.n = k; e.k = p; e.A = Y; e.lda = P.ldp; e.B = Vy; e.ldb = P.ldp; e.C = E; e.ldc = P.ldk;
     rc = xgemm<T>(e, s);
     if (rc) return rc;
-    sym_residual_kernel<T><<<1, 1024, 0, s>>>(E, P.ldk, Zr, P.ldk, D, k, lam, shift, stats);
+    residual_kernel<T><<<kResidBlocks, 256, 0, s>>>(E, P.ldk, Zr, P.ldk, D, k, lam, shift, 1, stats, resid_part, resid_cnt);
     copy_vals_kernel<T><<<(unsigned)ceil_div(k, 128), 128, 0, s>>>(lam, vals, k);
     count_launches(2);
     CCAB_CUDA(cudaGetLastError());

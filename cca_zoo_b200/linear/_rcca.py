@@ -79,11 +79,11 @@ class rCCA(BaseModel):
         if self.solver == "auto" and not (min(dims) >= 256 and n_local > max(dims)):
             return None
         k = min(int(self.latent_dimensions), dims[0], dims[1])
-        over = int(os.environ.get("CCAB_FIT_OVERSAMPLE", "0")) or max(32, k // 2)
+        over = int(os.environ.get("CCAB_FIT_OVERSAMPLE", "0")) or max(16, k // 4)
         p = min(min(dims), k + over)
         if 4 * k > min(dims) or p > 128:
             return None
-        first = int(os.environ.get("CCAB_FIT_ITERS", "0")) or 5
+        first = int(os.environ.get("CCAB_FIT_ITERS", "0")) or 6
         c_ = [float(x) for x in perview_parameter("c", self.c, 0.0, 2)]
         center = bool(self.center)
 
