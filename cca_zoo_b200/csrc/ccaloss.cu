@@ -315,32 +315,35 @@ __global__ void __launch_bounds__(1024) ccaloss_small_fwd_kernel(const double* _
     I1[i * kLP + j] = I2[i * kLP + j] = (i == j) ? T(1) : T(0);
   }
   __syncthreads();
-  const double inv = 1.0 / (n - 1.0);
+  const double inv = 1.0 / (n - 1.0), inv_n = 1.0 / n;
   int notfinite = 0;
+#pragma unroll 4
   for (int e = threadIdx.x; e < d1 * d1; e += blockDim.x) {
     const int i = e / d1, j = e % d1;
     const double m = M[(size_t)min(i, j) * Dp + max(i, j)];
     notfinite |= !isfinite(m);
-    I1[i * kLP + j] = (T)((m - s[i] * s[j] / n) * inv) + (i == j ? eps : T(0));
+    I1[i * kLP + j] = (T)((m - s[i] * s[j] * inv_n) * inv) + (i == j ? eps : T(0));
   }
+#pragma unroll 4
   for (int e = threadIdx.x; e < d2 * d2; e += blockDim.x) {
     const int i = e / d2, j = e % d2;
     const double m = M[(size_t)(o2 + min(i, j)) * Dp + o2 + max(i, j)];
     notfinite |= !isfinite(m);
-    I2[i * kLP + j] = (T)((m - s[o2 + i] * s[o2 + j] / n) * inv) + (i == j ? eps : T(0));
+    I2[i * kLP + j] = (T)((m - s[o2 + i] * s[o2 + j] * inv_n) * inv) + (i == j ? eps : T(0));
   }
+#pragma unroll 4
   for (int e = threadIdx.x; e < d1 * d2; e += blockDim.x) {
     const int i = e / d2, j = e % d2;
     const double m = M[(size_t)i * Dp + o2 + j];
     notfinite |= !isfinite(m);
-    S12[i * kLP + j] = (T)((m - s[i] * s[o2 + j] / n) * inv);
+    S12[i * kLP + j] = (T)((m - s[i] * s[o2 + j] * inv_n) * inv);
   }
   if (notfinite) bad = 1;
   T* G11 = saved;
   T* Pout = saved + (size_t)d1 * d1;
   T* G22 = Pout + (size_t)d1 * d2;
   T* mean = G22 + (size_t)d2 * d2;
-  for (int i = threadIdx.x; i < d1 + d2; i += blockDim.x) mean[i] = (T)(s[i < d1 ? i : o2 + i - d1] / n);
+  for (int i = threadIdx.x; i < d1 + d2; i += blockDim.x) mean[i] = (T)(s[i < d1 ? i : o2 + i - d1] * inv_n);
   __syncthreads();
   chol_inverse_pair(I1, d1, I2, d2, Tm, Tm2, Pm, rowk, T(0.25) * eps, notpd);
   smem_matmul4<T, 0, 0>(I1, S12, Tm, d1, d2, d1);      // Tm  = A1 S12          (Q)

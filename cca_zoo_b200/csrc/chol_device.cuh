@@ -50,11 +50,13 @@ __device__ __forceinline__ void warp_trinv_32(const T* S, const T* dinv_s, T* X,
   const int lane = threadIdx.x & 31;
   T x[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    T s = (lane == i) ? T(1) : T(0);
+  for (int i = 0; i < 32; ++i) x[i] = (lane == i) ? T(1) : T(0);
+  // column-oriented substitution: x_i final -> the later right-hand sides update independently (short chain)
 #pragma unroll
-    for (int k = 0; k < i; ++k) s = fma(-S[(rb + i) * LD + rb + k], x[k], s);
-    x[i] = s * dinv_s[rb + i];
+  for (int i = 0; i < 32; ++i) {
+    x[i] *= dinv_s[rb + i];
+#pragma unroll
+    for (int j = i + 1; j < 32; ++j) x[j] = fma(-S[(rb + j) * LD + rb + i], x[i], x[j]);
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) X[(rb + i) * LD + rb + lane] = x[i];

@@ -61,6 +61,7 @@ __device__ __forceinline__ void smem_mm(T* Cm, int ldc, const T* Am, int lda, co
 #pragma unroll
       for (int j = 0; j < NT; ++j) acc[i][j] = T(0);
     const int kb = klo(r0), ke = khi(r0);
+#pragma unroll 4
     for (int k = kb; k < ke; ++k) {
       T a[4], b[NT];
 #pragma unroll
@@ -107,12 +108,29 @@ chol_diag_inv_kernel(T* __restrict__ A, int64_t lda, int64_t strideA, int nb, in
   const int tid = threadIdx.x;
   const T tol = (T)(piv_tol_dev ? piv_tol_dev[blockIdx.x] : piv_tol);
   if (tid == 0) bad = 0;
-  for (int e = tid; e < NB * NB; e += kDiagThreads) {
-    const int r = e / NB, c = e % NB;
-    T v = (r == c) ? T(1) : T(0);              // padding: identity
-    if (r < nb && c < nb) v = c <= r ? Ab[(size_t)r * lda + c] : T(0);
-    S[r * LD + c] = v;
-    X[r * LD + c] = T(0);
+  {
+    // 8 independent global loads in flight per thread (a load-then-store loop serialises on the memory latency);
+    // the strict upper triangle is loaded too (it lies inside the matrix) but never used
+    constexpr int kPer = NB * NB / kDiagThreads;
+    static_assert(kPer % 8 == 0 && NB * NB % kDiagThreads == 0, "load tiling");
+    for (int base = 0; base < kPer; base += 8) {
+      T v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = tid + (base + u) * kDiagThreads;
+        const int r = e / NB, c = e % NB;
+        v[u] = (r < nb && c < nb) ? Ab[(size_t)r * lda + c] : T(0);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = tid + (base + u) * kDiagThreads;
+        const int r = e / NB, c = e % NB;
+        T w = (r == c) ? T(1) : T(0);            // padding: identity
+        if (r < nb && c < nb) w = c <= r ? v[u] : T(0);
+        S[r * LD + c] = w;
+        X[r * LD + c] = T(0);
+      }
+    }
   }
   if (tid < NB) dinv_s[tid] = T(1);
   __syncthreads();
@@ -131,12 +149,13 @@ chol_diag_inv_kernel(T* __restrict__ A, int64_t lda, int64_t strideA, int nb, in
       T a[32];
 #pragma unroll
       for (int c = 0; c < 32; ++c) a[c] = row[c];
+      // column-oriented: once a[c] is final, the 31 - c later entries take their update independently (a short
+      // dependent chain of 32 scale + update steps instead of 496 chained FMAs)
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        T v = a[c];
+        a[c] *= dinv_s[rb + c];
 #pragma unroll
-        for (int k = 0; k < c; ++k) v = fma(-a[k], S[(rb + c) * LD + rb + k], v);   // warp broadcast
-        a[c] = v * dinv_s[rb + c];
+        for (int j = c + 1; j < 32; ++j) a[j] = fma(-a[c], S[(rb + j) * LD + rb + c], a[j]);   // warp broadcast
       }
 #pragma unroll
       for (int c = 0; c < 32; ++c) row[c] = a[c];

@@ -96,6 +96,7 @@ syevj_small_kernel(const T* __restrict__ A, int64_t lda, int64_t strideA, int n,
 
   // ---- load (symmetrised), V = I (own columns), ||H||_F^2 ----
   T fro_local = T(0);
+#pragma unroll 4
   for (int e = tid; e < N * N; e += kSmallThreads) {
     const int r = e / N, c = e % N;
     T v = T(0);
