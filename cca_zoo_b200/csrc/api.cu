@@ -680,6 +680,7 @@ int ccab_debug_set(const char* key, int value) {
   else if (!strcmp(key, "f64_simt")) d.f64_simt = value < 0 ? 0 : value;
   else if (!strcmp(key, "x3b_oneshot")) d.x3b_oneshot = value < 0 ? 0 : value;
   else if (!strcmp(key, "gemm_force_fma")) xgemm_force_fma() = value < 0 ? 0 : value;
+  else if (!strcmp(key, "gemm_split")) xgemm_split_enabled() = value < 0 ? 1 : value;
   else if (!strcmp(key, "jacobi_inner_sweeps")) jacobi_inner_sweeps() = value;
   else if (!strcmp(key, "jacobi_force_unfused")) jacobi_force_unfused() = value;
   else {

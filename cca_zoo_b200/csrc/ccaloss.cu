@@ -317,21 +317,18 @@ __global__ void __launch_bounds__(1024) ccaloss_small_fwd_kernel(const double* _
   __syncthreads();
   const double inv = 1.0 / (n - 1.0), inv_n = 1.0 / n;
   int notfinite = 0;
-#pragma unroll 4
   for (int e = threadIdx.x; e < d1 * d1; e += blockDim.x) {
     const int i = e / d1, j = e % d1;
     const double m = M[(size_t)min(i, j) * Dp + max(i, j)];
     notfinite |= !isfinite(m);
     I1[i * kLP + j] = (T)((m - s[i] * s[j] * inv_n) * inv) + (i == j ? eps : T(0));
   }
-#pragma unroll 4
   for (int e = threadIdx.x; e < d2 * d2; e += blockDim.x) {
     const int i = e / d2, j = e % d2;
     const double m = M[(size_t)(o2 + min(i, j)) * Dp + o2 + max(i, j)];
     notfinite |= !isfinite(m);
     I2[i * kLP + j] = (T)((m - s[o2 + i] * s[o2 + j] * inv_n) * inv) + (i == j ? eps : T(0));
   }
-#pragma unroll 4
   for (int e = threadIdx.x; e < d1 * d2; e += blockDim.x) {
     const int i = e / d2, j = e % d2;
     const double m = M[(size_t)i * Dp + o2 + j];

@@ -275,21 +275,23 @@ __global__ void __launch_bounds__(256) dgemm_mma_kernel(const GemmArgs<double> g
       }
 }
 
-// C (+ Ct) = alpha * sum_s partial[s] + beta * C, splits added in index order
-__global__ void splitk_reduce_kernel(const GemmArgs<double> g, int nsplit, const double* __restrict__ partial) {
+// C (+ Ct) = alpha * sum_s partial[s] + beta * C, splits added in index order; partial[bz][s] is m x ldp
+template <typename T>
+__global__ void splitk_reduce_kernel(const GemmArgs<T> g, int nsplit, const T* __restrict__ partial, int64_t ldp) {
   const size_t mn = (size_t)g.m * g.n;
+  const size_t slab = (size_t)g.m * ldp;
   const int bz = blockIdx.y, b1 = bz % g.batch, b2 = bz / g.batch;
-  double* C = g.C ? g.C + (size_t)b1 * g.strideC + (size_t)b2 * g.strideC2 : nullptr;
-  double* Ct = g.Ct ? g.Ct + (size_t)b1 * g.strideCt + (size_t)b2 * g.strideCt2 : nullptr;
-  const double* Pp = partial + (size_t)bz * nsplit * mn;
+  T* C = g.C ? g.C + (size_t)b1 * g.strideC + (size_t)b2 * g.strideC2 : nullptr;
+  T* Ct = g.Ct ? g.Ct + (size_t)b1 * g.strideCt + (size_t)b2 * g.strideCt2 : nullptr;
+  const T* Pp = partial + (size_t)bz * nsplit * slab;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < mn; e += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(e / g.n), c = (int)(e % g.n);
     if (g.lower_only && (c / 64) > (r / 64)) continue;
-    double acc = 0.0;
-    for (int s = 0; s < nsplit; ++s) acc += Pp[(size_t)s * mn + e];
-    double v = g.alpha * acc;
+    T acc = T(0);
+    for (int s = 0; s < nsplit; ++s) acc += Pp[(size_t)s * slab + (size_t)r * ldp + c];
+    T v = (T)g.alpha * acc;
     if (C) {
-      if (g.beta != 0.0) v += g.beta * C[(size_t)r * g.ldc + c];
+      if (g.beta != 0.0) v += (T)g.beta * C[(size_t)r * g.ldc + c];
       C[(size_t)r * g.ldc + c] = v;
     }
     if (Ct) Ct[(size_t)c * g.ldct + r] = v;
@@ -324,7 +326,7 @@ int gemm_dmma(const GemmArgs<double>& g, cudaStream_t stream) {
   if (nsplit > 1) {
     const size_t mn = (size_t)g.m * g.n;
     dim3 rgrid((unsigned)std::min<size_t>((mn + 255) / 256, 592), (unsigned)(g.batch * g.batch2));
-    splitk_reduce_kernel<<<rgrid, 256, 0, stream>>>(g, nsplit, partial);
+    splitk_reduce_kernel<double><<<rgrid, 256, 0, stream>>>(g, nsplit, partial, g.n);
     count_launches(1);
   }
   CCAB_CUDA(cudaGetLastError());
@@ -343,7 +345,38 @@ int xgemm<float>(const GemmArgs<float>& g, cudaStream_t stream) {
   a.Ct = g.Ct; a.ldct = g.ldct; a.strideCt = g.strideCt; a.strideCt2 = g.strideCt2;
   a.batch = g.batch; a.batch2 = g.batch2; a.lower_only = g.lower_only;
   const bool big = (int64_t)g.m * g.n * g.k >= ((int64_t)1 << 21) && g.k >= 16;   // >= 128^3: the pipeline fill (~9 us) pays off
-  if (big && !xgemm_force_fma() && tgemm_supported(a)) return tgemm(a, stream);
+  if (big && !xgemm_force_fma() && tgemm_supported(a)) {
+    // thin products (few 128 x 64 output tiles, long reduction) occupy a handful of SMs for k / 32 pipeline steps:
+    // when the caller lends scratch, run equal k-slices as a batch and add the partial tiles in slice order
+    // (deterministic).  Slices along a K-major operand overlap in memory (batch stride < row stride), which TMA
+    // tensor maps allow; should the encoder refuse, the unsplit product below still runs.
+    const int64_t tiles = ceil_div(g.m, 128) * ceil_div(g.n, 64);
+    if (g.splitk_ws && xgemm_split_enabled() && g.batch == 1 && g.batch2 == 1 && !g.lower_only && tiles <= 24 && g.k >= 512) {
+      int ns = (int)std::min<int64_t>(std::min<int64_t>(8, 148 / tiles), g.k / 128);
+      while (ns >= 2 && (g.k % ns != 0 || (g.k / ns) % 32 != 0)) --ns;
+      const int64_t ldp = ceil_div(g.n, 4) * 4;
+      const size_t need = (size_t)ns * g.m * ldp * sizeof(float);
+      if (ns >= 2 && need <= g.splitk_ws_bytes && (reinterpret_cast<uintptr_t>(g.splitk_ws) & 15) == 0) {
+        const int kc = g.k / ns;
+        TgemmArgs b = a;
+        b.k = kc; b.alpha = 1.0; b.beta = 0.0;
+        b.C = static_cast<float*>(g.splitk_ws); b.ldc = ldp; b.strideC = (int64_t)g.m * ldp;
+        b.Ct = nullptr;
+        b.batch = ns;
+        b.strideA = g.transa ? (int64_t)kc * g.lda : kc;
+        b.strideB = g.transb ? kc : (int64_t)kc * g.ldb;
+        if (tgemm_supported(b) && tgemm(b, stream) == 0) {
+          const size_t mn = (size_t)g.m * g.n;
+          splitk_reduce_kernel<float><<<(unsigned)std::min<size_t>((mn + 255) / 256, 592), 256, 0, stream>>>(
+              g, ns, static_cast<const float*>(g.splitk_ws), ldp);
+          count_launches(1);
+          CCAB_CUDA(cudaGetLastError());
+          return 0;
+        }
+      }
+    }
+    return tgemm(a, stream);
+  }
   return gemm_fma<float>(g, stream);
 }
 template <>
@@ -353,6 +386,10 @@ int xgemm<double>(const GemmArgs<double>& g, cudaStream_t stream) {
 }
 int& xgemm_force_fma() {
   static int v = 0;
+  return v;
+}
+int& xgemm_split_enabled() {
+  static int v = 1;
   return v;
 }
 

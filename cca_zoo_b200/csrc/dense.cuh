@@ -23,7 +23,7 @@ struct GemmArgs {
   int64_t ldct = 0, strideCt = 0, strideCt2 = 0;
   int batch = 1, batch2 = 1;
   int lower_only = 0;             // skip output tiles strictly above the diagonal
-  void* splitk_ws = nullptr;      // optional scratch: thin float64 products split their reduction over CTAs and
+  void* splitk_ws = nullptr;      // optional scratch: thin products split their reduction over CTAs / a batch and
   size_t splitk_ws_bytes = 0;     // add the partial tiles in a fixed order (deterministic); unused when too small
 };
 template <typename T>
@@ -31,6 +31,7 @@ int gemm_fma(const GemmArgs<T>& g, cudaStream_t stream);   // exact FMA tiles on
 template <typename T>
 int xgemm(const GemmArgs<T>& g, cudaStream_t stream);      // float: tcgen05 when TMA-addressable, else gemm_fma
 int& xgemm_force_fma();                                    // debug knob: 1 = never use the tensor pipe
+int& xgemm_split_enabled();                                // debug knob: 0 = never split thin float32 products over k
 
 // C (m x n, row-major, ldc) = alpha * op(A) * op(B) + beta * C ; op(X) = X or X^T, row-major storage.
 template <typename T>

@@ -238,8 +238,8 @@ int cholqr(const T* Zin, int64_t ldz, T* Zout, int64_t ldo, int rows, int p, con
 struct RccaPlan {
   int d1, d2, D, k, p;
   int64_t ldC, ld1, ld2, ldT, ldp, ldk;
-  size_t oC, oR, oLinv, oT1, oT, oZ, oZ2, oY, oG, oGinv, oH, oLam, oVy, oU, oV, oE, oPws, oSmall, total;
-  size_t pws_bytes;
+  size_t oC, oR, oLinv, oT1, oT, oZ, oZ2, oY, oG, oGinv, oH, oLam, oVy, oU, oV, oE, oPws, oSplit, oSmall, total;
+  size_t pws_bytes, split_bytes;
   size_t r_mean, r_sig, r_w1, r_w2, r_total;
 };
 
@@ -271,6 +271,8 @@ RccaPlan make_rcca_plan(int d1, int d2, int k, int p) {
   P.oE = take((size_t)d2 * P.ldk);
   P.pws_bytes = std::max(potrf_inv_workspace_bytes<T>(dm, 2), potrf_inv_workspace_bytes<T>(p, 1));
   P.oPws = o; o += al256(P.pws_bytes);
+  P.split_bytes = 8 * (size_t)dm * r4(std::max(p, k)) * sizeof(T);   // k-slices of the thin products (xgemm)
+  P.oSplit = o; o += al256(P.split_bytes);
   P.oSmall = o; o += 4096;   // flags, infos, dmax, tolerances, stats, device pointer tables
   P.total = o + 256;
   size_t r = sizeof(double) * kFitHeaderDoubles;
@@ -333,6 +335,9 @@ int rcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
   cq.pws = w + P.oPws;
   cq.pws_bytes = P.pws_bytes;
   cq.ldg = P.ldp;
+  cq.splitk_ws = w + P.oSplit;
+  cq.splitk_ws_bytes = P.split_bytes;
+  auto thin = [&](GemmArgs<T>& g) { g.splitk_ws = cq.splitk_ws; g.splitk_ws_bytes = cq.splitk_ws_bytes; };
   // small device scratch
   uint8_t* sm = w + P.oSmall;
   int* flags = reinterpret_cast<int*>(sm);                     // [1]
@@ -416,8 +421,9 @@ int rcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
   }
   for (int it = 0; it < iters; ++it) {
     if (gram) {
-      GemmArgs<T> a;   // Z2 = (T^T T) Z
-      a.m = d2; a.n = p; a.k = d2; a.A = T1; a.lda = P.ldT; a.B = Z; a.ldb = P.ldp; a.C = Z2; a.ldc = P.ldp;
+      GemmArgs<T> a;   // Z2 = (T^T T) Z, as A^T Z: the k-slices of both operands are then whole row blocks
+      a.transa = 1; a.m = d2; a.n = p; a.k = d2; a.A = T1; a.lda = P.ldT; a.B = Z; a.ldb = P.ldp; a.C = Z2; a.ldc = P.ldp;
+      thin(a);
       rc = xgemm<T>(a, s);
       if (rc) return rc;
     } else {
@@ -442,10 +448,12 @@ int rcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
   {
     GemmArgs<T> a;
     a.m = d1; a.n = p; a.k = d2; a.A = Tm; a.lda = P.ldT; a.B = Z; a.ldb = P.ldp; a.C = Y; a.ldc = P.ldp;
+    thin(a);
     rc = xgemm<T>(a, s);
     if (rc) return rc;
     GemmArgs<T> h;
     h.transa = 1; h.m = p; h.n = p; h.k = d1; h.A = Y; h.lda = P.ldp; h.B = Y; h.ldb = P.ldp; h.C = H; h.ldc = P.ldp;
+    thin(h);
     rc = xgemm<T>(h, s);
     if (rc) return rc;
     rc = syevj_small<T>(p, 1, H, P.ldp, 0, lam, p, Vy, P.ldp, 0, rr_info, s);
@@ -462,6 +470,7 @@ int rcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
     if (rc) return rc;
     GemmArgs<T> e;   // E = T^T U  (compare with V diag(sig))
     e.transa = 1; e.m = d2; e.n = k; e.k = d1; e.A = Tm; e.lda = P.ldT; e.B = U; e.ldb = P.ldk; e.C = E; e.ldc = P.ldk;
+    thin(e);
     rc = xgemm<T>(e, s);
     if (rc) return rc;
     residual_kernel<T><<<kResidBlocks, 256, 0, s>>>(E, P.ldk, V, P.ldk, d2, k, sig, 0.0, 0, stats, resid_part, resid_cnt);
@@ -472,10 +481,12 @@ int rcca_fit(const ColumnLayout& L, const double* moments, const double* n_dev, 
   {
     GemmArgs<T> a;
     a.transa = 1; a.m = d1; a.n = k; a.k = d1; a.A = Li1; a.lda = ldr1; a.B = U; a.ldb = P.ldk; a.C = W1; a.ldc = k;
+    thin(a);
     rc = xgemm<T>(a, s);
     if (rc) return rc;
     GemmArgs<T> b;
     b.transa = 1; b.m = d2; b.n = k; b.k = d2; b.A = Li2; b.lda = ldr2; b.B = V; b.ldb = P.ldk; b.C = W2; b.ldc = k;
+    thin(b);
     rc = xgemm<T>(b, s);
     if (rc) return rc;
   }

@@ -917,11 +917,11 @@ moments_x3b_persist_kernel(const __grid_constant__ TcParams3 p) {
 // pre-pass of the persistent kernel: the bf16 copies of tf32_bf16_split_kernel AND the exact fp32 column sums of a slab of
 // rows per block (psum[slab][padded column], pad columns written as zero; summed in fixed order by reduce_colsums_kernel)
 template <int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256)   // blockDim.x columns-groups (<= 256) of VEC columns, one slab of rows
 tf32_bf16_split_sums_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx, uint16_t* __restrict__ bhi,
                             uint16_t* __restrict__ blo, int64_t ldo, int rows_per_slab, float* __restrict__ psum,
                             int ldps, int pw) {
-  const int c = (blockIdx.x * 256 + threadIdx.x) * VEC;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (c >= pw) return;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_slab;
   const int64_t r1 = r0 + rows_per_slab < n ? r0 + rows_per_slab : n;
@@ -1401,7 +1401,7 @@ TcPlan plan_tc(const ColumnLayout& L, int64_t n_rows, int mode) {
   P.split_bytes = 0;
   P.sum_rows = P.sum_slabs = 0;
   if (mode == 3) {
-    P.sum_rows = (int)std::max<int64_t>(128, ceil_div(ceil_div(n_rows, 1024), 8) * 8);
+    P.sum_rows = (int)std::max<int64_t>(8, ceil_div(ceil_div(n_rows, 1024), 8) * 8);   // <= 1024 slabs, >= 8 rows each
     P.sum_slabs = (int)ceil_div(n_rows, P.sum_rows);
     P.sum_bytes = (size_t)std::max(P.num_splits, P.sum_slabs) * P.ldp * sizeof(float);
     for (int v = 0; v < L.n_views; ++v) {
@@ -1484,13 +1484,15 @@ int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t*
         const int pw = L.poff[v + 1] - L.poff[v];   // padded width of this view (multiple of 128)
         float* ps = d_partial_sum + L.poff[v];
         if (vec4) {
-          dim3 grid((unsigned)ceil_div(pw, 1024), (unsigned)P.sum_slabs);
-          tf32_bf16_split_sums_kernel<4><<<grid, 256, 0, stream>>>(x, n_rows, L.dims[v], lds[v], bhi, blo, ldo, P.sum_rows,
-                                                                  ps, P.ldp, pw);
+          const int bt = std::min(256, pw / 4);          // pw is a multiple of 128: 32 .. 256 threads, none idle
+          dim3 grid((unsigned)ceil_div(pw, 4 * bt), (unsigned)P.sum_slabs);
+          tf32_bf16_split_sums_kernel<4><<<grid, bt, 0, stream>>>(x, n_rows, L.dims[v], lds[v], bhi, blo, ldo, P.sum_rows,
+                                                                 ps, P.ldp, pw);
         } else {
-          dim3 grid((unsigned)ceil_div(pw, 256), (unsigned)P.sum_slabs);
-          tf32_bf16_split_sums_kernel<1><<<grid, 256, 0, stream>>>(x, n_rows, L.dims[v], lds[v], bhi, blo, ldo, P.sum_rows,
-                                                                  ps, P.ldp, pw);
+          const int bt = std::min(256, pw);
+          dim3 grid((unsigned)ceil_div(pw, bt), (unsigned)P.sum_slabs);
+          tf32_bf16_split_sums_kernel<1><<<grid, bt, 0, stream>>>(x, n_rows, L.dims[v], lds[v], bhi, blo, ldo, P.sum_rows,
+                                                                 ps, P.ldp, pw);
         }
       } else {
         const int64_t total = n_rows * (int64_t)L.dims[v] / (vec4 ? 4 : 1);
