@@ -6,8 +6,9 @@
 // are rotated at once.  Thread i < n/2 computes the rotation of pair i from the current 2 x 2 pivot block; then the
 // (n/2)^2 2 x 2 blocks  H[{p_i,q_i}, {p_j,q_j}]  are each updated by ONE thread (row rotation of pair i, column
 // rotation of pair j -- the blocks partition H, so there is no hazard) and the eigenvector rows are rotated
-// alongside.  Two block barriers per step, n - 1 steps per sweep; the off-diagonal mass seen during a sweep decides
-// convergence on the device.  Eigenvalues are returned in descending order with the eigenvectors as rows.
+// alongside.  Two block barriers per step, n - 1 steps per sweep, software-pipelined: the rotations of step t + 1 are
+// computed (by n/2 threads) while the other threads rotate the eigenvectors of step t; only the upper triangle of H
+// is kept.  The off-diagonal mass seen during a sweep decides convergence on the device.  Eigenvalues are returned in descending order with the eigenvectors as rows.
 //
 // Two-sided Jacobi resolves eigenvalues to eps * ||H|| (absolute): right for the Ritz problem, whose block is well
 // conditioned; the whitening eigenproblems (tiny eigenvalues matter relatively) stay on the one-sided solver of
@@ -24,7 +25,7 @@ namespace {
 constexpr int kSmallThreads = 512;
 constexpr int kSmallMaxN = 128;                      // (n/2)^2 2 x 2 blocks over 1024 threads: 4 per thread
 constexpr int kHB = ((kSmallMaxN / 2) * (kSmallMaxN / 2 + 1) / 2 + kSmallThreads - 1) / kSmallThreads;   // upper-triangle pair blocks per thread
-constexpr int kVB = (kSmallMaxN / 2) * (kSmallMaxN / 4) / kSmallThreads;   // V items per thread: (n/2) * ceil(n/4) <= 2048
+constexpr int kVB = ((kSmallMaxN / 2) * (kSmallMaxN / 4) + kSmallThreads - 64 - 1) / (kSmallThreads - 64);   // V items per non-rotation thread: (n/2) * ceil(n/4) <= 2048
 
 template <typename T>
 struct SmallEps;
@@ -86,8 +87,8 @@ syevj_small_kernel(const T* __restrict__ A, int64_t lda, int64_t strideA, int n,
   T* const V0 = H1 + (size_t)N * LD;
   T* const V1 = V0 + (size_t)N * LDV;
   T* red = V1 + (size_t)N * LDV;                         // [32]
-  Rot2<T>* rot = reinterpret_cast<Rot2<T>*>((reinterpret_cast<uintptr_t>(red + 32) + 15) & ~uintptr_t(15));   // [m2]
-  int* label = reinterpret_cast<int*>(rot + m2);         // [2][N] original index held by a position (-1: the bye)
+  Rot2<T>* rot = reinterpret_cast<Rot2<T>*>((reinterpret_cast<uintptr_t>(red + 32) + 15) & ~uintptr_t(15));   // [2][m2]
+  int* label = reinterpret_cast<int*>(rot + 2 * m2);     // [2][N] original index held by a position (-1: the bye)
   int* rank = label + 2 * N;                             // [N]
   __shared__ int done;
   const int tid = threadIdx.x;
@@ -130,70 +131,96 @@ syevj_small_kernel(const T* __restrict__ A, int64_t lda, int64_t strideA, int n,
       bi[u] = i; bj[u] = i + t;
     }
   }
+  // V items go to the threads that do not compute rotations (tid >= 64): the two run side by side in phase B
+  constexpr int kVThreads = kSmallThreads - 64;
   int vi[kVB], vc[kVB];
 #pragma unroll
   for (int u = 0; u < kVB; ++u) {
-    const int e = tid + u * kSmallThreads;
-    vi[u] = (ncol > 0 && e < m2 * ncol) ? e / ncol : -1;
-    vc[u] = (ncol > 0 && e < m2 * ncol) ? e % ncol : 0;
+    const int e = (tid - 64) + u * kVThreads;
+    const bool ok = tid >= 64 && ncol > 0 && e < m2 * ncol;
+    vi[u] = ok ? e / ncol : -1;
+    vc[u] = ok ? e % ncol : 0;
   }
 
-  int cur = 0, sweeps = 0;
+  // rotation of the adjacent pair (2 tid, 2 tid + 1) of Hs into rbuf[tid]; returns the off-diagonal mass it removes.
+  // Only the UPPER triangle of H is maintained (element (r, c) lives at [min][max]): half the scattered stores.
+  auto make_rotation = [&](const T* Hs, Rot2<T>* rbuf) -> T {
+    const int p = 2 * tid, q = p + 1;
+    const T hpp = Hs[p * LD + p], hqq = Hs[q * LD + q], hpq = Hs[p * LD + q];
+    T sn = T(0), tau = T(0);
+    // the whole CTA waits for these few threads: keep the dependent chain short (4 special-function ops).
+    // With z = (hqq - hpp) / 2 and r = hypot(z, hpq):  tan = hpq / (z + sign(z) r)  (the smaller root),
+    // c = 1 / sqrt(1 + tan^2), s = tan c, tau = s / (1 + c).  The rotation only has to be orthogonal to
+    // rounding (it is, by construction of the update from s and tau) and ANNIHILATE approximately: a pivot left
+    // at 1e-7 of its size is finished off by the next sweep, so fast reciprocals are good enough in float.
+    if (hpq * hpq > SmallEps<T>::v * SmallEps<T>::v * T(1e-4) * fabs(hpp * hqq) && hpq != T(0)) {
+      const T z = T(0.5) * (hqq - hpp);
+      const T r = fast_sqrt(fma(z, z, hpq * hpq));
+      const T tt = fast_div(hpq, z + (z >= T(0) ? r : -r));
+      const T c = fast_rsqrt(fma(tt, tt, T(1)));
+      sn = tt * c;
+      tau = fast_div(sn, T(1) + c);
+    }
+    Rot2<T> r;
+    r.s = sn; r.tau = tau;
+    rbuf[tid] = r;
+    return T(2) * hpq * hpq;
+  };
+
+  // Software pipeline: per step  A: H update with rot[rc] (all threads)  | barrier |
+  //                              B: rotations of the NEXT step from the new H (tid < m2) alongside the eigenvector
+  //                                 update of THIS step with rot[rc] (tid >= 64)                      | barrier |
+  // so the few threads of the rotation chain no longer stall the whole CTA.
+  int cur = 0, rc = 0, sweeps = 0;
+  T off_local = T(0), off_next = T(0);
+  if (tid < m2) off_local = make_rotation(H0, rot);
+  __syncthreads();
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-    T off_local = T(0);
     for (int t = 0; t < N - 1; ++t) {
       const T* H = cur ? H1 : H0;
       T* Hn = cur ? H0 : H1;
       const T* V = cur ? V1 : V0;
       T* Vn = cur ? V0 : V1;
-      if (tid < m2) {
-        const int p = 2 * tid, q = p + 1;
-        const T hpp = H[p * LD + p], hqq = H[q * LD + q], hpq = H[p * LD + q];
-        T s = T(0), tau = T(0);
-        off_local = fma(T(2) * hpq, hpq, off_local);
-        // the whole CTA waits for these few threads: keep the dependent chain short (4 special-function ops).
-        // With z = (hqq - hpp) / 2 and r = hypot(z, hpq):  tan = hpq / (z + sign(z) r)  (the smaller root),
-        // c = 1 / sqrt(1 + tan^2), s = tan c, tau = s / (1 + c).  The rotation only has to be orthogonal to
-        // rounding (it is, by construction of the update from s and tau) and ANNIHILATE approximately: a pivot left
-        // at 1e-7 of its size is finished off by the next sweep, so fast reciprocals are good enough in float.
-        if (hpq * hpq > SmallEps<T>::v * SmallEps<T>::v * T(1e-4) * fabs(hpp * hqq) && hpq != T(0)) {
-          const T z = T(0.5) * (hqq - hpp);
-          const T r = fast_sqrt(fma(z, z, hpq * hpq));
-          const T tt = fast_div(hpq, z + (z >= T(0) ? r : -r));
-          const T c = fast_rsqrt(fma(tt, tt, T(1)));
-          s = tt * c;
-          tau = fast_div(s, T(1) + c);
-        }
-        Rot2<T> r;
-        r.s = s; r.tau = tau;
-        rot[tid] = r;
-      }
+      const Rot2<T>* rcur = rot + rc * m2;
+      Rot2<T>* rnext = rot + (rc ^ 1) * m2;
+      // ---- phase A: H <- J^T H J on the upper-triangle pair blocks, written to the NEXT buffer at the positions the
+      // tournament moves them to (reads and writes never touch the same buffer) ----
       if (tid < N) label[(cur ^ 1) * N + rr_dest(tid, N)] = label[cur * N + tid];
-      __syncthreads();
-      // H <- J^T H J on the upper-triangle pair blocks, written (with their mirror images) to the NEXT buffer at the
-      // positions the tournament moves them to: reads and writes never touch the same buffer, one barrier per phase
 #pragma unroll
       for (int u = 0; u < kHB; ++u) {
         if (bi[u] < 0) continue;
         const int i = bi[u], j = bj[u];
-        const Rot2<T> ri = rot[i], rj = rot[j];
+        const Rot2<T> ri = rcur[i], rj = rcur[j];
         const T* h0 = H + (2 * i) * LD + 2 * j;
-        const T a = h0[0], b = h0[1], c_ = h0[LD], d = h0[LD + 1];
+        const T a = h0[0], b = h0[1], d = h0[LD + 1];
+        const T c_ = i == j ? b : h0[LD];             // the pivot block's lower element is its upper one
         const T a1 = a - ri.s * (c_ + ri.tau * a), c1 = c_ + ri.s * (a - ri.tau * c_);
         const T b1 = b - ri.s * (d + ri.tau * b), d1 = d + ri.s * (b - ri.tau * d);
         T a2 = a1 - rj.s * (b1 + rj.tau * a1), b2 = b1 + rj.s * (a1 - rj.tau * b1);
         T c2 = c1 - rj.s * (d1 + rj.tau * c1), d2 = d1 + rj.s * (c1 - rj.tau * d1);
-        if (i == j) {                               // pivot block: annihilated exactly, kept symmetric
-          if (ri.s != T(0)) { b2 = T(0); c2 = T(0); } else { c2 = b2; }
-        }
         const int rp = rr_dest(2 * i, N), rq = rr_dest(2 * i + 1, N), cp = rr_dest(2 * j, N), cq = rr_dest(2 * j + 1, N);
-        Hn[rp * LD + cp] = a2; Hn[rp * LD + cq] = b2; Hn[rq * LD + cp] = c2; Hn[rq * LD + cq] = d2;
-        if (i != j) { Hn[cp * LD + rp] = a2; Hn[cq * LD + rp] = b2; Hn[cp * LD + rq] = c2; Hn[cq * LD + rq] = d2; }
+        if (i == j) {                               // pivot block: annihilated exactly (kept when not rotated)
+          if (ri.s != T(0)) b2 = T(0);
+          Hn[rp * LD + rp] = a2;
+          Hn[rq * LD + rq] = d2;
+          Hn[min(rp, rq) * LD + max(rp, rq)] = b2;
+        } else {
+          Hn[min(rp, cp) * LD + max(rp, cp)] = a2;
+          Hn[min(rp, cq) * LD + max(rp, cq)] = b2;
+          Hn[min(rq, cp) * LD + max(rq, cp)] = c2;
+          Hn[min(rq, cq) * LD + max(rq, cq)] = d2;
+        }
+      }
+      __syncthreads();
+      // ---- phase B ----
+      if (tid < m2) {
+        const T o = make_rotation(Hn, rnext);
+        if (t == N - 2) off_next = o; else off_local += o;   // the last one already belongs to the next sweep
       }
 #pragma unroll
       for (int u = 0; u < kVB; ++u) {
         if (vi[u] < 0) continue;
-        const Rot2<T> r = rot[vi[u]];
+        const Rot2<T> r = rcur[vi[u]];
         const int p = 2 * vi[u];
         const T vp = V[p * LDV + vc[u]], vq = V[(p + 1) * LDV + vc[u]];
         Vn[rr_dest(p, N) * LDV + vc[u]] = vp - r.s * (vq + r.tau * vp);
@@ -201,6 +228,7 @@ syevj_small_kernel(const T* __restrict__ A, int64_t lda, int64_t strideA, int n,
       }
       __syncthreads();
       cur ^= 1;
+      rc ^= 1;
     }
     ++sweeps;
     for (int o = 16; o > 0; o >>= 1) off_local += __shfl_xor_sync(0xffffffffu, off_local, o);
@@ -213,6 +241,8 @@ syevj_small_kernel(const T* __restrict__ A, int64_t lda, int64_t strideA, int n,
     }
     __syncthreads();
     if (done) break;
+    off_local = off_next;
+    off_next = T(0);
   }
 
   // ---- sort (rank by counting, descending; ties by position) and write ----
@@ -250,7 +280,7 @@ template <typename T>
 size_t small_smem_bytes(int n) {
   const int N = (n + 1) & ~1;
   const int cw = (n + small_nsplit(n) - 1) / small_nsplit(n);
-  return sizeof(T) * (2 * (size_t)N * (N + 2) + 2 * (size_t)N * (cw + 1) + 32) + sizeof(Rot2<T>) * (size_t)(N / 2) +
+  return sizeof(T) * (2 * (size_t)N * (N + 2) + 2 * (size_t)N * (cw + 1) + 32) + sizeof(Rot2<T>) * (size_t)N +
          sizeof(int) * 3 * (size_t)N + 128;
 }
 
