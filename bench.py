@@ -406,7 +406,7 @@ def run_ours(args):
             pass
         if k1:
             ach = flops / (k1 * 1e-3) / 1e12
-            kname = {"tf32x3b": "moments_x3b_2cta_kernel (2 bf16 cross-term + 2 tf32 MMAs per 16 samples)",
+            kname = {"tf32x3b": "moments_x3b_persist_kernel (persistent CTA pairs; 2 bf16 cross-term + 2 tf32 MMAs per 16 samples)",
                      "tf32x3": "moments_tf32_2cta_kernel<X3> (3 tf32 MMAs per k-step)"}.get(
                          args.precision, "moments_tf32_2cta_kernel")
             roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": bf16 / 2,
