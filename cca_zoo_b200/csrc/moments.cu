@@ -1227,8 +1227,19 @@ __global__ void reduce_partials_kernel(const T* __restrict__ partial, const T* _
     double acc = 0.0;
     if (i < (size_t)Dp * Dp) {
       const int r = (int)(i / Dp), c = (int)(i % Dp);
-      if (r / blk <= c / blk)
-        for (int s = 0; s < S; ++s) acc += (double)partial[(size_t)s * slab + (size_t)r * ldp + c];
+      if (r / blk <= c / blk) {
+        // 8 independent loads in flight, added in split order (the sum is the same as the plain loop's)
+        const T* src = partial + (size_t)r * ldp + c;
+        int s = 0;
+        for (; s + 8 <= S; s += 8) {
+          T v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = src[(size_t)(s + u) * slab];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc += (double)v[u];
+        }
+        for (; s < S; ++s) acc += (double)src[(size_t)s * slab];
+      }
     } else {
       const size_t j = i - (size_t)Dp * Dp;
       for (int s = 0; s < S; ++s) acc += (double)partial_sum[(size_t)s * ldp + j];
@@ -1981,6 +1992,7 @@ __global__ void pilot_kernel(const T* __restrict__ X, int64_t rows, int d, int64
   double a = 0.0, b = 0.0;
   const double ref = j < d ? (double)X[j] : 0.0;     // first row as a provisional origin: the pilot itself must not cancel
   if (j < d)
+#pragma unroll 8
     for (int64_t i = rg; i < rows; i += 32) {
       const double v = (double)X[i * ld + j] - ref;
       a += v;
