@@ -1992,7 +1992,6 @@ __global__ void pilot_kernel(const T* __restrict__ X, int64_t rows, int d, int64
   double a = 0.0, b = 0.0;
   const double ref = j < d ? (double)X[j] : 0.0;     // first row as a provisional origin: the pilot itself must not cancel
   if (j < d)
-#pragma unroll 8
     for (int64_t i = rg; i < rows; i += 32) {
       const double v = (double)X[i * ld + j] - ref;
       a += v;
