@@ -50,14 +50,10 @@ struct DiagCfg<double> {
 // warp broadcasts, the B values conflict-free; 4 + NT loads per 4 * NT FMAs.  BT: B(k, c) = Bm[c * ldb + k] (the
 // A A^T form of the trailing update) else Bm[k * ldb + c].  tri: 0 none, 1 = only c <= r is needed (lower part),
 // klo / khi: per-tile reduction bounds for triangular operands (see the callers).
-// wfirst: the first warp that takes part (warps below it return at once -- they do something else meanwhile);
-// diag_off: with lower_only, keep c <= r + diag_off (the tile's origin sits diag_off rows below the diagonal).
 template <typename T, int NT, bool BT, typename KLo, typename KHi>
 __device__ __forceinline__ void smem_mm(T* Cm, int ldc, const T* Am, int lda, const T* Bm, int ldb, int M, int Nc,
-                                        T sign, bool accumulate, bool lower_only, KLo klo, KHi khi, int nthreads,
-                                        int wfirst = 0, int diag_off = 0) {
-  const int warp = (int)(threadIdx.x >> 5) - wfirst, lane = threadIdx.x & 31, nwarps = (nthreads >> 5) - wfirst;
-  if (warp < 0) return;
+                                        T sign, bool accumulate, bool lower_only, KLo klo, KHi khi, int nthreads) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = nthreads >> 5;
   for (int r0 = warp * 4; r0 < M; r0 += nwarps * 4) {
     T acc[4][NT];
 #pragma unroll
@@ -85,7 +81,7 @@ __device__ __forceinline__ void smem_mm(T* Cm, int ldc, const T* Am, int lda, co
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         const int r = r0 + i, c = lane + 32 * j;
-        if (r < M && c < Nc && (!lower_only || c <= r + diag_off)) {
+        if (r < M && c < Nc && (!lower_only || c <= r)) {
           const T v = sign * acc[i][j];
           Cm[r * ldc + c] = accumulate ? Cm[r * ldc + c] + v : v;
         }
@@ -140,10 +136,11 @@ chol_diag_inv_kernel(T* __restrict__ A, int64_t lda, int64_t strideA, int nb, in
   __syncthreads();
 
   const int nsub = (nb + 31) / 32;
-  if (tid < 32) warp_chol_32<T, LD>(S, dinv_s, 0, nb, j0, tol, &bad);
-  __syncthreads();
-  for (int jb = 0; jb + 1 < nsub; ++jb) {
+  for (int jb = 0; jb < nsub; ++jb) {
     const int rb = jb * 32;
+    if (tid < 32) warp_chol_32<T, LD>(S, dinv_s, rb, nb, j0, tol, &bad);
+    __syncthreads();
+    if (jb + 1 >= nsub) break;                  // nothing below / to the right
     const int r0 = rb + 32;
     const int R = nsub * 32 - r0;               // rows that hold data
     // ---- panel: row r of the block column <- a_r L_jj^-T by forward substitution, one thread per row ----
@@ -164,16 +161,9 @@ chol_diag_inv_kernel(T* __restrict__ A, int64_t lda, int64_t strideA, int nb, in
       for (int c = 0; c < 32; ++c) row[c] = a[c];
     }
     __syncthreads();
-    // ---- trailing update S[r][c] -= sum_k P[r][k] P[c][k] (lower part), with look-ahead: the next diagonal block
-    // first, then warp 0 factors it WHILE the other warps update the rest of the trailing matrix ----
-    smem_mm<T, 1, true>(S + r0 * LD + r0, LD, S + r0 * LD + rb, LD, S + r0 * LD + rb, LD, 32, 32, T(-1), true, true,
-                        [](int) { return 0; }, [](int) { return 32; }, kDiagThreads);
-    __syncthreads();
-    if (tid < 32) warp_chol_32<T, LD>(S, dinv_s, r0, nb, j0, tol, &bad);
-    if (R > 32)
-      smem_mm<T, NSUB - 1, true>(S + (r0 + 32) * LD + r0, LD, S + (r0 + 32) * LD + rb, LD, S + r0 * LD + rb, LD, R - 32,
-                                 R, T(-1), true, true, [](int) { return 0; }, [](int) { return 32; }, kDiagThreads, 1,
-                                 32);
+    // ---- trailing update (lower part): S[r][c] -= sum_k P[r][k] P[c][k] ----
+    smem_mm<T, NSUB - 1, true>(S + r0 * LD + r0, LD, S + r0 * LD + rb, LD, S + r0 * LD + rb, LD, R, R, T(-1), true,
+                               true, [](int) { return 0; }, [](int) { return 32; }, kDiagThreads);
     __syncthreads();
   }
 
