@@ -962,7 +962,8 @@ tf32_bf16_split_sums_kernel(const float* __restrict__ x, int64_t n, int d, int64
 
 // out[col] = sum over the S slabs of psum[s][col] in double, fixed order (32 strided chains, then a 32-term tail)
 __global__ void __launch_bounds__(1024)
-reduce_colsums_kernel(const float* __restrict__ psum, int S, int ldps, int Dp, double* __restrict__ out) {
+reduce_colsums_kernel(const float* __restrict__ psum, int S, int ldps, int Dp, double* __restrict__ out,
+                      int accumulate) {
   __shared__ double sm[32][33];
   const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;
@@ -975,7 +976,7 @@ reduce_colsums_kernel(const float* __restrict__ psum, int S, int ldps, int Dp, d
     double t = 0.0;
 #pragma unroll
     for (int i = 0; i < 32; ++i) t += sm[i][cx];
-    out[col] = t;
+    out[col] = accumulate ? out[col] + t : t;
   }
 }
 
@@ -1219,7 +1220,8 @@ __global__ void __launch_bounds__(256) moments_dmma_kernel(const SimtParams p) {
 // ldp: leading dimension (and row count) of each partial slab, >= Dp
 template <typename T>
 __global__ void reduce_partials_kernel(const T* __restrict__ partial, const T* __restrict__ partial_sum,
-                                       int S, int Dp, int ldp, int blk, double* __restrict__ out) {
+                                       int S, int Dp, int ldp, int blk, double* __restrict__ out,
+                                       int accumulate = 0) {
   const size_t total = (size_t)Dp * Dp + (partial_sum ? Dp : 0);   // partial_sum == NULL: the sums come from elsewhere
   const size_t slab = (size_t)ldp * ldp;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
@@ -1244,7 +1246,7 @@ __global__ void reduce_partials_kernel(const T* __restrict__ partial, const T* _
       const size_t j = i - (size_t)Dp * Dp;
       for (int s = 0; s < S; ++s) acc += (double)partial_sum[(size_t)s * ldp + j];
     }
-    out[i] = acc;
+    out[i] = accumulate ? out[i] + acc : acc;
   }
 }
 
@@ -1429,6 +1431,16 @@ TcPlan plan_tc(const ColumnLayout& L, int64_t n_rows, int mode) {
   return P;
 }
 
+// rows one pass of the 3xTF32 modes may take: the split count that keeps the partials below 2 GiB (<= 256) times the
+// 2048-sample accumulator run
+int64_t tc_rows_cap(const ColumnLayout& L, int mode) {
+  if (mode == 0) return (int64_t)1 << 31;
+  const int64_t ldp = (tc_debug().variant != 1 || mode == 3) ? (int64_t)((L.nblocks + 1) / 2) * 256 : L.Dp;
+  const int64_t slab = ldp * ldp * (int64_t)sizeof(float);
+  const int64_t max_splits = std::max<int64_t>(1, std::min<int64_t>(256, ((int64_t)2 << 30) / slab));
+  return max_splits * 2048;
+}
+
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct SimtPlan {
@@ -1457,19 +1469,45 @@ size_t moments_workspace_bytes(int dtype, int precision, const ColumnLayout& L, 
     size_t el = dtype == 1 ? 8 : 4;
     return align256((size_t)P.num_splits * L.Dp * L.Dp * el) + align256((size_t)P.num_splits * L.Dp * el);
   }
-  TcPlan P = plan_tc(L, n_rows, precision);
+  TcPlan P = plan_tc(L, std::min(n_rows, tc_rows_cap(L, precision)), precision);   // sized for one pass
   return align256(P.partial_bytes) + align256(P.sum_bytes) + align256(P.split_bytes) + 256;
 }
 
+namespace {
+int moments_tf32_pass(const ColumnLayout& L, const void* const* views, const int64_t* lds, int64_t n_rows, int mode,
+                      double* moments_out, void* ws, size_t ws_bytes, cudaStream_t stream, int accumulate);
+}
+
+// The 3xTF32 modes bound one accumulator run to 2048 samples (plan_tc) and the split partials to 2 GiB: inputs longer
+// than tc_rows_cap() rows are processed in equal passes whose float64 moments add up in moments_out (the moments are
+// additive over rows; operands and partials are sized for one pass).
 int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t* lds, int64_t n_rows, int mode,
                  double* moments_out, void* ws, size_t ws_bytes, cudaStream_t stream) {
-  const bool x3 = mode == 1;
   CCAB_CHECK_ARG(n_rows >= 1 && n_rows < (int64_t)1 << 31, "n_rows out of range");
   {
     int dev = 0;   // bind the primary context to this thread before the driver-API tensor-map encoder (see tgemm.cu)
     CCAB_CUDA(cudaGetDevice(&dev));
     CCAB_CUDA(cudaSetDevice(dev));
   }
+  const int64_t cap = tc_rows_cap(L, mode);
+  if (n_rows <= cap) return moments_tf32_pass(L, views, lds, n_rows, mode, moments_out, ws, ws_bytes, stream, 0);
+  const int64_t npass = ceil_div(n_rows, cap);
+  const int64_t per = std::min(cap, ceil_div(ceil_div(n_rows, npass), 2048) * 2048);
+  int pass = 0;
+  for (int64_t r0 = 0; r0 < n_rows; r0 += per, ++pass) {
+    const void* sub[kMaxViews];
+    for (int v = 0; v < L.n_views; ++v) sub[v] = static_cast<const float*>(views[v]) + r0 * lds[v];
+    int rc = moments_tf32_pass(L, sub, lds, std::min(per, n_rows - r0), mode, moments_out, ws, ws_bytes, stream,
+                               pass > 0);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+namespace {
+int moments_tf32_pass(const ColumnLayout& L, const void* const* views, const int64_t* lds, int64_t n_rows, int mode,
+                      double* moments_out, void* ws, size_t ws_bytes, cudaStream_t stream, int accumulate) {
+  const bool x3 = mode == 1;
   TcPlan P = plan_tc(L, n_rows, mode);
   const size_t need = align256(P.partial_bytes) + align256(P.sum_bytes) + align256(P.split_bytes) + 256;
   CCAB_CHECK_ARG(ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
@@ -1592,12 +1630,12 @@ int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t*
     const size_t total = (size_t)L.Dp * L.Dp + (persist ? 0 : L.Dp);
     int rblocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
     reduce_partials_kernel<float><<<rblocks, 256, 0, stream>>>(d_partial, persist ? nullptr : d_partial_sum, P.num_splits,
-                                                              L.Dp, P.ldp, kBlk, moments_out);
+                                                              L.Dp, P.ldp, kBlk, moments_out, accumulate);
     count_launches(1);
     CCAB_CUDA(cudaGetLastError());
     if (persist) {
       reduce_colsums_kernel<<<(unsigned)ceil_div(L.Dp, 32), 1024, 0, stream>>>(d_partial_sum, P.sum_slabs, P.ldp, L.Dp,
-                                                                             moments_out + (size_t)L.Dp * L.Dp);
+                                                                             moments_out + (size_t)L.Dp * L.Dp, accumulate);
       count_launches(1);
       CCAB_CUDA(cudaGetLastError());
     }
@@ -1738,10 +1776,11 @@ int moments_tf32(const ColumnLayout& L, const void* const* views, const int64_t*
   const size_t total = (size_t)L.Dp * L.Dp + L.Dp;
   int rblocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
   reduce_partials_kernel<float><<<rblocks, 256, 0, stream>>>(d_partial, d_partial_sum, P.num_splits, L.Dp, P.ldp,
-                                                            kBlk, moments_out); count_launches(1);
+                                                            kBlk, moments_out, accumulate); count_launches(1);
   CCAB_CUDA(cudaGetLastError());
   return 0;
 }
+}  // namespace
 
 template <typename T>
 int moments_simt(const ColumnLayout& L, const void* const* views, const int64_t* lds, int64_t n_rows,

@@ -58,6 +58,44 @@ def test_moments_and_covariance(precision, dtype, rtol, n, dims):
     assert (mean.cpu() - ref_mean.cpu()).abs().max() < mtol * (1 + ref_mean.abs().max())
 
 
+@pytest.mark.parametrize("precision", ["tf32x3b", "tf32x3"])
+def test_inputs_longer_than_one_pass_keep_the_accumulator_run_bound(precision):
+    """the 2048-sample accumulator run of the 3xTF32 modes used to stretch once the split count hit its
+    cap (n > 256 * 2048 rows), letting the round-toward-zero drift of TMEM back in.  Long inputs are now processed in
+    equal passes whose float64 moments add up: the result IS the sum of the passes' moments (bitwise), and as accurate
+    as a short input's."""
+    from cca_zoo_b200 import ops
+
+    n, dims = 1_200_000, [64, 64]          # cap = 256 splits x 2048 rows = 524288 rows per pass -> 3 passes
+    cap = 256 * 2048
+    npass = -(-n // cap)
+    per = min(cap, -(-(-(-n // npass)) // 2048) * 2048)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    views = [torch.randn(n, d, generator=g, device="cuda") + 0.25 for d in dims]
+    mom = ops.moments(views, precision=precision)
+    parts = None
+    for r0 in range(0, n, per):
+        m = ops.moments([v[r0:r0 + per] for v in views], precision=precision)
+        parts = m if parts is None else parts + m
+    assert torch.equal(mom, parts), "the passes must add up to the one-call result exactly"
+    Dp = 256
+    M = mom[:Dp * Dp].view(Dp, Dp)
+    X = torch.cat(views, dim=1).double()
+    ref_diag = (X * X).sum(dim=0)
+    got = torch.cat([torch.diagonal(M)[:64], torch.diagonal(M)[128:192]])
+    rel = ((got - ref_diag) / ref_diag).cpu().numpy()
+    assert np.abs(rel).max() < 5e-5, f"diagonal of the raw moments off by {np.abs(rel).max():.2e}"
+    s = mom[Dp * Dp:Dp * Dp + Dp]
+    ref_s = X.sum(dim=0)
+    got_s = torch.cat([s[:64], s[128:192]])
+    assert ((got_s - ref_s).abs() / ref_s.abs()).max() < 1e-5
+    Cm, _ = ops.covariance(mom, dims, n, center=True, dtype=torch.float64)
+    Xc = X - X.mean(dim=0)
+    ref = (Xc.T @ Xc / (n - 1)).cpu().numpy()
+    scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+    assert (np.abs(Cm.cpu().numpy() - ref) / scale).max() < 5e-5
+
+
 def test_moments_uncentred_and_nonzero_mean():
     from cca_zoo_b200 import ops
 
