@@ -141,7 +141,7 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
 template <int TA, int TB>
 __global__ void __launch_bounds__(256) dgemm_mma_kernel(const GemmArgs<double> g, int nsplit, int kchunk,
                                                         double* __restrict__ partial) {
-  constexpr int KC = 16, LDS = 64 + 8;
+  constexpr int KC = 16, LDS = 64 + 4;   // row stride = 8 banks (mod 32): the 4 k-rows x 8 columns of a fragment load hit 32 distinct banks
   __shared__ double As[2][KC][LDS];
   __shared__ double Bs[2][KC][LDS];
   const int m = g.m, n = g.n;

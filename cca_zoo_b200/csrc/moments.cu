@@ -1138,7 +1138,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 
 __global__ void __launch_bounds__(256) moments_dmma_kernel(const SimtParams p) {
   constexpr int KC = 16;
-  constexpr int LDS = 64 + 8;
+  constexpr int LDS = 64 + 4;   // row stride = 8 banks (mod 32): fragment loads (4 k-rows x 8 columns) are conflict-free
   __shared__ double As[KC][LDS];
   __shared__ double Bs[KC][LDS];
   int t = blockIdx.x, bi = 0, rowlen = p.nb64;
@@ -1172,16 +1172,30 @@ __global__ void __launch_bounds__(256) moments_dmma_kernel(const SimtParams p) {
   double csum = 0.0;                            // column sums: thread c < 64 of a diagonal tile sums column c
 
   const int lc = threadIdx.x & 63, lr = threadIdx.x >> 6;
-  for (int64_t r = r0; r < r1; r += KC) {
+  // register prefetch: the global loads of chunk c + 1 are in flight while the tensor pipe works on chunk c
+  double ra[KC / 4], rb[KC / 4];
+  auto gload = [&](int64_t r) {
 #pragma unroll
     for (int i = 0; i < KC / 4; ++i) {
-      const int kr = lr + 4 * i;
-      const int64_t row = r + kr;
+      const int64_t row = r + lr + 4 * i;
       const bool rv = row < r1;
-      As[kr][lc] = (rv && cA + lc < dA) ? XA[row * ldA + cA + lc] : 0.0;
-      Bs[kr][lc] = (rv && cB + lc < dB) ? XB[row * ldB + cB + lc] : 0.0;
+      ra[i] = (rv && cA + lc < dA) ? XA[row * ldA + cA + lc] : 0.0;
+      rb[i] = (rv && cB + lc < dB) ? XB[row * ldB + cB + lc] : 0.0;
     }
-    __syncthreads();
+  };
+  auto sstore = [&]() {
+#pragma unroll
+    for (int i = 0; i < KC / 4; ++i) {
+      As[lr + 4 * i][lc] = ra[i];
+      Bs[lr + 4 * i][lc] = rb[i];
+    }
+  };
+  gload(r0);
+  sstore();
+  __syncthreads();
+  for (int64_t r = r0; r < r1; r += KC) {
+    const bool more = r + KC < r1;
+    if (more) gload(r + KC);
 #pragma unroll
     for (int k0 = 0; k0 < KC; k0 += 4) {
       double a[4], b[2];
@@ -1199,6 +1213,10 @@ __global__ void __launch_bounds__(256) moments_dmma_kernel(const SimtParams p) {
       for (int k = 0; k < KC; ++k) csum += Bs[k][threadIdx.x];
     }
     __syncthreads();
+    if (more) {
+      sstore();
+      __syncthreads();
+    }
   }
   double* P = static_cast<double*>(p.partial) + (size_t)split * p.Dp * p.Dp;
 #pragma unroll
