@@ -1139,8 +1139,8 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 __global__ void __launch_bounds__(256) moments_dmma_kernel(const SimtParams p) {
   constexpr int KC = 16;
   constexpr int LDS = 64 + 4;   // row stride = 8 banks (mod 32): fragment loads (4 k-rows x 8 columns) are conflict-free
-  __shared__ double As[KC][LDS];
-  __shared__ double Bs[KC][LDS];
+  __shared__ double As[2][KC][LDS];   // double buffered: one block barrier per 16-row chunk
+  __shared__ double Bs[2][KC][LDS];
   int t = blockIdx.x, bi = 0, rowlen = p.nb64;
   while (t >= rowlen) { t -= rowlen; ++bi; --rowlen; }
   const int bj = bi + t;
@@ -1183,26 +1183,27 @@ __global__ void __launch_bounds__(256) moments_dmma_kernel(const SimtParams p) {
       rb[i] = (rv && cB + lc < dB) ? XB[row * ldB + cB + lc] : 0.0;
     }
   };
-  auto sstore = [&]() {
+  auto sstore = [&](int buf) {
 #pragma unroll
     for (int i = 0; i < KC / 4; ++i) {
-      As[lr + 4 * i][lc] = ra[i];
-      Bs[lr + 4 * i][lc] = rb[i];
+      As[buf][lr + 4 * i][lc] = ra[i];
+      Bs[buf][lr + 4 * i][lc] = rb[i];
     }
   };
   gload(r0);
-  sstore();
+  sstore(0);
   __syncthreads();
-  for (int64_t r = r0; r < r1; r += KC) {
+  int buf = 0;
+  for (int64_t r = r0; r < r1; r += KC, buf ^= 1) {
     const bool more = r + KC < r1;
     if (more) gload(r + KC);
 #pragma unroll
     for (int k0 = 0; k0 < KC; k0 += 4) {
       double a[4], b[2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[k0 + tq][wm + 8 * i + gq];   // A[m][k] = X[k][m]
+      for (int i = 0; i < 4; ++i) a[i] = As[buf][k0 + tq][wm + 8 * i + gq];   // A[m][k] = X[k][m]
 #pragma unroll
-      for (int j = 0; j < 2; ++j) b[j] = Bs[k0 + tq][wn + 8 * j + gq];   // B[k][n] = X[k][n]
+      for (int j = 0; j < 2; ++j) b[j] = Bs[buf][k0 + tq][wn + 8 * j + gq];   // B[k][n] = X[k][n]
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -1210,13 +1211,10 @@ __global__ void __launch_bounds__(256) moments_dmma_kernel(const SimtParams p) {
     }
     if (bi == bj && threadIdx.x < 64) {
 #pragma unroll
-      for (int k = 0; k < KC; ++k) csum += Bs[k][threadIdx.x];
+      for (int k = 0; k < KC; ++k) csum += Bs[buf][k][threadIdx.x];
     }
+    if (more) sstore(buf ^ 1);   // the other buffer was last read before the previous barrier
     __syncthreads();
-    if (more) {
-      sstore();
-      __syncthreads();
-    }
   }
   double* P = static_cast<double*>(p.partial) + (size_t)split * p.Dp * p.Dp;
 #pragma unroll
