@@ -293,8 +293,10 @@ int ccab_frobenius_norm(int dtype, int m, int n, const void* A, int64_t lda, voi
 int ccab_profile_moments(int enable);
 double ccab_profile_moments_last_ms(void);
 
-/* Debug/tuning knobs of the tcgen05 kernel ("lbo_bytes", "sbo_bytes", "tma_dtype", "force_splits");
- * value < 0 restores the default.  Not part of the stable surface. */
+/* Debug/tuning knobs ("lbo_bytes", "sbo_bytes", "tma_dtype", "force_splits", "tc_variant", "tc_kc", "x3_split",
+ * "x3b_oneshot" = 1: one (tile, split) unit per CTA pair instead of the persistent moment kernel, "f64_simt",
+ * "gemm_force_fma", "gemm_split" = 0: never split thin float32 products over k, "jacobi_inner_sweeps",
+ * "jacobi_force_unfused"); value < 0 restores the default.  Not part of the stable surface. */
 int ccab_debug_set(const char* key, int value);
 
 #ifdef __cplusplus
