@@ -21,6 +21,6 @@ fake_ops.install(mp)
 FILES = ["tests/test_linear_gpu.py", "tests/test_ext_gpu.py", "tests/test_zz_center_gpu.py"]
 # tests that move tensors to the GPU themselves or time device paths cannot run on the stand-in
 SKIP = ("accepts_cuda_and_cpu_tensors or batches_tensors or device_score_path or partial_fit_and_streamed or pickle "
-        "or float32_precisions or edge_shapes")
+        "or float32_precisions or edge_shapes or transform_on_the_device")
 sys.exit(pytest.main([f for f in FILES if os.path.exists(f)] + ["-m", "gpu", "-q", "-k", f"not ({SKIP})", "-p",
                                                                  "no:cacheprovider"] + sys.argv[1:]))
