@@ -87,6 +87,75 @@ def _wide_views(n=3000, dims=(300, 280), k=6, seed=3, dtype=np.float64):
     return [(z @ rng.standard_normal((k, d)) * 0.4 + rng.standard_normal((n, d))).astype(dtype) for d in dims]
 
 
+def test_device_fit_status_word_drives_retry_fallback_and_errors(host, monkeypatch):
+    """The device-side fit reports through the header of its result block (csrc/fit.cu, include/ccab200.h): 'not
+    converged' is answered by ONE more call with the larger iteration count, every other failure bit by the
+    host-assembled routes, non-finite input by the reference's ValueError; ``weights_`` always match the oracle."""
+    from cca_zoo_b200 import ops
+    from cca_zoo_b200.linear import rCCA
+
+    views = _wide_views()
+    w_ref, _ = R.ref_rcca_fit(views, 4, 0.2)
+    real = ops.rcca_fit
+    seen = []
+
+    def flaky(mom, dims, n_host, n_dev, center, c, k, p, iters, dtype):
+        seen.append(iters)
+        block, offsets = real(mom, dims, n_host, n_dev, center, c, k, p, iters, dtype)
+        if len(seen) == 1:                                   # first attempt: pretend the tolerance was missed
+            block.numpy()[:8].view(np.float64)[0] = ops.FIT_NOT_CONVERGED
+        return block, offsets
+
+    monkeypatch.setattr(ops, "rcca_fit", flaky)
+    est = rCCA(latent_dimensions=4, c=0.2).fit(views)
+    assert len(seen) == 2 and seen[1] > seen[0], seen
+    assert est._fit_info["route"] == "device" and est._fit_info["iters"] == seen[1]
+    assert R.max_rel_err_per_vector(est.weights_, w_ref) < 1e-8
+
+    def declined(bit):
+        def f(mom, dims, n_host, n_dev, center, c, k, p, iters, dtype):
+            seen.append(iters)
+            block, offsets = real(mom, dims, n_host, n_dev, center, c, k, p, iters, dtype)
+            block.numpy()[:8].view(np.float64)[0] = bit
+            return block, offsets
+        return f
+
+    for bit in (ops.FIT_NOT_POSITIVE_DEFINITE, ops.FIT_TOO_FEW_SAMPLES, ops.FIT_NOT_POSITIVE_DEFINITE | ops.FIT_NOT_CONVERGED):
+        seen.clear()
+        monkeypatch.setattr(ops, "rcca_fit", declined(bit))
+        est = rCCA(latent_dimensions=4, c=0.2).fit(views)
+        assert len(seen) == 1, "only a missed tolerance is worth a second device attempt"
+        assert est._fit_info == {"route": "host", "device_status": bit}
+        assert R.max_rel_err_per_vector(est.weights_, w_ref) < 1e-8
+        assert est.n_samples_ == views[0].shape[0]
+
+    monkeypatch.setattr(ops, "rcca_fit", declined(ops.FIT_NON_FINITE))
+    with pytest.raises(ValueError, match="NaN or infinity"):
+        rCCA(latent_dimensions=4, c=0.2).fit(views)
+
+
+def test_device_fit_plan_limits(host, monkeypatch):
+    """When the one-call fit is taken (csrc/fit.cu needs p <= 128 for its single-CTA Ritz solve and 4k <= min d_i) and
+    how the block width / first-try iteration count are chosen; the environment knobs are for experiments only."""
+    from cca_zoo_b200.linear import MCCA, rCCA
+
+    f32 = torch.float32
+    plan = rCCA(latent_dimensions=64, c=0.1)._device_fit_plan([1024, 1024], 100000, f32)
+    assert plan is not None and plan["k"] == 64 and plan["iters"] == [6, 20]
+    assert rCCA(latent_dimensions=64, c=0.1, solver="eigen")._device_fit_plan([1024, 1024], 100000, f32) is None
+    assert rCCA(latent_dimensions=64, c=0.1)._device_fit_plan([200, 1024], 100000, f32) is None      # narrow view
+    assert rCCA(latent_dimensions=64, c=0.1)._device_fit_plan([1024, 1024], 900, f32) is None        # n <= d
+    assert rCCA(latent_dimensions=120, c=0.1)._device_fit_plan([1024, 1024], 100000, f32) is None    # p would exceed 128
+    assert rCCA(latent_dimensions=300, c=0.1)._device_fit_plan([1024, 1024], 100000, f32) is None    # 4k > min d
+    monkeypatch.setenv("CCAB_FIT_OVERSAMPLE", "32")
+    monkeypatch.setenv("CCAB_FIT_ITERS", "5")
+    assert rCCA(latent_dimensions=64, c=0.1)._device_fit_plan([1024, 1024], 100000, f32)["iters"] == [5, 20]
+    monkeypatch.delenv("CCAB_FIT_OVERSAMPLE")
+    monkeypatch.delenv("CCAB_FIT_ITERS")
+    assert MCCA(latent_dimensions=32, c=0.1)._device_fit_plan([512] * 4, 125000, f32) is not None
+    assert MCCA(latent_dimensions=32, c=0.95)._device_fit_plan([512] * 4, 125000, f32) is None       # shift needs c <= 0.9
+
+
 def test_cholesky_and_eigen_routes_agree_on_wide_views(host):
     """min(dims) >= 256 and n > max(dims): ``auto`` takes the device-side fit (one library call); when that is not
     available the host-assembled Cholesky + subspace-iteration route; both agree with the eigen route."""
