@@ -134,6 +134,44 @@ def test_device_fit_status_word_drives_retry_fallback_and_errors(host, monkeypat
         rCCA(latent_dimensions=4, c=0.2).fit(views)
 
 
+def test_parameter_validation_runs_once_per_parameter_set(host, monkeypatch):
+    """sklearn's validation is a function of the constructor parameters alone: a re-fit with unchanged parameters skips
+    it (pure host time in front of the first kernel), any change -- rebinding or in-place mutation -- repeats it, and an
+    invalid value still raises at fit time as in the reference (cca_zoo/_base.py:88)."""
+    from sklearn.base import BaseEstimator, clone
+    from sklearn.utils._param_validation import InvalidParameterError
+
+    from cca_zoo_b200.linear import rCCA
+
+    calls = {"n": 0}
+    real = BaseEstimator._validate_params
+
+    def spy(self):
+        calls["n"] += 1
+        return real(self)
+
+    monkeypatch.setattr(BaseEstimator, "_validate_params", spy)
+    rng = np.random.default_rng(0)
+    views = [rng.standard_normal((200, 10)), rng.standard_normal((200, 8))]
+    est = rCCA(latent_dimensions=2, c=[0.1, 0.2])
+    est.fit(views)
+    est.fit(views)
+    assert calls["n"] == 1
+    est.c[0] = 0.3                                   # in-place mutation of a list parameter
+    est.fit(views)
+    assert calls["n"] == 2
+    est.latent_dimensions = 0
+    with pytest.raises(InvalidParameterError):
+        est.fit(views)
+    assert calls["n"] == 3
+    est.latent_dimensions = 2                        # back to the last set that passed: nothing to re-check
+    est.fit(views)
+    assert calls["n"] == 3
+    assert not hasattr(clone(est), "_validated_params_")      # a clone validates for itself
+    clone(est).fit(views)
+    assert calls["n"] == 4
+
+
 def test_device_fit_plan_limits(host, monkeypatch):
     """When the one-call fit is taken (csrc/fit.cu needs p <= 128 for its single-CTA Ritz solve and 4k <= min d_i) and
     how the block width / first-try iteration count are chosen; the environment knobs are for experiments only."""
